@@ -1,0 +1,146 @@
+"""File formats at the drop-in boundary: FASTA/FASTQ(.gz) reads, .fai,
+jellyfish.db, kmer.loc, .sunkpos, .rlen, BED.  Host-side plumbing only -- no compute here.
+
+The FASTA/FASTQ reader mirrors the `readfq` port the reference's Nim tools use
+(workflow/src/kmerpos_annot3.nim:85, workflow/src/rlen.nim:13; behaviour pinned by probe B.8 /
+tests/golden/rlen_b8.json.gz): the record name ends at the first space or tab, multi-line
+sequences are concatenated, blank lines are ignored, a trailing CR is stripped, internal
+spaces are kept as sequence characters, empty records are emitted, FASTA and FASTQ records may
+be mixed in one file.
+"""
+from __future__ import annotations
+
+import gzip
+import io
+import os
+from typing import Iterable, Iterator, List, Tuple
+
+import numpy as np
+
+
+def open_maybe_gz(path: str):
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b":
+        return gzip.open(path, "rb")
+    return open(path, "rb")
+
+
+def iter_fastx(fp) -> Iterator[Tuple[str, bytes]]:
+    """Heng Li's readfq state machine over a binary line iterator."""
+    last = None
+    it = iter(fp)
+    while True:
+        if last is None:
+            for l in it:
+                if l[:1] in (b">", b"@"):
+                    last = l.rstrip(b"\r\n")
+                    break
+            if last is None:
+                return
+        hdr = last[1:]
+        # name = up to first whitespace
+        name = hdr.split(None, 1)[0] if hdr.strip() else b""
+        if hdr[:1] in (b" ", b"\t"):
+            name = b""
+        seqs: List[bytes] = []
+        last = None
+        for l in it:
+            if l[:1] in (b"@", b"+", b">"):
+                last = l.rstrip(b"\r\n")
+                break
+            seqs.append(l.rstrip(b"\r\n"))
+        seq = b"".join(seqs)
+        if last is None or last[:1] != b"+":
+            yield name.decode("latin-1"), seq
+            if last is None:
+                return
+        else:  # FASTQ: skip quality lines
+            qlen = 0
+            last = None
+            for l in it:
+                qlen += len(l.rstrip(b"\r\n"))
+                if qlen >= len(seq):
+                    break
+            yield name.decode("latin-1"), seq
+            # (truncated quality: record still yielded, as readfq does)
+
+
+def read_fastx(path_or_bytes) -> List[Tuple[str, bytes]]:
+    if isinstance(path_or_bytes, (bytes, bytearray)):
+        data = bytes(path_or_bytes)
+        if data[:2] == b"\x1f\x8b":
+            data = gzip.decompress(data)
+        return list(iter_fastx(io.BytesIO(data)))
+    with open_maybe_gz(path_or_bytes) as f:
+        return list(iter_fastx(f))
+
+
+def pack_reads(reads: Iterable[Tuple[str, bytes]]):
+    """-> (names, seq uint8[total], off uint64[n+1])"""
+    names, parts, lens = [], [], []
+    for n, s in reads:
+        names.append(n)
+        parts.append(s)
+        lens.append(len(s))
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    if lens:
+        off[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64))
+    seq = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    return names, seq, off
+
+
+def read_fai(path: str) -> List[Tuple[str, int]]:
+    out = []
+    with open(path) as f:
+        for l in f:
+            p = l.rstrip("\n").split("\t")
+            if len(p) >= 2:
+                out.append((p[0], int(p[1])))
+    return out
+
+
+def read_db(path: str) -> List[str]:
+    with open(path) as f:
+        return [l.rstrip("\n") for l in f if l.rstrip("\n") != ""]
+
+
+def read_loc(path: str):
+    """kmer.loc: contig \t start0 \t kmer \t group_start  (defineSUNKs.smk:126)"""
+    contig, start, kmer, group = [], [], [], []
+    with open(path) as f:
+        for l in f:
+            p = l.rstrip("\n").split("\t")
+            if len(p) < 4:
+                continue
+            contig.append(p[0])
+            start.append(int(p[1]))
+            kmer.append(p[2])
+            group.append(int(p[3]))
+    return contig, start, kmer, group
+
+
+def read_sunkpos(path_or_text):
+    """rows (read, pos, contig, start, group)"""
+    if os.path.exists(path_or_text) if isinstance(path_or_text, str) and "\t" not in path_or_text else False:
+        with open_maybe_gz(path_or_text) as f:
+            text = f.read().decode()
+    else:
+        text = path_or_text
+    rows = []
+    for l in text.splitlines():
+        p = l.split("\t")
+        if len(p) < 5:
+            continue
+        rows.append((p[0], int(p[1]), p[2], int(p[3]), int(p[4])))
+    return rows
+
+
+def format_sunkpos(rows) -> str:
+    return "".join(f"{r[0]}\t{r[1]}\t{r[2]}\t{r[3]}\t{r[4]}\n" for r in rows)
+
+
+def write_bed(path: str, rows):
+    with open(path, "w") as f:
+        for r in rows:
+            f.write("\t".join(str(x) for x in r) + "\n")

@@ -1,0 +1,69 @@
+"""Oracle (oracle/gavisunk_oracle.py) pinned against the outputs of the reference's own ELF
+binaries recorded in tests/golden/*.json.gz (made by tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+import gavisunk_oracle as O
+from gavisunk_b200 import io as gio
+from conftest import load_golden
+
+
+def _parse_db_loc(case):
+    db = [O.encode(l) for l in case["db"].splitlines() if l]
+    loc = []
+    for l in case["loc"].splitlines():
+        c, s, km, g = l.split("\t")
+        loc.append((c, int(s), O.encode(km), int(g)))
+    return db, loc
+
+
+@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes"])
+def test_match_kats(name):
+    case = load_golden(name)
+    db, loc = _parse_db_loc(case)
+    reads = gio.read_fastx(case["reads"].encode("latin-1"))
+    rows = O.match_chunk(reads, db, loc, case["k"])
+    assert gio.format_sunkpos(rows) == case["out"]
+
+
+def test_b1_expected_rows():
+    # SURVEY Appendix B.1 literal expectation
+    case = load_golden("kat_b1")
+    got = [tuple(l.split("\t")) for l in case["out"].splitlines()]
+    assert got == [("r1", "2", "c1", "100", "100"), ("r1", "7", "c1", "200", "200"), ("r2", "5", "c1", "100", "100"),
+                   ("r3", "2", "c1", "200", "200"), ("r3", "7", "c1", "101", "100"), ("r4", "7", "c1", "200", "200"),
+                   ("r4", "14", "c1", "100", "100")]
+
+
+def test_rlen_b8():
+    case = load_golden("rlen_b8")
+    reads = gio.read_fastx(case["reads"].encode("latin-1"))
+    assert "".join(f"{n}\t{len(s)}\n" for n, s in reads) == case["rlen"]
+
+
+@pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many"])
+def test_match_and_diag_random(name):
+    case = load_golden(name)
+    db, loc = _parse_db_loc(case)
+    for ch in case["chunks"]:
+        reads = gio.read_fastx(ch["reads"].encode("latin-1"))
+        assert "".join(f"{n}\t{len(s)}\n" for n, s in reads) == ch["rlen"]
+        rows = O.match_chunk(reads, db, loc, case["k"])
+        assert gio.format_sunkpos(rows) == ch["sunkpos"]
+        fai = case["fai1"] if ch["hap"] == 1 else case["fai2"]
+        contigs = {l.split("\t")[0] for l in fai.splitlines()}
+        diag = O.diag_filter_v3(rows, contigs)
+        assert "".join("\t".join(str(x) for x in d) + "\n" for d in diag) == ch["diag"]
+        kept = O.diag_filter_step2(rows, diag)
+        assert gio.format_sunkpos(kept) == ch["diag2"]
+
+
+def test_diag_cases():
+    for case in load_golden("diag_cases"):
+        rows = gio.read_sunkpos(case["sunkpos"])
+        contigs = {l.split("\t")[0] for l in case["fai"].splitlines()}
+        diag = O.diag_filter_v3(rows, contigs)
+        got = "".join("\t".join(str(x) for x in d) + "\n" for d in diag)
+        assert got == case["diag"], case["name"]
+        kept = O.diag_filter_step2(rows, diag)
+        assert gio.format_sunkpos(kept) == case["diag2"], case["name"]
