@@ -1,0 +1,84 @@
+"""ctypes binding of libgavisunk_b200.so (the C ABI declared in include/gavisunk_b200.h).
+
+There is no CPU fallback: if the shared library has not been built (``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C gavisunk_b200/csrc``) loading raises, and every
+compute entry point fails when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgavisunk_b200.so")
+
+u8p, u32p, u64p, i32p, i64p, f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_double))
+vp = C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/gavisunk_b200.h one to one
+PROTOTYPES = {
+    "gvs_create": (vp, [C.c_int, C.c_int]),
+    "gvs_destroy": (None, [vp]),
+    "gvs_last_error": (C.c_char_p, [vp]),
+    "gvs_version": (C.c_char_p, []),
+    "gvs_set_stream": (C.c_int, [vp, vp]),
+    "gvs_sync": (C.c_int, [vp]),
+    "gvs_set_profiling": (C.c_int, [vp, C.c_int]),
+    "gvs_stage_ms": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float)]),
+    "gvs_launch_count": (C.c_uint64, [vp]),
+    "gvs_db_load_loc": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64, C.c_uint32]),
+    "gvs_db_build": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_int]),
+    "gvs_db_size": (C.c_int, [vp, u64p, u64p]),
+    "gvs_db_export": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+    "gvs_reads_set": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_int]),
+    "gvs_match": (C.c_int, [vp, u64p]),
+    "gvs_rows_get": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
+    "gvs_diag_filter": (C.c_int, [vp, vp, vp, u64p, u64p]),
+    "gvs_best_get": (C.c_int, [vp, vp, vp, vp, vp]),
+    "gvs_group_hist": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "gvs_hist_mode": (C.c_int, [vp, i64p]),
+    "gvs_bad_groups": (C.c_int, [vp, i64p, u64p]),
+    "gvs_bad_get": (C.c_int, [vp, vp]),
+    "gvs_validate": (C.c_int, [vp, C.c_uint32, u64p]),
+    "gvs_pairs_get": (C.c_int, [vp, vp, vp, vp, vp]),
+    "gvs_components_local": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "gvs_components_merge": (C.c_int, [vp, vp]),
+    "gvs_intervals": (C.c_int, [vp, u64p]),
+    "gvs_intervals_get": (C.c_int, [vp, vp, vp, vp]),
+    "gvs_gaps": (C.c_int, [vp, vp, u64p, u64p]),
+    "gvs_gaps_get": (C.c_int, [vp, vp, vp, vp, vp]),
+    "gvs_covprob_table": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_double, C.c_double, vp]),
+    "gvs_synth_assembly": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_double, C.c_double, C.c_uint64]),
+    "gvs_synth_reads_plan": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_double, C.c_double,
+                                       C.c_uint32, C.c_uint32, C.c_uint64, vp, u64p]),
+    "gvs_synth_reads_fill": (C.c_int, [vp, vp, vp, vp, C.c_uint64]),
+}
+
+GVS_E_KEYERROR = -3
+STAGES = {"probe": 0, "emit": 1, "diag": 2, "hist": 3, "validate": 4, "intervals": 5, "dbbuild": 6}
+
+_lib = None
+
+
+class GavisunkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libgavisunk_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """Load the shared library (once) and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+            "g.build()').  gavisunk_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

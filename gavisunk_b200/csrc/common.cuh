@@ -1,0 +1,363 @@
+// common.cuh -- context, device-buffer arena, error handling and the device-wide scan primitive
+// shared by every stage of libgavisunk_b200.so.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gavisunk_b200.h"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
+typedef int64_t i64;
+
+#define GVS_NSM_DEFAULT 148
+
+// grow-only device buffer: stages re-use their scratch across calls so that the timed loop of
+// bench.py never allocates after the first (warm-up) step.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T>
+  T* as() const { return (T*)p; }
+};
+
+struct Rows {  // sunkpos rows, structure of arrays (24 B per row)
+  DevBuf read, pos, contig, start, group, gidx;
+  u64 n = 0;
+};
+
+struct gvs_ctx {
+  int device = 0;
+  int k = 20;
+  int n_sm = GVS_NSM_DEFAULT;
+  cudaStream_t stream = 0;
+  std::string err;
+  u64 launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev0[GVS_ST_COUNT], ev1[GVS_ST_COUNT];
+  bool ev_valid[GVS_ST_COUNT];
+  std::vector<void*> pinned;  // small pinned host staging blocks
+
+  // ---- database ----
+  bool db_ready = false;
+  u64 n_loc = 0, n_groups = 0;
+  u32 n_contigs = 0;
+  DevBuf loc_kmer, loc_contig, loc_start, loc_group, loc_gidx;  // per .loc row
+  DevBuf grp_contig, grp_start;                                  // per group (index = gidx)
+  DevBuf tab_keys, tab_rows;                                     // open-addressed probe table
+  u64 tab_slots = 0;                                             // power of two, buckets of 4
+  DevBuf filt;                                                   // 64-bit-word blocked Bloom filter
+  u64 filt_words = 0;                                            // power of two
+  DevBuf contig_hap, contig_hash, contig_len;
+
+  // ---- reads ----
+  bool reads_ready = false;
+  const u8* seq = nullptr;     // device
+  const u64* read_off = nullptr;  // device, n_reads+1
+  u64 n_reads = 0, total_bases = 0;
+  DevBuf own_seq, own_off;     // when copied from the host
+  DevBuf chunk_first, chunk_hap;  // device copies
+  std::vector<u64> h_chunk_first;
+  std::vector<u8> h_chunk_hap;
+  u32 n_chunks = 0;
+
+  // ---- match ----
+  DevBuf tile_first, tile_cnt, tile_off, tile_dst;
+  DevBuf hit_read, hit_w, hit_row;     // unordered (per-tile allocated)
+  DevBuf ohit_read, ohit_w, ohit_row;  // ordered
+  u64 hit_cap = 0, n_hits = 0;
+  DevBuf counters;                     // small block of device counters / flags
+  DevBuf scan_tmp, scan_tmp2, flags_a, flags_b, flags_c;
+  Rows rows;                           // gvs_match output
+  bool match_ready = false;
+
+  // ---- diag ----
+  DevBuf seg_start;     // per segment (read with rows): first row, n_seg+1
+  u64 n_seg = 0;
+  DevBuf seg_ndist, seg_cap, seg_best, seg_good, seg_dir;
+  DevBuf diag_scratch;
+  Rows kept;
+  DevBuf best_read, best_contig, best_good, best_dir;
+  u64 n_best = 0;
+  bool diag_ready = false;
+
+  // ---- histogram / bad groups ----
+  DevBuf hist, cnt_hist, bad_flag, bad_list;
+  u64 n_bad = 0;
+  bool hist_ready = false, bad_ready = false;
+
+  // ---- validation ----
+  DevBuf kseg_start;  // segments of kept rows
+  u64 n_kseg = 0;
+  DevBuf val_scratch, val_cnt, val_off;
+  DevBuf pair_read, pair_contig, pair_group, pair_gidx;
+  u64 n_pairs = 0;
+  bool val_ready = false;
+
+  // ---- components / intervals / gaps ----
+  DevBuf parent, present, comp_min, comp_max, comp_cnt;
+  DevBuf iv_contig, iv_start, iv_end;
+  u64 n_iv = 0;
+  DevBuf gap_contig, gap_start, gap_end, nodata_contig;
+  u64 n_gaps = 0, n_nodata = 0;
+  bool comp_ready = false, iv_ready = false, gaps_ready = false;
+};
+
+// -------------------------------------------------------------------------------------------
+// error handling
+// -------------------------------------------------------------------------------------------
+static inline int gvs_fail(gvs_ctx* c, int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
+#include <stdarg.h>
+static inline int gvs_fail(gvs_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return gvs_fail(ctx, GVS_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,           \
+                      cudaGetErrorString(e__));                                             \
+  } while (0)
+
+#define CKR(call)            \
+  do {                       \
+    int r__ = (call);        \
+    if (r__ != 0) return r__; \
+  } while (0)
+
+// kernel launch with launch counting + error check
+#define LAUNCH(kern, grid, block, smem, ...)                                                \
+  do {                                                                                      \
+    kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                            \
+    ctx->launches++;                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                 \
+      return gvs_fail(ctx, GVS_E_CUDA, "%s:%d launch %s: %s", __FILE__, __LINE__, #kern,    \
+                      cudaGetErrorString(e__));                                             \
+  } while (0)
+
+static inline int gvs_reserve(gvs_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (b.cap >= bytes) return 0;
+  // stream-ordered work may still use the old block: wait before freeing
+  if (b.p) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 8 + 256;  // slack so that slightly larger batches do not realloc
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return gvs_fail(ctx, GVS_E_NOMEM, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
+  }
+  b.cap = want;
+  return 0;
+}
+
+static inline void gvs_release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+struct StageTimer {
+  gvs_ctx* c;
+  int st;
+  StageTimer(gvs_ctx* c_, int st_) : c(c_), st(st_) {
+    if (c->profiling) cudaEventRecord(c->ev0[st], c->stream);
+  }
+  ~StageTimer() {
+    if (c->profiling) {
+      cudaEventRecord(c->ev1[st], c->stream);
+      c->ev_valid[st] = true;
+    }
+  }
+};
+
+static inline u64 next_pow2(u64 x) {
+  u64 p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+static inline u64 cdiv(u64 a, u64 b) { return (a + b - 1) / b; }
+
+// -------------------------------------------------------------------------------------------
+// hashing shared by table build and probe
+// -------------------------------------------------------------------------------------------
+#define GVS_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define GVS_ROW_MISSING 0xFFFFFFFFu  // db k-mer without a .loc row (reference: KeyError)
+#define GVS_ROW_NOTINDB 0xFFFFFFFEu  // .loc k-mer that is not in the db set (never a hit)
+
+__host__ __device__ __forceinline__ u64 gvs_mix(u64 x) {
+  x *= 0x9E3779B97F4A7C15ull;
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 32;
+  return x;
+}
+// filter: word index from the low bits, two bit positions from a re-mix of the high half
+__host__ __device__ __forceinline__ u64 gvs_filt_word(u64 h, u64 filt_words) { return h & (filt_words - 1); }
+__host__ __device__ __forceinline__ u64 gvs_filt_bits(u64 h) {
+  u32 g = (u32)(h >> 32) * 0x85EBCA6Bu;
+  return (1ull << (g >> 26)) | (1ull << ((g >> 20) & 63));
+}
+// table: bucket (4 slots = one 32-byte sector of keys) from bits 24.. of the hash
+__host__ __device__ __forceinline__ u64 gvs_tab_bucket(u64 h, u64 tab_slots) { return (h >> 24) & ((tab_slots >> 2) - 1); }
+
+// -------------------------------------------------------------------------------------------
+// device-wide exclusive scan (3 launches: tile reduce, scan of tile sums, tile scan + write)
+// The input is produced by a functor so that flag arrays never have to be materialised.
+// -------------------------------------------------------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+struct OpSum {
+  template <typename T>
+  __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
+  template <typename T>
+  __device__ __forceinline__ T identity() const { return (T)0; }
+};
+struct OpMax {
+  template <typename T>
+  __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; }
+  template <typename T>
+  __device__ __forceinline__ T identity() const { return (T)0; }  // unsigned inputs only
+};
+
+template <typename T, typename Op>
+__device__ __forceinline__ T warp_incl_scan(T v, Op op) {
+  int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+    if (lane >= d) v = op(o, v);
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
+template <typename T, typename Op>
+__device__ __forceinline__ T block_excl_scan(T v, Op op, T* total, T* smem /* >= 33 entries */) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  T inc = warp_incl_scan(v, op);
+  if (lane == 31) smem[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    T w = (lane < nw) ? smem[lane] : op.template identity<T>();
+    T winc = warp_incl_scan(w, op);
+    smem[lane] = winc;  // inclusive per-warp sums
+  }
+  __syncthreads();
+  T wprefix = (wid == 0) ? op.template identity<T>() : smem[wid - 1];
+  T tot = smem[nw - 1];
+  T excl_in_warp = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+  if (lane == 0) excl_in_warp = op.template identity<T>();
+  __syncthreads();
+  if (total) *total = tot;
+  return op(wprefix, excl_in_warp);
+}
+
+template <typename T, typename Op, typename F>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(F f, u64 n, T* tile_sums, Op op) {
+  __shared__ T sm[33];
+  u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+  T acc = op.template identity<T>();
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    u64 j = base + i;
+    if (j < n) acc = op(acc, f(j));
+  }
+  T tot;
+  block_excl_scan(acc, op, &tot, sm);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+template <typename T, typename Op>
+__global__ void __launch_bounds__(1024) k_scan_sums(T* tile_sums, u64 n_tiles, T* total_out, Op op) {
+  __shared__ T sm[33];
+  __shared__ T carry_s;
+  if (threadIdx.x == 0) carry_s = op.template identity<T>();
+  __syncthreads();
+  for (u64 base = 0; base < n_tiles; base += 1024) {
+    u64 j = base + threadIdx.x;
+    T v = (j < n_tiles) ? tile_sums[j] : op.template identity<T>();
+    T tot;
+    T ex = block_excl_scan(v, op, &tot, sm);
+    T carry = carry_s;
+    if (j < n_tiles) tile_sums[j] = op(carry, ex);
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = op(carry, tot);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+
+template <typename T, typename Op, typename F, typename G>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(F f, G g, u64 n, const T* tile_sums, Op op) {
+  __shared__ T sm[33];
+  u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+  T v[SCAN_ITEMS];
+  T acc = op.template identity<T>();
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    u64 j = base + i;
+    v[i] = (j < n) ? f(j) : op.template identity<T>();
+    acc = op(acc, v[i]);
+  }
+  T ex = block_excl_scan(acc, op, (T*)nullptr, sm);
+  T run = op(tile_sums[blockIdx.x], ex);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    u64 j = base + i;
+    if (j < n) g(j, run, v[i]);  // g(index, exclusive prefix, own value)
+    run = op(run, v[i]);
+  }
+}
+
+// exclusive scan: out via g(j, excl, v).  total_dev (may be null) receives the grand total.
+template <typename T, typename Op, typename F, typename G>
+static int device_scan(gvs_ctx* ctx, u64 n, F f, G g, Op op, T* total_dev) {
+  u64 n_tiles = cdiv(n, SCAN_TILE);
+  if (n_tiles == 0) n_tiles = 1;
+  CKR(gvs_reserve(ctx, ctx->scan_tmp, n_tiles * sizeof(T)));
+  T* sums = ctx->scan_tmp.as<T>();
+  LAUNCH((k_scan_reduce<T, Op, F>), (unsigned)n_tiles, SCAN_THREADS, 0, f, n, sums, op);
+  LAUNCH((k_scan_sums<T, Op>), 1, 1024, 0, sums, n_tiles, total_dev, op);
+  LAUNCH((k_scan_apply<T, Op, F, G>), (unsigned)n_tiles, SCAN_THREADS, 0, f, g, n, sums, op);
+  return 0;
+}
+
+// small helpers to read device scalars (synchronises the stream)
+template <typename T>
+static int read_dev(gvs_ctx* ctx, const T* d, T* h, size_t n = 1) {
+  CK(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+template <typename T>
+static int to_dev(gvs_ctx* ctx, DevBuf& b, const T* h, size_t n) {
+  CKR(gvs_reserve(ctx, b, n * sizeof(T)));
+  if (n) CK(cudaMemcpyAsync(b.p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+// stage entry points implemented in the other translation units
+int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db);  // table.cu

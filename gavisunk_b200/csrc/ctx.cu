@@ -1,0 +1,129 @@
+// ctx.cu -- context life cycle, stream / profiling control, read-batch registration.
+#include "common.cuh"
+
+extern "C" const char* gvs_version(void) { return "gavisunk_b200 0.1 (sm_100a)"; }
+
+extern "C" gvs_ctx* gvs_create(int device, int k) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return nullptr;  // no CPU fallback
+  if (k < 1 || k > 32) return nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  gvs_ctx* c = new gvs_ctx();
+  c->device = device;
+  c->k = k;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
+  for (int i = 0; i < GVS_ST_COUNT; i++) {
+    cudaEventCreate(&c->ev0[i]);
+    cudaEventCreate(&c->ev1[i]);
+    c->ev_valid[i] = false;
+  }
+  if (gvs_reserve(c, c->counters, 64 * sizeof(u64)) != 0) {
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+static void release_rows(Rows& r) {
+  gvs_release(r.read); gvs_release(r.pos); gvs_release(r.contig);
+  gvs_release(r.start); gvs_release(r.group); gvs_release(r.gidx);
+}
+
+extern "C" void gvs_destroy(gvs_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* all[] = {&c->loc_kmer, &c->loc_contig, &c->loc_start, &c->loc_group, &c->loc_gidx, &c->grp_contig,
+                   &c->grp_start, &c->tab_keys, &c->tab_rows, &c->filt, &c->contig_hap, &c->contig_hash,
+                   &c->contig_len, &c->own_seq, &c->own_off, &c->chunk_first, &c->chunk_hap, &c->tile_first,
+                   &c->tile_cnt, &c->tile_off, &c->tile_dst, &c->hit_read, &c->hit_w, &c->hit_row, &c->ohit_read,
+                   &c->ohit_w, &c->ohit_row, &c->counters, &c->scan_tmp, &c->scan_tmp2, &c->flags_a, &c->flags_b,
+                   &c->flags_c, &c->seg_start, &c->seg_ndist, &c->seg_cap, &c->seg_best, &c->seg_good, &c->seg_dir,
+                   &c->diag_scratch, &c->best_read, &c->best_contig, &c->best_good, &c->best_dir, &c->hist,
+                   &c->cnt_hist, &c->bad_flag, &c->bad_list, &c->kseg_start, &c->val_scratch, &c->val_cnt,
+                   &c->val_off, &c->pair_read, &c->pair_contig, &c->pair_group, &c->pair_gidx, &c->parent,
+                   &c->present, &c->comp_min, &c->comp_max, &c->comp_cnt, &c->iv_contig, &c->iv_start, &c->iv_end,
+                   &c->gap_contig, &c->gap_start, &c->gap_end, &c->nodata_contig};
+  for (DevBuf* b : all) gvs_release(*b);
+  release_rows(c->rows);
+  release_rows(c->kept);
+  for (int i = 0; i < GVS_ST_COUNT; i++) {
+    cudaEventDestroy(c->ev0[i]);
+    cudaEventDestroy(c->ev1[i]);
+  }
+  delete c;
+}
+
+extern "C" const char* gvs_last_error(gvs_ctx* c) { return c ? c->err.c_str() : "null context (no CUDA device?)"; }
+
+extern "C" int gvs_set_stream(gvs_ctx* ctx, void* s) {
+  if (!ctx) return GVS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = (cudaStream_t)s;
+  return 0;
+}
+
+extern "C" int gvs_sync(gvs_ctx* ctx) {
+  if (!ctx) return GVS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int gvs_set_profiling(gvs_ctx* ctx, int on) {
+  if (!ctx) return GVS_E_ARG;
+  ctx->profiling = on != 0;
+  for (int i = 0; i < GVS_ST_COUNT; i++) ctx->ev_valid[i] = false;
+  return 0;
+}
+
+extern "C" int gvs_stage_ms(gvs_ctx* ctx, int stage, float* ms) {
+  if (!ctx || stage < 0 || stage >= GVS_ST_COUNT || !ms) return GVS_E_ARG;
+  if (!ctx->ev_valid[stage]) return gvs_fail(ctx, GVS_E_STATE, "stage %d was not timed", stage);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->ev1[stage]));
+  CK(cudaEventElapsedTime(ms, ctx->ev0[stage], ctx->ev1[stage]));
+  return 0;
+}
+
+extern "C" uint64_t gvs_launch_count(gvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* read_off, uint64_t n_reads,
+                             const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks,
+                             int on_device) {
+  if (!ctx) return GVS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!read_off || !chunk_first || !chunk_hap || n_chunks == 0) return gvs_fail(ctx, GVS_E_ARG, "null read batch arrays");
+  if (n_reads >= 0xFFFFFFF0ull) return gvs_fail(ctx, GVS_E_OVERFLOW, "more than 2^32 reads in one batch");
+  ctx->reads_ready = false;
+  ctx->match_ready = ctx->diag_ready = ctx->val_ready = false;
+  if (chunk_first[0] != 0 || chunk_first[n_chunks] != n_reads) return gvs_fail(ctx, GVS_E_ARG, "chunk_first must span [0, n_reads]");
+  for (u32 c = 0; c < n_chunks; c++)
+    if (chunk_first[c] > chunk_first[c + 1]) return gvs_fail(ctx, GVS_E_ARG, "chunk_first not monotone");
+  ctx->h_chunk_first.assign(chunk_first, chunk_first + n_chunks + 1);
+  ctx->h_chunk_hap.assign(chunk_hap, chunk_hap + n_chunks);
+  ctx->n_chunks = n_chunks;
+  CKR(to_dev(ctx, ctx->chunk_first, chunk_first, (size_t)n_chunks + 1));
+  CKR(to_dev(ctx, ctx->chunk_hap, chunk_hap, (size_t)n_chunks));
+  u64 total = 0;
+  if (on_device) {
+    CKR(read_dev(ctx, read_off + n_reads, &total));
+    ctx->seq = seq;
+    ctx->read_off = read_off;
+  } else {
+    total = read_off[n_reads];
+    // 64 bytes of slack: the probe kernel stages 16-byte vectors and may touch the tail
+    CKR(gvs_reserve(ctx, ctx->own_seq, total + 64));
+    CKR(gvs_reserve(ctx, ctx->own_off, (n_reads + 1) * sizeof(u64)));
+    if (total) CK(cudaMemcpyAsync(ctx->own_seq.p, seq, total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->own_off.p, read_off, (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->seq = ctx->own_seq.as<u8>();
+    ctx->read_off = ctx->own_off.as<u64>();
+  }
+  ctx->n_reads = n_reads;
+  ctx->total_bases = total;
+  ctx->reads_ready = true;
+  return 0;
+}

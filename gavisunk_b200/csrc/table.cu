@@ -1,0 +1,216 @@
+// table.cu -- SUNK probe table + filter construction from .loc rows (kmerpos_annot3's table
+// load, workflow/src/kmerpos_annot3.nim:20-26,57-69) and database export.
+#include "table.cuh"
+
+// ---- kernels -------------------------------------------------------------------------------
+__global__ void k_fill_u64(u64* p, u64 n, u64 v) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_fill_u32(u32* p, u64 n, u32 v) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// .loc rows: later rows of the same k-mer win (nim:68 `coords[...] = curcoord`): slot value =
+// max(row index + 1)
+__global__ void k_tab_insert_loc(const u64* __restrict__ kmer, u64 n, u64* keys, u32* rows, u64 slots) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u64 key = kmer[i];
+    u64 s = tab_insert(keys, slots, key, gvs_mix(key));
+    atomicMax(&rows[s], (u32)(i + 1));
+  }
+}
+// db set membership (nim:20-26): bit 31 of the slot value
+__global__ void k_tab_mark_db(const u64* __restrict__ kmer, u64 n, u64* keys, u32* rows, u64 slots) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u64 key = kmer[i];
+    u64 s = tab_insert(keys, slots, key, gvs_mix(key));
+    atomicOr(&rows[s], 0x80000000u);
+  }
+}
+__global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slots, u64* filt, u64 filt_words) {
+  for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
+    u64 key = keys[s];
+    if (key == GVS_EMPTY_KEY) continue;
+    u32 v = rows[s];
+    u32 r = v & 0x7FFFFFFFu;
+    if (!(v >> 31)) {
+      rows[s] = GVS_ROW_NOTINDB;  // in .loc but not in the db set: `x in uniqueKmers` is false
+      continue;
+    }
+    rows[s] = r ? r - 1 : GVS_ROW_MISSING;
+    u64 h = gvs_mix(key);
+    atomicOr((unsigned long long*)&filt[gvs_filt_word(h, filt_words)], (unsigned long long)gvs_filt_bits(h));
+  }
+}
+
+// group identity (contig, group start) -> representative (first) row, through a scratch table
+__global__ void k_grp_insert(const u32* __restrict__ contig, const u32* __restrict__ group, u64 n, u64* keys,
+                             u32* minrow, u64 slots) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u64 key = ((u64)contig[i] << 32) | group[i];
+    u64 s = tab_insert(keys, slots, key, gvs_mix(key));
+    atomicMin(&minrow[s], (u32)i);
+  }
+}
+__global__ void k_grp_rep(const u32* __restrict__ contig, const u32* __restrict__ group, u64 n, u64* keys,
+                          const u32* __restrict__ minrow, u64 slots, u32* rep) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u64 key = ((u64)contig[i] << 32) | group[i];
+    u64 s = tab_insert(keys, slots, key, gvs_mix(key));
+    rep[i] = minrow[s];
+  }
+}
+__global__ void k_grp_fill(const u32* __restrict__ rep, const u32* __restrict__ dense_of_row, u64 n, u32* gidx,
+                           const u32* __restrict__ contig, const u32* __restrict__ group, u32* grp_contig,
+                           u32* grp_start) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u32 r = rep[i];
+    u32 g = dense_of_row[r];
+    gidx[i] = g;
+    if (r == i) {
+      grp_contig[g] = contig[i];
+      grp_start[g] = group[i];
+    }
+  }
+}
+
+static unsigned grid_for(gvs_ctx* ctx, u64 n, int block) {
+  u64 g = cdiv(n, block);
+  u64 cap = (u64)ctx->n_sm * 16;
+  if (g > cap) g = cap;
+  if (g == 0) g = 1;
+  return (unsigned)g;
+}
+
+// Build tab_keys/tab_rows/filt from ctx->loc_kmer (device) and a device array of db k-mers
+// (d_db_kmer == nullptr: the db set is exactly the .loc k-mers).
+int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
+  u64 n_loc = ctx->n_loc;
+  u64 nk = n_loc + (d_db_kmer ? n_db : 0);
+  u64 slots = next_pow2(nk * 2 < 1024 ? 1024 : nk * 2);
+  if (n_loc >= 0x7FFFFFF0ull) return gvs_fail(ctx, GVS_E_OVERFLOW, "more than 2^31 .loc rows");
+  ctx->tab_slots = slots;
+  CKR(gvs_reserve(ctx, ctx->tab_keys, slots * sizeof(u64)));
+  CKR(gvs_reserve(ctx, ctx->tab_rows, slots * sizeof(u32)));
+  // filter: ~32 bits per key, between 2^14 and 2^23 words (64 MiB: stays L2-resident on B200)
+  u64 fw = next_pow2(cdiv((n_loc ? n_loc : 1) * 32, 64));
+  if (fw < (1ull << 14)) fw = 1ull << 14;
+  if (fw > (1ull << 23)) fw = 1ull << 23;
+  ctx->filt_words = fw;
+  CKR(gvs_reserve(ctx, ctx->filt, fw * sizeof(u64)));
+  u64* keys = ctx->tab_keys.as<u64>();
+  u32* rows = ctx->tab_rows.as<u32>();
+  LAUNCH(k_fill_u64, grid_for(ctx, slots, 256), 256, 0, keys, slots, GVS_EMPTY_KEY);
+  LAUNCH(k_fill_u32, grid_for(ctx, slots, 256), 256, 0, rows, slots, 0u);
+  LAUNCH(k_fill_u64, grid_for(ctx, fw, 256), 256, 0, ctx->filt.as<u64>(), fw, 0ull);
+  if (n_loc) LAUNCH(k_tab_insert_loc, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
+  if (d_db_kmer) {
+    if (n_db) LAUNCH(k_tab_mark_db, grid_for(ctx, n_db, 256), 256, 0, d_db_kmer, n_db, keys, rows, slots);
+  } else if (n_loc) {
+    LAUNCH(k_tab_mark_db, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
+  }
+  LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u64>(), fw);
+  return 0;
+}
+
+// dense group index by first appearance of (contig, group) in .loc row order
+static int build_group_index_body(gvs_ctx* ctx, DevBuf& gk, DevBuf& gm, DevBuf& rep, DevBuf& dense, u64 slots) {
+  u64 n = ctx->n_loc;
+  const u32* contig = ctx->loc_contig.as<u32>();
+  const u32* group = ctx->loc_group.as<u32>();
+  LAUNCH(k_fill_u64, grid_for(ctx, slots, 256), 256, 0, gk.as<u64>(), slots, GVS_EMPTY_KEY);
+  LAUNCH(k_fill_u32, grid_for(ctx, slots, 256), 256, 0, gm.as<u32>(), slots, 0xFFFFFFFFu);
+  LAUNCH(k_grp_insert, grid_for(ctx, n, 256), 256, 0, contig, group, n, gk.as<u64>(), gm.as<u32>(), slots);
+  LAUNCH(k_grp_rep, grid_for(ctx, n, 256), 256, 0, contig, group, n, gk.as<u64>(), gm.as<u32>(), slots, rep.as<u32>());
+  const u32* repp = rep.as<u32>();
+  u32* densep = dense.as<u32>();
+  u32* total = (u32*)ctx->counters.as<u64>();
+  auto f = [repp] __device__(u64 i) -> u32 { return repp[i] == (u32)i ? 1u : 0u; };
+  auto g = [densep] __device__(u64 i, u32 ex, u32 v) { densep[i] = ex; };
+  CKR((device_scan<u32>(ctx, n, f, g, OpSum(), total)));
+  u32 ng = 0;
+  CKR(read_dev(ctx, total, &ng));
+  ctx->n_groups = ng;
+  CKR(gvs_reserve(ctx, ctx->grp_contig, (u64)ng * sizeof(u32)));
+  CKR(gvs_reserve(ctx, ctx->grp_start, (u64)ng * sizeof(u32)));
+  LAUNCH(k_grp_fill, grid_for(ctx, n, 256), 256, 0, repp, densep, n, ctx->loc_gidx.as<u32>(), contig, group,
+         ctx->grp_contig.as<u32>(), ctx->grp_start.as<u32>());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static int build_group_index(gvs_ctx* ctx) {
+  u64 n = ctx->n_loc;
+  CKR(gvs_reserve(ctx, ctx->loc_gidx, n * sizeof(u32)));
+  CKR(gvs_reserve(ctx, ctx->counters, 64 * sizeof(u64)));
+  if (n == 0) {
+    ctx->n_groups = 0;
+    return 0;
+  }
+  u64 slots = next_pow2(n * 2 < 1024 ? 1024 : n * 2);
+  DevBuf gk, gm, rep, dense;
+  int rc = gvs_reserve(ctx, gk, slots * sizeof(u64));
+  if (!rc) rc = gvs_reserve(ctx, gm, slots * sizeof(u32));
+  if (!rc) rc = gvs_reserve(ctx, rep, n * sizeof(u32));
+  if (!rc) rc = gvs_reserve(ctx, dense, n * sizeof(u32));
+  if (!rc) rc = build_group_index_body(ctx, gk, gm, rep, dense, slots);
+  cudaStreamSynchronize(ctx->stream);
+  gvs_release(gk); gvs_release(gm); gvs_release(rep); gvs_release(dense);
+  return rc;
+}
+
+int gvs_group_index_impl(gvs_ctx* ctx) { return build_group_index(ctx); }
+
+// ---- C ABI ---------------------------------------------------------------------------------
+extern "C" int gvs_db_load_loc(gvs_ctx* ctx, const uint64_t* db_kmer, uint64_t n_db, const uint64_t* loc_kmer,
+                               const uint32_t* loc_contig, const uint32_t* loc_start, const uint32_t* loc_group,
+                               uint64_t n_loc, uint32_t n_contigs) {
+  if (!ctx) return GVS_E_ARG;
+  if (n_loc && (!loc_kmer || !loc_contig || !loc_start || !loc_group)) return gvs_fail(ctx, GVS_E_ARG, "null .loc column");
+  CK(cudaSetDevice(ctx->device));
+  ctx->db_ready = false;
+  ctx->n_loc = n_loc;
+  ctx->n_contigs = n_contigs;
+  CKR(to_dev(ctx, ctx->loc_kmer, loc_kmer, n_loc));
+  CKR(to_dev(ctx, ctx->loc_contig, loc_contig, n_loc));
+  CKR(to_dev(ctx, ctx->loc_start, loc_start, n_loc));
+  CKR(to_dev(ctx, ctx->loc_group, loc_group, n_loc));
+  DevBuf dbk;
+  int rc = 0;
+  if (db_kmer || n_db == 0) {
+    rc = to_dev(ctx, dbk, db_kmer, n_db);
+    if (!rc) rc = gvs_tab_build_impl(ctx, dbk.as<u64>(), n_db);
+  } else {
+    rc = gvs_fail(ctx, GVS_E_ARG, "null db_kmer with n_db > 0");
+  }
+  if (!rc) rc = build_group_index(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  gvs_release(dbk);
+  if (rc) return rc;
+  ctx->db_ready = true;
+  return 0;
+}
+
+extern "C" int gvs_db_size(gvs_ctx* ctx, uint64_t* n_sunks, uint64_t* n_groups) {
+  if (!ctx) return GVS_E_ARG;
+  if (!ctx->db_ready) return gvs_fail(ctx, GVS_E_STATE, "no database");
+  if (n_sunks) *n_sunks = ctx->n_loc;
+  if (n_groups) *n_groups = ctx->n_groups;
+  return 0;
+}
+
+extern "C" int gvs_db_export(gvs_ctx* ctx, uint64_t* kmer, uint32_t* contig, uint32_t* start, uint32_t* group,
+                             uint32_t* group_index) {
+  if (!ctx) return GVS_E_ARG;
+  if (!ctx->db_ready) return gvs_fail(ctx, GVS_E_STATE, "no database");
+  CK(cudaSetDevice(ctx->device));
+  u64 n = ctx->n_loc;
+  if (n == 0) return 0;
+  if (kmer) CK(cudaMemcpyAsync(kmer, ctx->loc_kmer.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (contig) CK(cudaMemcpyAsync(contig, ctx->loc_contig.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (start) CK(cudaMemcpyAsync(start, ctx->loc_start.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (group) CK(cudaMemcpyAsync(group, ctx->loc_group.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (group_index) CK(cudaMemcpyAsync(group_index, ctx->loc_gidx.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}

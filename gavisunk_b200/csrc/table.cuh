@@ -1,0 +1,59 @@
+// table.cuh -- device-side view of the SUNK probe structures (shared by build and probe kernels)
+//
+// Layout in HBM (DESIGN.md "Data layout"):
+//   filt      u64[filt_words]   word-blocked Bloom filter, 2 bits per key inside ONE 64-bit word;
+//                               sized to stay L2-resident (<= 64 MiB), probed once per read base
+//   tab_keys  u64[tab_slots]    open-addressed canonical k-mers, buckets of 4 slots = one 32-byte
+//                               sector, load factor <= 0.5, EMPTY = all ones (k <= 31 => < 2^62)
+//   tab_rows  u32[tab_slots]    .loc row of the key (or GVS_ROW_MISSING / GVS_ROW_NOTINDB);
+//                               touched only on a key match
+#pragma once
+#include "common.cuh"
+
+struct TabView {
+  const u64* __restrict__ filt;
+  u64 filt_words;
+  const u64* __restrict__ keys;
+  const u32* __restrict__ rows;
+  u64 slots;
+};
+
+#define GVS_NOHIT 0xFFFFFFFDu
+
+// exact lookup; returns row, GVS_ROW_MISSING, or GVS_NOHIT
+__device__ __forceinline__ u32 tab_lookup(const TabView& t, u64 key, u64 h) {
+  u64 nb = t.slots >> 2;
+  u64 b = gvs_tab_bucket(h, t.slots);
+  for (u64 it = 0; it < nb; it++) {
+    const ulonglong2* p = (const ulonglong2*)(t.keys + (b << 2));
+    ulonglong2 a = __ldg(p), c = __ldg(p + 1);
+    if (a.x == key) return __ldg(t.rows + (b << 2) + 0);
+    if (a.y == key) return __ldg(t.rows + (b << 2) + 1);
+    if (c.x == key) return __ldg(t.rows + (b << 2) + 2);
+    if (c.y == key) return __ldg(t.rows + (b << 2) + 3);
+    if (a.x == GVS_EMPTY_KEY || a.y == GVS_EMPTY_KEY || c.x == GVS_EMPTY_KEY || c.y == GVS_EMPTY_KEY)
+      return GVS_NOHIT;
+    b = (b + 1) & (nb - 1);
+  }
+  return GVS_NOHIT;
+}
+
+// find-or-insert; returns slot index (never fails while load < 1)
+__device__ __forceinline__ u64 tab_insert(u64* keys, u64 slots, u64 key, u64 h) {
+  u64 nb = slots >> 2;
+  u64 b = gvs_tab_bucket(h, slots);
+  for (;;) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      u64 s = (b << 2) + j;
+      u64 cur = keys[s];
+      if (cur == key) return s;
+      if (cur == GVS_EMPTY_KEY) {
+        u64 old = atomicCAS((unsigned long long*)&keys[s], (unsigned long long)GVS_EMPTY_KEY,
+                            (unsigned long long)key);
+        if (old == GVS_EMPTY_KEY || old == key) return s;
+      }
+    }
+    b = (b + 1) & (nb - 1);
+  }
+}

@@ -1,0 +1,335 @@
+"""Host-side driver of libgavisunk_b200.so: one Engine per GPU.
+
+The methods mirror the reference's stages one to one (names of the reference programs in the
+docstrings; file:line relative to the reference repository).  Everything here is plumbing --
+array marshalling, the scalar arithmetic the reference does in Python, name <-> index maps; all
+per-base / per-row work happens in the CUDA library.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import GavisunkError
+
+_LUT = np.zeros(256, dtype=np.uint64)
+for _ch, _v in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("U", 3)):
+    _LUT[ord(_ch)] = _v
+    _LUT[ord(_ch.lower())] = _v
+_LUT[1], _LUT[2], _LUT[3] = 1, 2, 3
+
+
+def encode_kmers(lines: Sequence[bytes], k: Optional[int] = None) -> np.ndarray:
+    """kmer.encode of every text k-mer (workflow/src/kmerpos_annot3.nim:24,68): 2-bit big-endian,
+    first base most significant.  Vectorised over equal-length k-mers."""
+    if len(lines) == 0:
+        return np.zeros(0, dtype=np.uint64)
+    if k is None:
+        k = len(lines[0])
+    if all(len(l) == k for l in lines):
+        a = np.frombuffer(b"".join(lines), dtype=np.uint8).reshape(len(lines), k)
+        codes = _LUT[a]
+        sh = (np.uint64(2) * np.arange(k - 1, -1, -1, dtype=np.uint64))
+        return np.bitwise_or.reduce(codes << sh, axis=1) if k else np.zeros(len(lines), dtype=np.uint64)
+    out = np.zeros(len(lines), dtype=np.uint64)
+    for i, l in enumerate(lines):  # ragged input: per line, wrapping like the reference's uint64
+        v = 0
+        for b in l:
+            v = ((v << 2) | int(_LUT[b])) & 0xFFFFFFFFFFFFFFFF
+        out[i] = v
+    return out
+
+
+def murmur3_32(data: bytes, seed: int = 0) -> int:
+    """MurmurHash3_x86_32 == Nim's `hash(string)` (workflow/src/diag_filter_v3.nim:54 Table keys)."""
+    c1, c2 = 0xCC9E2D51, 0x1B873593
+    h = seed & 0xFFFFFFFF
+    n = len(data)
+    nb = n // 4
+    for i in range(nb):
+        kk = int.from_bytes(data[4 * i:4 * i + 4], "little")
+        kk = (kk * c1) & 0xFFFFFFFF
+        kk = ((kk << 15) | (kk >> 17)) & 0xFFFFFFFF
+        kk = (kk * c2) & 0xFFFFFFFF
+        h ^= kk
+        h = ((h << 13) | (h >> 19)) & 0xFFFFFFFF
+        h = (h * 5 + 0xE6546B64) & 0xFFFFFFFF
+    tail = data[4 * nb:]
+    kk = 0
+    if len(tail) >= 3:
+        kk ^= tail[2] << 16
+    if len(tail) >= 2:
+        kk ^= tail[1] << 8
+    if len(tail) >= 1:
+        kk ^= tail[0]
+        kk = (kk * c1) & 0xFFFFFFFF
+        kk = ((kk << 15) | (kk >> 17)) & 0xFFFFFFFF
+        kk = (kk * c2) & 0xFFFFFFFF
+        h ^= kk
+    h ^= n
+    h ^= h >> 16
+    h = (h * 0x85EBCA6B) & 0xFFFFFFFF
+    h ^= h >> 13
+    h = (h * 0xC2B2AE35) & 0xFFFFFFFF
+    h ^= h >> 16
+    return h
+
+
+def nim_hash(name: str) -> int:
+    h = murmur3_32(name.encode("utf-8"))
+    return 314159265 if h == 0 else h  # tables.nim remaps a zero hash code
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Engine:
+    """One GPU context (gvs_ctx)."""
+
+    def __init__(self, k: int, device: int = 0, stream: Optional[int] = None):
+        self.lib = _lib.load()
+        self.k = int(k)
+        self.device = device
+        self.ctx = self.lib.gvs_create(device, self.k)
+        if not self.ctx:
+            raise GavisunkError(-1, f"gvs_create(device={device}, k={k}) failed: no CUDA device or bad k "
+                                    "(gavisunk_b200 has no CPU fallback)")
+        self.contig_names: List[str] = []
+        self._keep = []  # host arrays that must outlive async copies
+        if stream is not None:
+            self._ck(self.lib.gvs_set_stream(self.ctx, C.c_void_p(stream)))
+
+    # ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.gvs_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            msg = self.lib.gvs_last_error(self.ctx).decode("utf-8", "replace")
+            if rc == _lib.GVS_E_KEYERROR:
+                raise KeyError(msg)
+            raise GavisunkError(rc, msg)
+
+    def sync(self):
+        self._ck(self.lib.gvs_sync(self.ctx))
+
+    def set_profiling(self, on: bool):
+        self._ck(self.lib.gvs_set_profiling(self.ctx, 1 if on else 0))
+
+    def stage_ms(self, stage: str) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.gvs_stage_ms(self.ctx, _lib.STAGES[stage], C.byref(ms)))
+        return float(ms.value)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.gvs_launch_count(self.ctx))
+
+    # ------------------------------------------------------------------------------------
+    # database
+    # ------------------------------------------------------------------------------------
+    def load_loc(self, db_kmer, loc_kmer, loc_contig, loc_start, loc_group, contig_names: Sequence[str]):
+        """kmerpos_annot3's table load (workflow/src/kmerpos_annot3.nim:20-26,57-69)."""
+        db_kmer = _c(db_kmer, np.uint64)
+        loc_kmer = _c(loc_kmer, np.uint64)
+        loc_contig = _c(loc_contig, np.uint32)
+        loc_start = _c(loc_start, np.uint32)
+        loc_group = _c(loc_group, np.uint32)
+        self.contig_names = list(contig_names)
+        self._ck(self.lib.gvs_db_load_loc(self.ctx, _ptr(db_kmer), len(db_kmer), _ptr(loc_kmer), _ptr(loc_contig),
+                                          _ptr(loc_start), _ptr(loc_group), len(loc_kmer), len(self.contig_names)))
+
+    def load_loc_text(self, db_lines: Sequence[bytes], loc_rows: Sequence[Tuple[str, int, bytes, int]],
+                      contig_names: Optional[Sequence[str]] = None):
+        """db_lines: lines of jellyfish.db; loc_rows: (contig, start, kmer, group) of kmer.loc."""
+        names = list(contig_names) if contig_names is not None else []
+        idx: Dict[str, int] = {n: i for i, n in enumerate(names)}
+        ci = np.zeros(len(loc_rows), dtype=np.uint32)
+        for i, r in enumerate(loc_rows):
+            j = idx.get(r[0])
+            if j is None:
+                j = idx[r[0]] = len(names)
+                names.append(r[0])
+            ci[i] = j
+        self.load_loc(encode_kmers(list(db_lines)), encode_kmers([r[2] for r in loc_rows]), ci,
+                      np.array([r[1] for r in loc_rows], dtype=np.uint32),
+                      np.array([r[3] for r in loc_rows], dtype=np.uint32), names)
+
+    def build_db(self, contigs: Sequence[Tuple[str, bytes]]):
+        """defineSUNKs.smk:1-127 on the GPU; contigs in ref.fa order (hap1 then hap2)."""
+        self.contig_names = [n for n, _ in contigs]
+        off = np.zeros(len(contigs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(s) for _, s in contigs], dtype=np.uint64)
+        seq = np.frombuffer(b"".join(s for _, s in contigs), dtype=np.uint8)
+        self._ck(self.lib.gvs_db_build(self.ctx, _ptr(seq), _ptr(off), len(contigs), 0))
+
+    def build_db_device(self, seq_dev_ptr: int, contig_off_dev_ptr: int, contig_names: Sequence[str]):
+        self.contig_names = list(contig_names)
+        self._ck(self.lib.gvs_db_build(self.ctx, C.c_void_p(seq_dev_ptr), C.c_void_p(contig_off_dev_ptr),
+                                       len(self.contig_names), 1))
+
+    def db_size(self) -> Tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.gvs_db_size(self.ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def db_export(self) -> Dict[str, np.ndarray]:
+        n, _ = self.db_size()
+        out = dict(kmer=np.zeros(n, np.uint64), contig=np.zeros(n, np.uint32), start=np.zeros(n, np.uint32),
+                   group=np.zeros(n, np.uint32), gidx=np.zeros(n, np.uint32))
+        self._ck(self.lib.gvs_db_export(self.ctx, _ptr(out["kmer"]), _ptr(out["contig"]), _ptr(out["start"]),
+                                        _ptr(out["group"]), _ptr(out["gidx"])))
+        return out
+
+    # ------------------------------------------------------------------------------------
+    # reads
+    # ------------------------------------------------------------------------------------
+    def set_reads(self, seq: np.ndarray, read_off: np.ndarray, chunk_first=None, chunk_hap=None):
+        """Host batch: concatenated ASCII reads + offsets (+ chunk table)."""
+        seq = _c(seq, np.uint8)
+        read_off = _c(read_off, np.uint64)
+        n = len(read_off) - 1
+        chunk_first = _c([0, n] if chunk_first is None else chunk_first, np.uint64)
+        chunk_hap = _c([0] * (len(chunk_first) - 1) if chunk_hap is None else chunk_hap, np.uint8)
+        self._keep = [seq, read_off]
+        self.n_reads = n
+        self._ck(self.lib.gvs_reads_set(self.ctx, _ptr(seq), _ptr(read_off), n, _ptr(chunk_first), _ptr(chunk_hap),
+                                        len(chunk_hap), 0))
+
+    def set_reads_device(self, seq_ptr: int, off_ptr: int, n_reads: int, chunk_first, chunk_hap):
+        chunk_first = _c(chunk_first, np.uint64)
+        chunk_hap = _c(chunk_hap, np.uint8)
+        self.n_reads = n_reads
+        self._ck(self.lib.gvs_reads_set(self.ctx, C.c_void_p(seq_ptr), C.c_void_p(off_ptr), n_reads, _ptr(chunk_first),
+                                        _ptr(chunk_hap), len(chunk_hap), 1))
+
+    # ------------------------------------------------------------------------------------
+    # stages
+    # ------------------------------------------------------------------------------------
+    def match(self) -> int:
+        """kmerpos_annot3 main loop (workflow/src/kmerpos_annot3.nim:81-97)."""
+        n = C.c_uint64()
+        self._ck(self.lib.gvs_match(self.ctx, C.byref(n)))
+        self.n_rows = int(n.value)
+        return self.n_rows
+
+    def rows(self, which: int = 0, n: Optional[int] = None) -> Dict[str, np.ndarray]:
+        if n is None:
+            n = self.n_rows if which == 0 else self.n_kept
+        out = {c: np.zeros(n, np.uint32) for c in ("read", "pos", "contig", "start", "group")}
+        self._ck(self.lib.gvs_rows_get(self.ctx, which, _ptr(out["read"]), _ptr(out["pos"]), _ptr(out["contig"]),
+                                       _ptr(out["start"]), _ptr(out["group"])))
+        return out
+
+    def diag_filter(self, contig_hap: Sequence[int]) -> Tuple[int, int]:
+        """diag_filter_v3 + diag_filter_step2 (workflow/src/diag_filter_v3.nim:18-229,
+        workflow/src/diag_filter_step2.nim:13-66).  contig_hap[c] = haplotype whose .fai lists
+        contig c (255 = neither)."""
+        ch = _c(contig_hap, np.uint8)
+        hh = np.array([nim_hash(n) for n in self.contig_names], dtype=np.uint32)
+        assert len(ch) == len(self.contig_names)
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.gvs_diag_filter(self.ctx, _ptr(ch), _ptr(hh), C.byref(a), C.byref(b)))
+        self.n_best, self.n_kept = int(a.value), int(b.value)
+        return self.n_best, self.n_kept
+
+    def best(self) -> Dict[str, np.ndarray]:
+        n = self.n_best
+        out = dict(read=np.zeros(n, np.uint32), contig=np.zeros(n, np.uint32), ngood=np.zeros(n, np.uint32),
+                   dir=np.zeros(n, np.uint8))
+        self._ck(self.lib.gvs_best_get(self.ctx, _ptr(out["read"]), _ptr(out["contig"]), _ptr(out["ngood"]),
+                                       _ptr(out["dir"])))
+        return out
+
+    def group_hist(self, accumulate: bool = False) -> int:
+        """badsunks_AR.py:20-27 histogram; returns the device pointer of the int32[n_groups] array."""
+        p = C.c_void_p()
+        self._ck(self.lib.gvs_group_hist(self.ctx, 1 if accumulate else 0, C.byref(p)))
+        return int(p.value or 0)
+
+    def bad_groups(self) -> int:
+        """badsunks_AR.py:43-52: mode per haplotype on the device, limit = m + 4*sqrt(m) in float64
+        on the host exactly as the reference computes it, threshold test on the device."""
+        mode = (C.c_int64 * 2)()
+        self._ck(self.lib.gvs_hist_mode(self.ctx, mode))
+        lim = (C.c_int64 * 2)()
+        self.modes = [int(mode[0]), int(mode[1])]
+        for h in range(2):
+            m = int(mode[h])
+            lim[h] = int(math.floor(m + (np.int64(m) ** 0.5) * 4)) if m > 0 else (1 << 62)
+        n = C.c_uint64()
+        self._ck(self.lib.gvs_bad_groups(self.ctx, lim, C.byref(n)))
+        self.n_bad = int(n.value)
+        return self.n_bad
+
+    def bad_list(self) -> np.ndarray:
+        out = np.zeros(self.n_bad, np.uint32)
+        self._ck(self.lib.gvs_bad_get(self.ctx, _ptr(out)))
+        return out
+
+    def validate(self, min_read_len: int = 10000) -> int:
+        """process-by-contig_lowmem_AR.py:50-207 (per-read part)."""
+        n = C.c_uint64()
+        self._ck(self.lib.gvs_validate(self.ctx, min_read_len, C.byref(n)))
+        self.n_pairs = int(n.value)
+        return self.n_pairs
+
+    def pairs(self) -> Dict[str, np.ndarray]:
+        n = self.n_pairs
+        out = {c: np.zeros(n, np.uint32) for c in ("read", "contig", "group", "gidx")}
+        self._ck(self.lib.gvs_pairs_get(self.ctx, _ptr(out["read"]), _ptr(out["contig"]), _ptr(out["group"]),
+                                        _ptr(out["gidx"])))
+        return out
+
+    def components_local(self, accumulate: bool = False) -> int:
+        p = C.c_void_p()
+        self._ck(self.lib.gvs_components_local(self.ctx, 1 if accumulate else 0, C.byref(p)))
+        return int(p.value or 0)
+
+    def components_merge(self, peer_parent_ptr: int):
+        self._ck(self.lib.gvs_components_merge(self.ctx, C.c_void_p(peer_parent_ptr)))
+
+    def intervals(self) -> Dict[str, np.ndarray]:
+        """process-by-contig_lowmem_AR.py:215-260 -> rows of bed_files/*.bed."""
+        n = C.c_uint64()
+        self._ck(self.lib.gvs_intervals(self.ctx, C.byref(n)))
+        n = int(n.value)
+        out = {c: np.zeros(n, np.uint32) for c in ("contig", "start", "end")}
+        self._ck(self.lib.gvs_intervals_get(self.ctx, _ptr(out["contig"]), _ptr(out["start"]), _ptr(out["end"])))
+        return out
+
+    def gaps(self, contig_len: Sequence[int]):
+        """get_gaps.py:17-123."""
+        cl = _c(contig_len, np.uint32)
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.gvs_gaps(self.ctx, _ptr(cl), C.byref(a), C.byref(b)))
+        g = {c: np.zeros(int(a.value), np.uint32) for c in ("contig", "start", "end")}
+        nd = np.zeros(int(b.value), np.uint32)
+        self._ck(self.lib.gvs_gaps_get(self.ctx, _ptr(g["contig"]), _ptr(g["start"]), _ptr(g["end"]), _ptr(nd)))
+        return g, nd
+
+    def covprob_table(self, kbp, cnt, genome_kbp: float, pn: float) -> np.ndarray:
+        """covprob.py:56-100."""
+        kbp = _c(kbp, np.int64)
+        cnt = _c(cnt, np.int64)
+        out = np.zeros(3500, np.float64)
+        self._ck(self.lib.gvs_covprob_table(self.ctx, _ptr(kbp), _ptr(cnt), len(kbp), float(genome_kbp), float(pn),
+                                            _ptr(out)))
+        return out

@@ -1,0 +1,210 @@
+/* gavisunk_b200.h -- C ABI of libgavisunk_b200.so
+ *
+ * B200-native (sm_100a) engine for GAVISUNK's data-parallel core: SUNK database build, SUNK
+ * matching of ONT reads, best-contig (diagonal band) filter, bad-SUNK histogram, inter-SUNK
+ * distance validation, validated intervals / gaps and the gap-spanning probability table.
+ *
+ * The reference (pdishuck/GAVISUNK) has no FFI: its seam is "one OS process per Snakemake rule,
+ * argv + TSV/BED files" (SURVEY.md section 8b).  Each entry point below names the reference
+ * program / function it replaces (file:line relative to the reference repository).  The Python
+ * package `gavisunk_b200` binds these with ctypes and re-creates the reference CLIs on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative GVS_E_* code on failure;
+ *     gvs_last_error(ctx) returns a NUL-terminated message owned by the context.
+ *   - one gvs_ctx per GPU; a context is not thread-safe; independent contexts may be driven from
+ *     different host threads.  There is NO CPU fallback: without a CUDA device gvs_create fails.
+ *   - "host" pointers are ordinary (ideally pinned) host memory; "dev" pointers are device
+ *     memory of the context's GPU (e.g. torch tensors' data_ptr()).
+ *   - all results live in device memory owned by the context until the next call of the same
+ *     stage; the *_get functions copy them to caller-provided host buffers.
+ *   - contig ids are indices into the contig list given at database build/load time (ref.fa
+ *     order: hap1 contigs then hap2 contigs, workflow/rules/defineSUNKs.smk:17).
+ */
+#ifndef GAVISUNK_B200_H
+#define GAVISUNK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gvs_ctx gvs_ctx;
+
+enum {
+  GVS_OK = 0,
+  GVS_E_CUDA = -1,      /* CUDA runtime error (message has the detail)                            */
+  GVS_E_ARG = -2,       /* bad argument / call order                                              */
+  GVS_E_KEYERROR = -3,  /* a read hit a db k-mer that has no .loc row: the reference raises
+                           KeyError here (workflow/src/kmerpos_annot3.nim:90)                     */
+  GVS_E_NOMEM = -4,
+  GVS_E_OVERFLOW = -5,  /* an internal capacity was exceeded (message says which)                 */
+  GVS_E_STATE = -6      /* stage called before its inputs exist                                   */
+};
+
+/* stage ids for gvs_stage_ms() */
+enum {
+  GVS_ST_PROBE = 0,     /* read scan / probe kernel (kmerpos_annot3.nim:85-96 inner loop)         */
+  GVS_ST_EMIT = 1,      /* hit ordering + consecutive-group suppression                           */
+  GVS_ST_DIAG = 2,      /* diag_filter_v3 + diag_filter_step2                                     */
+  GVS_ST_HIST = 3,      /* badsunks_AR.py histogram + mode                                        */
+  GVS_ST_VALIDATE = 4,  /* process-by-contig per-read validation                                  */
+  GVS_ST_INTERVALS = 5, /* contig-wide components + intervals + gaps                              */
+  GVS_ST_DBBUILD = 6,
+  GVS_ST_COUNT = 8
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* context                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+/* k = SUNK_len (config/config.yaml:2).  1 <= k <= 31 (k = 32 yields no hits in the reference,
+ * SURVEY Q2; it is accepted here and produces zero hits as well). */
+gvs_ctx* gvs_create(int device, int k);
+void gvs_destroy(gvs_ctx* ctx);
+const char* gvs_last_error(gvs_ctx* ctx);
+const char* gvs_version(void);
+/* Launch all work of this context on `cuda_stream` (a cudaStream_t; NULL = legacy default). */
+int gvs_set_stream(gvs_ctx* ctx, void* cuda_stream);
+int gvs_sync(gvs_ctx* ctx);
+/* Enable per-stage CUDA-event timing; gvs_stage_ms returns the device time of the last run of
+ * that stage (sum of its kernels), measured with events on the context's stream. */
+int gvs_set_profiling(gvs_ctx* ctx, int on);
+int gvs_stage_ms(gvs_ctx* ctx, int stage, float* ms);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t gvs_launch_count(gvs_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------ */
+/* SUNK database                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+/* Replaces the table load of kmerpos_annot3 (workflow/src/kmerpos_annot3.nim:20-26 db set,
+ * :57-69 loc table): db_kmer = kmer.encode() of every jellyfish.db line, loc_* = the four
+ * columns of mrsfast/kmer.loc in file order (later duplicates of a k-mer overwrite earlier ones,
+ * nim:68).  contig ids index the caller's contig-name list.  All pointers are host memory. */
+int gvs_db_load_loc(gvs_ctx* ctx, const uint64_t* db_kmer, uint64_t n_db,
+                    const uint64_t* loc_kmer, const uint32_t* loc_contig,
+                    const uint32_t* loc_start, const uint32_t* loc_group, uint64_t n_loc,
+                    uint32_t n_contigs);
+
+/* Replaces workflow/rules/defineSUNKs.smk:1-127 (combine_asm_haps, jellyfish count -C -U 1,
+ * define_SUNKs, mrsfast index/search -e 0, bed_convert): canonical k-mers of the concatenated
+ * assembly that occur exactly once, their location and the start of their merged
+ * (overlapping-or-book-ended) run.  seq = concatenated contig sequences (ASCII, any case, non-ACGT
+ * breaks windows), contig_off[n_contigs+1] = offsets into seq.  `seq_on_device` != 0: both
+ * pointers are device memory. */
+int gvs_db_build(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* contig_off, uint32_t n_contigs,
+                 int seq_on_device);
+
+int gvs_db_size(gvs_ctx* ctx, uint64_t* n_sunks, uint64_t* n_groups);
+/* kmer.loc rows in file order ((contig, start) order for a built database): host buffers of
+ * n_sunks entries each; any pointer may be NULL. */
+int gvs_db_export(gvs_ctx* ctx, uint64_t* kmer, uint32_t* contig, uint32_t* start,
+                  uint32_t* group, uint32_t* group_index);
+
+/* ------------------------------------------------------------------------------------------ */
+/* reads                                                                                       */
+/* ------------------------------------------------------------------------------------------ */
+/* A batch = the reads of one or more chunk files (temp/{sample}/reads/{hap}_{i-of-N}.fq.gz,
+ * workflow/rules/tagONT.smk:17), concatenated in file order.
+ *   seq            ASCII bases of all reads back to back (no separators)
+ *   read_off       n_reads+1 offsets into seq
+ *   chunk_first    n_chunks+1 read indices: chunk c = reads [chunk_first[c], chunk_first[c+1]);
+ *                  the kmerpos_annot3 `prevLoc` carry (nim:82-84) restarts per chunk
+ *   chunk_hap      n_chunks entries, the haplotype (0/1) whose .fai the chunk's reads are
+ *                  filtered against (workflow/rules/tagONT.smk:79,92)
+ * on_device != 0: seq and read_off are device pointers that stay valid until the next
+ * gvs_reads_* call (no copy is made); chunk arrays are always host memory.
+ * With on_device == 0 the arrays are copied host->device on the context's stream. */
+int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* read_off, uint64_t n_reads,
+                  const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks,
+                  int on_device);
+
+/* ------------------------------------------------------------------------------------------ */
+/* stages (must be called in this order; each consumes the previous stage's device results)    */
+/* ------------------------------------------------------------------------------------------ */
+/* kmerpos_annot3 main loop (workflow/src/kmerpos_annot3.nim:81-97): sunkpos rows
+ * (read, pos, contig, start, group) with the consecutive-(contig,group) suppression and the
+ * position drift it causes. */
+int gvs_match(gvs_ctx* ctx, uint64_t* n_rows);
+/* which: 0 = rows of gvs_match ({hap}_{i}.sunkpos), 1 = rows kept by gvs_diag_filter
+ * ({hap}_{i}_diag2.sunkpos).  Host buffers of n_rows entries; any may be NULL. */
+int gvs_rows_get(gvs_ctx* ctx, int which, uint32_t* read_idx, uint32_t* pos, uint32_t* contig,
+                 uint32_t* start, uint32_t* group);
+
+/* diag_filter_v3 (workflow/src/diag_filter_v3.nim:18-229) + diag_filter_step2
+ * (workflow/src/diag_filter_step2.nim:13-66).
+ *   contig_hap[n_contigs]   haplotype (0/1) whose .fai lists the contig, 255 = in neither
+ *   contig_hash[n_contigs]  Nim `hash(name)` of the contig name (MurmurHash3_x86_32, seed 0,
+ *                           0 remapped) -- decides ties through Table iteration order
+ * n_best = reads that got a best contig, n_kept = rows that survive. */
+int gvs_diag_filter(gvs_ctx* ctx, const uint8_t* contig_hap, const uint32_t* contig_hash,
+                    uint64_t* n_best, uint64_t* n_kept);
+/* rows of {hap}_{i}_diag.sunkpos: read, contig, n, dir (0 = '-', 1 = '+') */
+int gvs_best_get(gvs_ctx* ctx, uint32_t* read_idx, uint32_t* contig, uint32_t* ngood,
+                 uint8_t* dir);
+
+/* badsunks_AR.py:20-52 histogram: rows per (contig, group) over the kept rows, accumulated into a
+ * device array of n_groups int32 (index = group_index of gvs_db_export).  *hist_dev receives the
+ * device pointer so that the caller can all-reduce it across GPUs (NCCL) before
+ * gvs_bad_groups.  accumulate != 0 adds to the previous histogram (several batches). */
+int gvs_group_hist(gvs_ctx* ctx, int accumulate, int32_t** hist_dev);
+/* mode of the non-zero counts per haplotype (badsunks_AR.py:43, smallest mode) */
+int gvs_hist_mode(gvs_ctx* ctx, int64_t mode[2]);
+/* bad group <=> count > limit[hap] or count < 2 (badsunks_AR.py:46-52); limit is computed by the
+ * caller exactly as the reference does (m + 4*sqrt(m) in float64) and passed as floor(limit). */
+int gvs_bad_groups(gvs_ctx* ctx, const int64_t limit_floor[2], uint64_t* n_bad);
+int gvs_bad_get(gvs_ctx* ctx, uint32_t* group_index /* n_bad entries */);
+
+/* process-by-contig_lowmem_AR.py:50-207 per-read part: validated (group, read) pairs = rows of
+ * inter_outs/{contig}_{hap}.tsv.  min_read_len is the reference's hard-coded 10000 (:106). */
+int gvs_validate(gvs_ctx* ctx, uint32_t min_read_len, uint64_t* n_pairs);
+int gvs_pairs_get(gvs_ctx* ctx, uint32_t* read_idx, uint32_t* contig, uint32_t* group,
+                  uint32_t* group_index);
+
+/* process-by-contig_lowmem_AR.py:215-260 contig-wide components.  The union-find parent array
+ * (n_groups uint32, index = group_index) is exposed so that several GPUs can merge their
+ * forests: gvs_components_local builds this GPU's forest, gvs_components_merge unions in a
+ * peer's forest (device pointer, e.g. an all-gathered copy), gvs_intervals finalises. */
+int gvs_components_local(gvs_ctx* ctx, int accumulate, uint32_t** parent_dev);
+int gvs_components_merge(gvs_ctx* ctx, const uint32_t* peer_parent_dev);
+/* validated intervals (contig, min group, max group) of components with >= 3 groups, sorted by
+ * (contig, start) = rows of bed_files/{contig}_{hap}.bed */
+int gvs_intervals(gvs_ctx* ctx, uint64_t* n_intervals);
+int gvs_intervals_get(gvs_ctx* ctx, uint32_t* contig, uint32_t* start, uint32_t* end);
+
+/* get_gaps.py:17-123: per contig merge intervals, gaps (prev_end, next_start-1); contigs without
+ * intervals are "nodata".  contig_len[n_contigs]. */
+int gvs_gaps(gvs_ctx* ctx, const uint32_t* contig_len, uint64_t* n_gaps, uint64_t* n_nodata);
+int gvs_gaps_get(gvs_ctx* ctx, uint32_t* contig, uint32_t* start, uint32_t* end,
+                 uint32_t* nodata_contig);
+
+/* covprob.py:56-100: table[0..3499] of gap-spanning probabilities from the read-length
+ * histogram.  kbp[n_bins], cnt[n_bins] = distinct int(len/1000) values and their multiplicities
+ * in the reference's iteration order, pn = run-of-k survival probability (covprob.py:79-81, host
+ * root solve), genome_kbp = sum(fai.len)/1000. */
+int gvs_covprob_table(gvs_ctx* ctx, const int64_t* kbp, const int64_t* cnt, uint32_t n_bins,
+                      double genome_kbp, double pn, double* table3500);
+
+/* ------------------------------------------------------------------------------------------ */
+/* synthetic workloads (bench.py / tests only)                                   */
+/* ------------------------------------------------------------------------------------------ */
+/* Deterministic diploid assembly on the device: hap1 = i.i.d. ACGT with segmental duplications
+ * and N runs, hap2 = hap1 with SNPs at rate snp_rate.  contig_len[n_contigs_per_hap].  Writes
+ * 2*sum(len) bytes to seq_dev (hap1 contigs then hap2 contigs). */
+int gvs_synth_assembly(gvs_ctx* ctx, uint8_t* seq_dev, const uint64_t* contig_len,
+                       uint32_t n_contigs_per_hap, double snp_rate, double dup_frac,
+                       uint64_t seed);
+/* ONT-like reads sampled from an assembly on the device (log-normal lengths, both strands,
+ * substitution/deletion/insertion errors, occasional N runs).  Two-step: _plan computes the
+ * read offsets (device array of n_reads+1, returned total in *total_bases), _fill writes bases. */
+int gvs_synth_reads_plan(gvs_ctx* ctx, const uint64_t* contig_off_dev, uint32_t contig_lo,
+                         uint32_t contig_hi, uint64_t n_reads, double len_mu, double len_sigma,
+                         uint32_t len_min, uint32_t len_max, uint64_t seed, uint64_t* read_off_dev,
+                         uint64_t* total_bases);
+int gvs_synth_reads_fill(gvs_ctx* ctx, const uint8_t* asm_seq_dev, uint8_t* reads_dev,
+                         const uint64_t* read_off_dev, uint64_t n_reads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAVISUNK_B200_H */

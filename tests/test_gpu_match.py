@@ -1,0 +1,35 @@
+"""GPU parity of the match stage (gvs_match) against the reference ELF outputs recorded in
+tests/golden (kmerpos_annot3) -- bit-exact rows, including quirks Q1-Q6."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, engine_from_case, run_match_chunks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes"])
+def test_match_kats(name):
+    case = load_golden(name)
+    eng, names = engine_from_case(case)
+    got = run_match_chunks(eng, names, [case["reads"]])
+    assert got[0] == case["out"]
+
+
+@pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many"])
+def test_match_random_per_chunk(name):
+    case = load_golden(name)
+    eng, names = engine_from_case(case)
+    for ch in case["chunks"]:
+        got = run_match_chunks(eng, names, [ch["reads"]])
+        assert got[0] == ch["sunkpos"]
+
+
+@pytest.mark.parametrize("name", ["rand_k20", "rand_k20_many"])
+def test_match_random_batched_chunks(name):
+    """all chunk files of a sample in ONE batch: the prevLoc carry must restart per chunk (Q4)"""
+    case = load_golden(name)
+    eng, names = engine_from_case(case)
+    got = run_match_chunks(eng, names, [ch["reads"] for ch in case["chunks"]])
+    for g, ch in zip(got, case["chunks"]):
+        assert g == ch["sunkpos"]
