@@ -31,6 +31,8 @@ PROTOTYPES = {
     "gvs_db_size": (C.c_int, [vp, u64p, u64p]),
     "gvs_db_export": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "gvs_reads_set": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_int]),
+    "gvs_reads_meta": (C.c_int, [vp, vp, C.c_uint64, vp, vp, C.c_uint32]),
+    "gvs_rows_set": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32]),
     "gvs_match": (C.c_int, [vp, u64p]),
     "gvs_rows_get": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
     "gvs_diag_filter": (C.c_int, [vp, vp, vp, u64p, u64p]),

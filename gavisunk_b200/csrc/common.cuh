@@ -68,6 +68,11 @@ struct gvs_ctx {
   std::vector<u64> h_chunk_first;
   std::vector<u8> h_chunk_hap;
   u32 n_chunks = 0;
+  DevBuf read_len;             // explicit lengths (gvs_reads_meta) when there are no sequences
+  bool have_read_len = false;
+  DevBuf gt_keys, gt_val;      // (contig, group) -> group index lookup for gvs_rows_set
+  u64 gt_slots = 0;
+  bool groups_ready = false;   // grp_contig / grp_start / n_groups valid (database or rows-derived)
 
   // ---- match ----
   DevBuf tile_first, tile_cnt, tile_off, tile_dst;
@@ -361,3 +366,6 @@ static int to_dev(gvs_ctx* ctx, DevBuf& b, const T* h, size_t n) {
 
 // stage entry points implemented in the other translation units
 int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db);  // table.cu
+int gvs_group_index_rows(gvs_ctx* ctx, const u32* contig, const u32* group, u64 n, u32* gidx_out);  // table.cu
+int gvs_build_segments(gvs_ctx* ctx, const u32* read, u64 n, DevBuf& seg_start, DevBuf& row_seg, u64* n_seg_out);  // diag.cu
+int gvs_reserve_rows(gvs_ctx* ctx, Rows& r, u64 n);

@@ -44,7 +44,7 @@ extern "C" void gvs_destroy(gvs_ctx* c) {
                    &c->cnt_hist, &c->bad_flag, &c->bad_list, &c->kseg_start, &c->val_scratch, &c->val_cnt,
                    &c->val_off, &c->pair_read, &c->pair_contig, &c->pair_group, &c->pair_gidx, &c->parent,
                    &c->present, &c->comp_min, &c->comp_max, &c->comp_cnt, &c->iv_contig, &c->iv_start, &c->iv_end,
-                   &c->gap_contig, &c->gap_start, &c->gap_end, &c->nodata_contig};
+                   &c->gap_contig, &c->gap_start, &c->gap_end, &c->nodata_contig, &c->read_len, &c->gt_keys, &c->gt_val};
   for (DevBuf* b : all) gvs_release(*b);
   release_rows(c->rows);
   release_rows(c->kept);

@@ -1,0 +1,509 @@
+// diag.cu -- best contig per read by diagonal band vote + row filter: the GPU replacement of
+// diag_filter_v3 (workflow/src/diag_filter_v3.nim:18-229) and diag_filter_step2
+// (workflow/src/diag_filter_step2.nim:13-66).  SURVEY.md A.4, quirks Q8-Q11.
+//
+// Flat decomposition over global scratch arrays (rows are ~1 per kb of read, so this stage moves
+// ~1 % of the bytes of the probe kernel):
+//   segments      consecutive rows of one read
+//   k_row_first   first row of every distinct contig of a read (Table insertion order) + its hit count
+//   candidates    first rows whose contig is in the read's haplotype .fai and has >= 2 hits
+//   k_cand_gather (pos, start, group) of a candidate's rows, contiguous
+//   k_cand_vote   both orientations: interpolated median, truncation toward zero, distinct groups
+//                 with |n - median| < 2500
+//   k_seg_best    argmax (good desc, hitlen asc); cross-contig ties are flagged ...
+//   k_seg_tie     ... and resolved by replaying Nim's Table[string, _] slot order (murmur3 & mask,
+//                 linear probing, growth at count*3 > cap*2, capacity sticky within a chunk)
+//   k_keep_rows   rows on the best contig survive (all of them, Q11)
+#include "common.cuh"
+
+#define NOBEST 0xFFFFFFFFu
+#define BANDWIDTH 2500
+
+int gvs_build_segments(gvs_ctx* ctx, const u32* read, u64 n, DevBuf& seg_start, DevBuf& row_seg, u64* n_seg_out);
+
+__global__ void __launch_bounds__(256) k_seg_fill(const u32* __restrict__ read, const u32* __restrict__ row_seg, u64 n,
+                                                  u32* seg_start, u32 n_seg) {
+  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n) return;
+  if (j == n) { seg_start[n_seg] = (u32)n; return; }
+  if (j == 0 || read[j] != read[j - 1]) seg_start[row_seg[j]] = (u32)j;
+}
+
+int gvs_build_segments(gvs_ctx* ctx, const u32* read, u64 n, DevBuf& seg_start, DevBuf& row_seg, u64* n_seg_out) {
+  CKR(gvs_reserve(ctx, row_seg, n * 4));
+  u32* rs = row_seg.as<u32>();
+  u32* tot = (u32*)(ctx->counters.as<u64>() + 8);
+  auto f = [read] __device__(u64 j) -> u32 { return (j == 0 || read[j] != read[j - 1]) ? 1u : 0u; };
+  auto g = [rs] __device__(u64 j, u32 ex, u32 v) { rs[j] = ex + v - 1; };
+  CKR((device_scan<u32>(ctx, n, f, g, OpSum(), tot)));
+  u32 ns = 0;
+  CKR(read_dev(ctx, tot, &ns));
+  CKR(gvs_reserve(ctx, seg_start, ((u64)ns + 1) * 4));
+  LAUNCH(k_seg_fill, (unsigned)cdiv(n + 1, 256), 256, 0, read, rs, n, seg_start.as<u32>(), ns);
+  *n_seg_out = ns;
+  return 0;
+}
+
+__device__ __forceinline__ u32 chunk_of_read(const u64* __restrict__ chunk_first, u32 n_chunks, u32 read) {
+  u32 lo = 0, hi = n_chunks;
+  while (hi - lo > 1) {
+    u32 mid = (lo + hi) >> 1;
+    if (chunk_first[mid] <= read) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) k_seg_info(const u32* __restrict__ read, const u32* __restrict__ seg_start, u32 n_seg,
+                                                  const u64* __restrict__ chunk_first, const u8* __restrict__ chunk_hap,
+                                                  u32 n_chunks, u32* seg_chunk, u8* seg_hap, u32* seg_ndist) {
+  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  u32 c = chunk_of_read(chunk_first, n_chunks, read[seg_start[s]]);
+  seg_chunk[s] = c;
+  seg_hap[s] = chunk_hap[c];
+  seg_ndist[s] = 0;
+}
+
+// row_cnt[j] = number of rows of j's contig in j's read if j is the first such row, else 0
+__global__ void __launch_bounds__(256) k_row_first(const u32* __restrict__ contig, const u32* __restrict__ row_seg,
+                                                   const u32* __restrict__ seg_start, u64 n, u32* row_cnt, u32* seg_ndist) {
+  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  u32 s = row_seg[j];
+  u32 a = seg_start[s], b = seg_start[s + 1];
+  u32 c = contig[j];
+  for (u32 i = a; i < (u32)j; i++)
+    if (contig[i] == c) { row_cnt[j] = 0; return; }
+  u32 cnt = 1;
+  for (u32 i = (u32)j + 1; i < b; i++) cnt += contig[i] == c;
+  row_cnt[j] = cnt;
+  atomicAdd(&seg_ndist[s], 1u);
+}
+
+// (pos, start, group) of the candidate's rows, in read order
+__global__ void __launch_bounds__(256) k_cand_gather(const u32* __restrict__ cand_row, const u32* __restrict__ cand_voff,
+                                                     u32 n_cand, const u32* __restrict__ contig, const u32* __restrict__ pos,
+                                                     const u32* __restrict__ start, const u32* __restrict__ group,
+                                                     const u32* __restrict__ row_seg, const u32* __restrict__ seg_start,
+                                                     u32* v_pos, u32* v_start, u32* v_group) {
+  u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= n_cand) return;
+  u32 j = cand_row[w];
+  u32 b = seg_start[row_seg[j] + 1];
+  u32 c = contig[j];
+  u32 o = cand_voff[w];
+  for (u32 base = j; base < b; base += 32) {
+    u32 i = base + lane;
+    bool m = i < b && contig[i] == c;
+    u32 bal = __ballot_sync(0xFFFFFFFFu, m);
+    if (m) {
+      u32 d = o + __popc(bal & ((1u << lane) - 1));
+      v_pos[d] = pos[i];
+      v_start[d] = start[i];
+      v_group[d] = group[i];
+    }
+    o += __popc(bal);
+  }
+}
+
+// one thread group (NT threads) per candidate; NT = 32 (a warp, 4 per block) or 1024 (a block)
+template <int NT>
+__global__ void __launch_bounds__(NT == 32 ? 128 : NT) k_cand_vote(const u32* __restrict__ cand_row,
+                                                                    const u32* __restrict__ cand_voff, u32 n_cand,
+                                                                    const u32* __restrict__ row_cnt,
+                                                                    const u32* __restrict__ v_pos,
+                                                                    const u32* __restrict__ v_start,
+                                                                    const u32* __restrict__ v_group, u32 small_max,
+                                                                    u32* cand_good, u8* cand_dir) {
+  constexpr int GROUPS = NT == 32 ? 4 : 1;
+  __shared__ i64 s_alo[GROUPS], s_ahi[GROUPS];
+  __shared__ u32 s_good[GROUPS];
+  const int grp = NT == 32 ? (threadIdx.x >> 5) : 0;
+  const int tid = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
+  u32 ci = NT == 32 ? blockIdx.x * GROUPS + grp : blockIdx.x;
+  bool active = ci < n_cand;
+  u32 cnt = 0, o = 0;
+  if (active) {
+    cnt = row_cnt[cand_row[ci]];
+    o = cand_voff[ci];
+    if (NT == 32 ? cnt > small_max : cnt <= small_max) active = false;
+  }
+  if (NT != 32 && !active) return;  // whole block
+  auto gsync = [&]() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
+  };
+  u32 good2[2] = {0, 0};
+  for (int orient = 0; orient < 2; orient++) {  // 0: reverse (pos + start), 1: forward (start - pos)
+    if (tid == 0) { s_alo[grp] = 0; s_ahi[grp] = 0; s_good[grp] = 0; }
+    gsync();
+    if (active) {
+      u32 lo = (cnt - 1) >> 1;
+      for (u32 i = tid; i < cnt; i += NT) {
+        i64 ni = orient == 0 ? (i64)v_start[o + i] + (i64)v_pos[o + i] : (i64)v_start[o + i] - (i64)v_pos[o + i];
+        u32 rank = 0;
+        for (u32 j = 0; j < cnt; j++) {
+          i64 nj = orient == 0 ? (i64)v_start[o + j] + (i64)v_pos[o + j] : (i64)v_start[o + j] - (i64)v_pos[o + j];
+          rank += (nj < ni) || (nj == ni && j < i);
+        }
+        if (rank == lo) s_alo[grp] = ni;
+        if (rank == lo + 1) s_ahi[grp] = ni;
+      }
+    }
+    gsync();
+    if (active) {
+      // arraymancer percentile(n, 50): linear interpolation in float64, then int() truncation
+      // toward zero (diag_filter_v3.nim:86,113; Q8)
+      i64 alo = s_alo[grp], med = alo;
+      if (!(cnt & 1)) {
+        i64 d = s_ahi[grp] - alo;  // >= 0
+        med = alo + (d >> 1);
+        if ((d & 1) && med < 0) med += 1;  // x.5 below zero truncates up
+      }
+      for (u32 i = tid; i < cnt; i += NT) {
+        i64 ni = orient == 0 ? (i64)v_start[o + i] + (i64)v_pos[o + i] : (i64)v_start[o + i] - (i64)v_pos[o + i];
+        i64 dv = ni - med;
+        if (dv < 0) dv = -dv;
+        if (dv >= BANDWIDTH) continue;
+        u32 gi = v_group[o + i];
+        bool dup = false;
+        for (u32 j = 0; j < i && !dup; j++) {
+          if (v_group[o + j] != gi) continue;
+          i64 nj = orient == 0 ? (i64)v_start[o + j] + (i64)v_pos[o + j] : (i64)v_start[o + j] - (i64)v_pos[o + j];
+          i64 dj = nj - med;
+          if (dj < 0) dj = -dj;
+          dup = dj < BANDWIDTH;
+        }
+        if (!dup) atomicAdd(&s_good[grp], 1u);
+      }
+    }
+    gsync();
+    good2[orient] = s_good[grp];
+    gsync();
+  }
+  if (active && tid == 0) {
+    // reverse is tried first; forward replaces it only on a strictly larger count (nim:98-138)
+    bool fwd = good2[1] > good2[0];
+    cand_good[ci] = fwd ? good2[1] : good2[0];
+    cand_dir[ci] = fwd ? 1 : 0;
+  }
+}
+
+// smallest power-of-two capacity >= 64 that holds n distinct keys without growing
+// (tables.nim mustRehash: cap*2 < count*3 checked before each insert, count = keys so far)
+__host__ __device__ __forceinline__ u32 cap_needed(u32 n) {
+  u32 cap = 64;
+  while (n > 0 && (u64)cap * 2 < (u64)(n - 1) * 3) cap <<= 1;
+  return cap;
+}
+
+__global__ void __launch_bounds__(256) k_seg_best(u32 n_seg, const u32* __restrict__ seg_start,
+                                                  const u32* __restrict__ cidx_excl, const u32* __restrict__ cand_row,
+                                                  const u32* __restrict__ row_cnt, const u32* __restrict__ contig,
+                                                  const u32* __restrict__ cand_good, const u8* __restrict__ cand_dir,
+                                                  u32* seg_best, u32* seg_good, u8* seg_dir, u8* seg_tie) {
+  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  u32 c0 = cidx_excl[seg_start[s]], c1 = cidx_excl[seg_start[s + 1]];
+  u32 maxgood = 0, maxhit = 0, best = NOBEST, ties = 0;
+  u8 dir = 0;
+  for (u32 ci = c0; ci < c1; ci++) {
+    u32 g = cand_good[ci], h = row_cnt[cand_row[ci]];
+    if (g > maxgood || (g == maxgood && g > 0 && h < maxhit)) {
+      maxgood = g; maxhit = h; best = contig[cand_row[ci]]; dir = cand_dir[ci]; ties = 1;
+    } else if (g == maxgood && g > 0 && h == maxhit) {
+      ties++;
+    }
+  }
+  bool ok = maxgood > 1;  // `if maxgood>1: echo ...` (nim:141)
+  seg_best[s] = ok ? best : NOBEST;
+  seg_good[s] = maxgood;
+  seg_dir[s] = dir;
+  seg_tie[s] = (ok && ties > 1) ? 1 : 0;
+}
+
+// replay Nim's Table for the reads whose optimum is shared by several contigs
+__global__ void __launch_bounds__(64) k_seg_tie(const u32* __restrict__ tie_seg, u32 n_tie, const u32* __restrict__ seg_start,
+                                                const u32* __restrict__ seg_cap, const u32* __restrict__ cidx_excl,
+                                                const u32* __restrict__ cand_row, const u32* __restrict__ row_cnt,
+                                                const u32* __restrict__ contig, const u32* __restrict__ contig_hash,
+                                                const u32* __restrict__ cand_good, const u8* __restrict__ cand_dir,
+                                                u32* scratch, u32 maxcap, u32* seg_best, u8* seg_dir) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tie) return;
+  u32 s = tie_seg[t];
+  u32 a = seg_start[s], b = seg_start[s + 1];
+  u32* A = scratch + (u64)t * 2 * maxcap;
+  u32* B = A + maxcap;
+  u32 cap = seg_cap[s], count = 0;
+  for (u32 i = 0; i < cap; i++) A[i] = NOBEST;
+  for (u32 j = a; j < b; j++) {
+    if (row_cnt[j] == 0) continue;  // not the first row of its contig
+    u32 c = contig[j];
+    if ((u64)cap * 2 < (u64)count * 3 || cap - count < 4) {  // enlarge: re-insert in old slot order
+      u32 ncap = cap * 2;
+      for (u32 i = 0; i < ncap; i++) B[i] = NOBEST;
+      for (u32 i = 0; i < cap; i++) {
+        u32 e = A[i];
+        if (e == NOBEST) continue;
+        u32 h = contig_hash[e] & (ncap - 1);
+        while (B[h] != NOBEST) h = (h + 1) & (ncap - 1);
+        B[h] = e;
+      }
+      u32* tmp = A; A = B; B = tmp;
+      cap = ncap;
+    }
+    u32 h = contig_hash[c] & (cap - 1);
+    while (A[h] != NOBEST) h = (h + 1) & (cap - 1);
+    A[h] = c;
+    count++;
+  }
+  // optimum of this read
+  u32 c0 = cidx_excl[a], c1 = cidx_excl[b];
+  u32 maxgood = 0, maxhit = 0;
+  for (u32 ci = c0; ci < c1; ci++) {
+    u32 g = cand_good[ci], h = row_cnt[cand_row[ci]];
+    if (g > maxgood || (g == maxgood && h < maxhit)) { maxgood = g; maxhit = h; }
+  }
+  for (u32 i = 0; i < cap; i++) {  // `for k,v in posStarts.pairs()`: slot order
+    u32 e = A[i];
+    if (e == NOBEST) continue;
+    for (u32 ci = c0; ci < c1; ci++) {
+      if (contig[cand_row[ci]] == e && cand_good[ci] == maxgood && row_cnt[cand_row[ci]] == maxhit) {
+        seg_best[s] = e;
+        seg_dir[s] = cand_dir[ci];
+        return;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_keep_rows(u64 n, const u32* __restrict__ keep_excl, const u32* __restrict__ row_seg,
+                                                   const u32* __restrict__ seg_best, const u32* __restrict__ read,
+                                                   const u32* __restrict__ pos, const u32* __restrict__ contig,
+                                                   const u32* __restrict__ start, const u32* __restrict__ group,
+                                                   const u32* __restrict__ gidx, u32* o_read, u32* o_pos, u32* o_contig,
+                                                   u32* o_start, u32* o_group, u32* o_gidx) {
+  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  u32 c = contig[j];
+  if (seg_best[row_seg[j]] != c) return;
+  u32 o = keep_excl[j];
+  o_read[o] = read[j];
+  o_pos[o] = pos[j];
+  o_contig[o] = c;
+  o_start[o] = start[j];
+  o_group[o] = group[j];
+  o_gidx[o] = gidx[j];
+}
+
+__global__ void __launch_bounds__(256) k_best_rows(u32 n_seg, const u32* __restrict__ best_excl,
+                                                   const u32* __restrict__ seg_best, const u32* __restrict__ seg_good,
+                                                   const u8* __restrict__ seg_dir, const u32* __restrict__ seg_start,
+                                                   const u32* __restrict__ read, u32* o_read, u32* o_contig, u32* o_good,
+                                                   u8* o_dir) {
+  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg || seg_best[s] == NOBEST) return;
+  u32 o = best_excl[s];
+  o_read[o] = read[seg_start[s]];
+  o_contig[o] = seg_best[s];
+  o_good[o] = seg_good[s];
+  o_dir[o] = seg_dir[s];
+}
+
+
+// scratch layout inside ctx->diag_scratch (u32 units)
+struct DiagScratch {
+  u32 *row_seg, *row_cnt, *cidx, *keep_excl, *cand_row, *cand_voff, *v_pos, *v_start, *v_group, *cand_good;
+  u32 *seg_chunk, *seg_ndist, *seg_cap, *seg_best, *seg_good, *best_excl, *tie_seg;
+  u8 *seg_hap, *seg_dir, *seg_tie, *cand_dir;
+};
+
+static int diag_impl(gvs_ctx* ctx, u64* n_best_out, u64* n_kept_out) {
+  Rows& R = ctx->rows;
+  u64 n = R.n;
+  ctx->kept.n = 0;
+  ctx->n_best = 0;
+  ctx->n_seg = 0;
+  if (n == 0) return 0;
+  StageTimer tm(ctx, GVS_ST_DIAG);
+  const u32 *read = R.read.as<u32>(), *pos = R.pos.as<u32>(), *contig = R.contig.as<u32>(), *start = R.start.as<u32>(),
+            *group = R.group.as<u32>(), *gidx = R.gidx.as<u32>();
+  u64 n_seg = 0;
+  CKR(gvs_build_segments(ctx, read, n, ctx->seg_start, ctx->flags_c, &n_seg));
+  ctx->n_seg = n_seg;
+  const u32* row_seg = ctx->flags_c.as<u32>();
+  const u32* seg_start = ctx->seg_start.as<u32>();
+  // carve scratch
+  u64 words = n * 9 + (n_seg + 1) * 8 + 64;
+  CKR(gvs_reserve(ctx, ctx->diag_scratch, words * 4 + n * 2 + (n_seg + 1) * 4));
+  u32* w = ctx->diag_scratch.as<u32>();
+  DiagScratch D;
+  D.row_cnt = w; w += n;
+  D.cidx = w; w += n + 1;
+  D.keep_excl = w; w += n;
+  D.cand_row = w; w += n;
+  D.cand_voff = w; w += n;
+  D.v_pos = w; w += n;
+  D.v_start = w; w += n;
+  D.v_group = w; w += n;
+  D.cand_good = w; w += n;
+  D.seg_chunk = w; w += n_seg;
+  D.seg_ndist = w; w += n_seg;
+  D.seg_cap = w; w += n_seg;
+  D.seg_best = w; w += n_seg;
+  D.seg_good = w; w += n_seg;
+  D.best_excl = w; w += n_seg + 1;
+  D.tie_seg = w; w += n_seg;
+  u8* bb = (u8*)(ctx->diag_scratch.as<u32>() + words);
+  D.cand_dir = bb; bb += n;
+  D.seg_hap = bb; bb += n_seg;
+  D.seg_dir = bb; bb += n_seg;
+  D.seg_tie = bb; bb += n_seg;
+
+  LAUNCH(k_seg_info, (unsigned)cdiv(n_seg, 256), 256, 0, read, seg_start, (u32)n_seg, ctx->chunk_first.as<u64>(),
+         ctx->chunk_hap.as<u8>(), ctx->n_chunks, D.seg_chunk, D.seg_hap, D.seg_ndist);
+  LAUNCH(k_row_first, (unsigned)cdiv(n, 256), 256, 0, contig, row_seg, seg_start, n, D.row_cnt, D.seg_ndist);
+  // candidates: first rows whose contig is in the read's haplotype and has >= 2 hits (nim:82,147)
+  const u8* contig_hap = ctx->contig_hap.as<u8>();
+  u64* tot = ctx->counters.as<u64>() + 9;
+  {
+    const u32* rc = D.row_cnt;
+    const u8* sh = D.seg_hap;
+    u32 *cidx = D.cidx, *crow = D.cand_row, *cvoff = D.cand_voff;
+    auto f = [rc, contig, contig_hap, sh, row_seg] __device__(u64 j) -> u64 {
+      u32 c = rc[j];
+      return (c >= 2 && contig_hap[contig[j]] == sh[row_seg[j]]) ? ((1ull << 32) | c) : 0ull;
+    };
+    auto g = [cidx, crow, cvoff] __device__(u64 j, u64 ex, u64 v) {
+      cidx[j] = (u32)(ex >> 32);
+      if (v) {
+        crow[ex >> 32] = (u32)j;
+        cvoff[ex >> 32] = (u32)ex;
+      }
+    };
+    CKR((device_scan<u64>(ctx, n, f, g, OpSum(), tot)));
+  }
+  u64 packed = 0;
+  CKR(read_dev(ctx, tot, &packed));
+  u32 n_cand = (u32)(packed >> 32);
+  CK(cudaMemcpyAsync(D.cidx + n, &n_cand, 4, cudaMemcpyHostToDevice, ctx->stream));
+  const u32 SMALL_MAX = 768;
+  if (n_cand) {
+    LAUNCH(k_cand_gather, (unsigned)cdiv((u64)n_cand * 32, 256), 256, 0, D.cand_row, D.cand_voff, n_cand, contig, pos, start,
+           group, row_seg, seg_start, D.v_pos, D.v_start, D.v_group);
+    LAUNCH(k_cand_vote<32>, (unsigned)cdiv(n_cand, 4), 128, 0, D.cand_row, D.cand_voff, n_cand, D.row_cnt, D.v_pos,
+           D.v_start, D.v_group, SMALL_MAX, D.cand_good, D.cand_dir);
+    LAUNCH(k_cand_vote<1024>, n_cand, 1024, 0, D.cand_row, D.cand_voff, n_cand, D.row_cnt, D.v_pos, D.v_start, D.v_group,
+           SMALL_MAX, D.cand_good, D.cand_dir);
+  }
+  LAUNCH(k_seg_best, (unsigned)cdiv(n_seg, 256), 256, 0, (u32)n_seg, seg_start, D.cidx, D.cand_row, D.row_cnt, contig,
+         D.cand_good, D.cand_dir, D.seg_best, D.seg_good, D.seg_dir, D.seg_tie);
+  // ---- ties: Table capacity at the start of each read (sticky within a chunk) ----
+  u32* tie_tot = (u32*)(ctx->counters.as<u64>() + 10);
+  {
+    const u8* st = D.seg_tie;
+    u32* ts = D.tie_seg;
+    auto f = [st] __device__(u64 s) -> u32 { return st[s]; };
+    auto g = [ts] __device__(u64 s, u32 ex, u32 v) { if (v) ts[ex] = (u32)s; };
+    CKR((device_scan<u32>(ctx, n_seg, f, g, OpSum(), tie_tot)));
+  }
+  u32 n_tie = 0;
+  CKR(read_dev(ctx, tie_tot, &n_tie));
+  if (n_tie) {
+    const u32 *sc = D.seg_chunk, *nd = D.seg_ndist;
+    u32* cap = D.seg_cap;
+    u64* mx = ctx->counters.as<u64>() + 11;
+    auto f = [sc, nd] __device__(u64 s) -> u64 { return ((u64)(sc[s] + 1) << 32) | cap_needed(nd[s]); };
+    auto g = [sc, cap] __device__(u64 s, u64 ex, u64 v) {
+      cap[s] = ((u32)(ex >> 32) == sc[s] + 1) ? (u32)ex : 64u;  // capacity left by earlier reads of the chunk
+    };
+    CKR((device_scan<u64>(ctx, n_seg, f, g, OpMax(), mx)));
+    u64 mxv = 0;
+    CKR(read_dev(ctx, mx, &mxv));
+    // any read may itself grow the table while it is replayed: bound by the largest need overall
+    u32 maxcap = 64;
+    {
+      // the u64 max is dominated by the chunk id; take a safe bound from the largest segment instead
+      u32 max_nd = 0;
+      const u32* ndp = D.seg_ndist;
+      u32* mnd = (u32*)(ctx->counters.as<u64>() + 12);
+      auto f2 = [ndp] __device__(u64 s) -> u32 { return ndp[s]; };
+      auto g2 = [] __device__(u64 s, u32 ex, u32 v) {};
+      CKR((device_scan<u32>(ctx, n_seg, f2, g2, OpMax(), mnd)));
+      CKR(read_dev(ctx, mnd, &max_nd));
+      maxcap = cap_needed(max_nd) * 2;
+    }
+    DevBuf& sb = ctx->scan_tmp2;
+    CKR(gvs_reserve(ctx, sb, (u64)n_tie * 2 * maxcap * 4));
+    LAUNCH(k_seg_tie, (unsigned)cdiv(n_tie, 64), 64, 0, D.tie_seg, n_tie, seg_start, D.seg_cap, D.cidx, D.cand_row, D.row_cnt,
+           contig, ctx->contig_hash.as<u32>(), D.cand_good, D.cand_dir, sb.as<u32>(), maxcap, D.seg_best, D.seg_dir);
+  }
+  // ---- kept rows + best list ----
+  u32* kt = (u32*)(ctx->counters.as<u64>() + 13);
+  {
+    const u32* sbest = D.seg_best;
+    u32* ke = D.keep_excl;
+    auto f = [sbest, row_seg, contig] __device__(u64 j) -> u32 { return sbest[row_seg[j]] == contig[j] ? 1u : 0u; };
+    auto g = [ke] __device__(u64 j, u32 ex, u32 v) { ke[j] = ex; };
+    CKR((device_scan<u32>(ctx, n, f, g, OpSum(), kt)));
+  }
+  u32* bt = (u32*)(ctx->counters.as<u64>() + 14);
+  {
+    const u32* sbest = D.seg_best;
+    u32* be = D.best_excl;
+    auto f = [sbest] __device__(u64 s) -> u32 { return sbest[s] != NOBEST ? 1u : 0u; };
+    auto g = [be] __device__(u64 s, u32 ex, u32 v) { be[s] = ex; };
+    CKR((device_scan<u32>(ctx, n_seg, f, g, OpSum(), bt)));
+  }
+  u32 n_kept = 0, n_best = 0;
+  CKR(read_dev(ctx, kt, &n_kept));
+  CKR(read_dev(ctx, bt, &n_best));
+  CKR(gvs_reserve_rows(ctx, ctx->kept, n_kept));
+  CKR(gvs_reserve(ctx, ctx->best_read, (u64)n_best * 4));
+  CKR(gvs_reserve(ctx, ctx->best_contig, (u64)n_best * 4));
+  CKR(gvs_reserve(ctx, ctx->best_good, (u64)n_best * 4));
+  CKR(gvs_reserve(ctx, ctx->best_dir, (u64)n_best));
+  LAUNCH(k_keep_rows, (unsigned)cdiv(n, 256), 256, 0, n, D.keep_excl, row_seg, D.seg_best, read, pos, contig, start, group, gidx,
+         ctx->kept.read.as<u32>(), ctx->kept.pos.as<u32>(), ctx->kept.contig.as<u32>(), ctx->kept.start.as<u32>(),
+         ctx->kept.group.as<u32>(), ctx->kept.gidx.as<u32>());
+  LAUNCH(k_best_rows, (unsigned)cdiv(n_seg, 256), 256, 0, (u32)n_seg, D.best_excl, D.seg_best, D.seg_good, D.seg_dir, seg_start,
+         read, ctx->best_read.as<u32>(), ctx->best_contig.as<u32>(), ctx->best_good.as<u32>(), ctx->best_dir.as<u8>());
+  ctx->kept.n = n_kept;
+  ctx->n_best = n_best;
+  *n_best_out = n_best;
+  *n_kept_out = n_kept;
+  return 0;
+}
+
+extern "C" int gvs_diag_filter(gvs_ctx* ctx, const uint8_t* contig_hap, const uint32_t* contig_hash, uint64_t* n_best,
+                               uint64_t* n_kept) {
+  if (!ctx) return GVS_E_ARG;
+  if (!ctx->match_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_diag_filter before gvs_match");
+  if (!contig_hap || !contig_hash) return gvs_fail(ctx, GVS_E_ARG, "null contig tables");
+  CK(cudaSetDevice(ctx->device));
+  ctx->diag_ready = false;
+  ctx->val_ready = false;
+  CKR(to_dev(ctx, ctx->contig_hap, contig_hap, ctx->n_contigs));
+  CKR(to_dev(ctx, ctx->contig_hash, contig_hash, ctx->n_contigs));
+  u64 nb = 0, nk = 0;
+  CKR(diag_impl(ctx, &nb, &nk));
+  if (n_best) *n_best = nb;
+  if (n_kept) *n_kept = nk;
+  ctx->diag_ready = true;
+  return 0;
+}
+
+extern "C" int gvs_best_get(gvs_ctx* ctx, uint32_t* read_idx, uint32_t* contig, uint32_t* ngood, uint8_t* dir) {
+  if (!ctx) return GVS_E_ARG;
+  if (!ctx->diag_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_best_get before gvs_diag_filter");
+  CK(cudaSetDevice(ctx->device));
+  u64 n = ctx->n_best;
+  if (n == 0) return 0;
+  if (read_idx) CK(cudaMemcpyAsync(read_idx, ctx->best_read.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (contig) CK(cudaMemcpyAsync(contig, ctx->best_contig.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ngood) CK(cudaMemcpyAsync(ngood, ctx->best_good.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dir) CK(cudaMemcpyAsync(dir, ctx->best_dir.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}

@@ -327,15 +327,6 @@ __global__ void __launch_bounds__(256) k_emit_rows(const u32* __restrict__ hread
   r_gidx[out] = loc_gidx[row];
 }
 
-static int reserve_rows(gvs_ctx* ctx, Rows& r, u64 n) {
-  CKR(gvs_reserve(ctx, r.read, n * 4));
-  CKR(gvs_reserve(ctx, r.pos, n * 4));
-  CKR(gvs_reserve(ctx, r.contig, n * 4));
-  CKR(gvs_reserve(ctx, r.start, n * 4));
-  CKR(gvs_reserve(ctx, r.group, n * 4));
-  CKR(gvs_reserve(ctx, r.gidx, n * 4));
-  return 0;
-}
 
 static int match_once(gvs_ctx* ctx, u64 n_tiles, bool* overflow, u64* need) {
   u64* counters = ctx->counters.as<u64>();
@@ -463,7 +454,7 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
   u64 packed_total = 0;
   CKR(read_dev(ctx, tot, &packed_total));
   u64 n_rows = packed_total >> 32;
-  CKR(reserve_rows(ctx, ctx->rows, n_rows));
+  CKR(gvs_reserve_rows(ctx, ctx->rows, n_rows));
   LAUNCH(k_emit_rows, (unsigned)cdiv(nh, 256), 256, 0, ctx->ohit_read.as<u32>(), ctx->ohit_w.as<u32>(),
          ctx->ohit_row.as<u32>(), fl, pex, sb, nh, ctx->loc_contig.as<u32>(), ctx->loc_start.as<u32>(),
          ctx->loc_group.as<u32>(), ctx->loc_gidx.as<u32>(), ctx->rows.read.as<u32>(), ctx->rows.pos.as<u32>(),

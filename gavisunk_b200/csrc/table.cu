@@ -114,10 +114,8 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
 }
 
 // dense group index by first appearance of (contig, group) in .loc row order
-static int build_group_index_body(gvs_ctx* ctx, DevBuf& gk, DevBuf& gm, DevBuf& rep, DevBuf& dense, u64 slots) {
-  u64 n = ctx->n_loc;
-  const u32* contig = ctx->loc_contig.as<u32>();
-  const u32* group = ctx->loc_group.as<u32>();
+static int build_group_index_body(gvs_ctx* ctx, const u32* contig, const u32* group, u64 n, u32* gidx_out, DevBuf& gk,
+                                  DevBuf& gm, DevBuf& rep, DevBuf& dense, u64 slots) {
   LAUNCH(k_fill_u64, grid_for(ctx, slots, 256), 256, 0, gk.as<u64>(), slots, GVS_EMPTY_KEY);
   LAUNCH(k_fill_u32, grid_for(ctx, slots, 256), 256, 0, gm.as<u32>(), slots, 0xFFFFFFFFu);
   LAUNCH(k_grp_insert, grid_for(ctx, n, 256), 256, 0, contig, group, n, gk.as<u64>(), gm.as<u32>(), slots);
@@ -133,15 +131,15 @@ static int build_group_index_body(gvs_ctx* ctx, DevBuf& gk, DevBuf& gm, DevBuf& 
   ctx->n_groups = ng;
   CKR(gvs_reserve(ctx, ctx->grp_contig, (u64)ng * sizeof(u32)));
   CKR(gvs_reserve(ctx, ctx->grp_start, (u64)ng * sizeof(u32)));
-  LAUNCH(k_grp_fill, grid_for(ctx, n, 256), 256, 0, repp, densep, n, ctx->loc_gidx.as<u32>(), contig, group,
+  LAUNCH(k_grp_fill, grid_for(ctx, n, 256), 256, 0, repp, densep, n, gidx_out, contig, group,
          ctx->grp_contig.as<u32>(), ctx->grp_start.as<u32>());
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
-static int build_group_index(gvs_ctx* ctx) {
-  u64 n = ctx->n_loc;
-  CKR(gvs_reserve(ctx, ctx->loc_gidx, n * sizeof(u32)));
+// dense index of the distinct (contig, group) pairs of n rows, in order of first appearance;
+// fills gidx_out[n], ctx->n_groups, ctx->grp_contig / grp_start
+int gvs_group_index_rows(gvs_ctx* ctx, const u32* contig, const u32* group, u64 n, u32* gidx_out) {
   CKR(gvs_reserve(ctx, ctx->counters, 64 * sizeof(u64)));
   if (n == 0) {
     ctx->n_groups = 0;
@@ -153,13 +151,16 @@ static int build_group_index(gvs_ctx* ctx) {
   if (!rc) rc = gvs_reserve(ctx, gm, slots * sizeof(u32));
   if (!rc) rc = gvs_reserve(ctx, rep, n * sizeof(u32));
   if (!rc) rc = gvs_reserve(ctx, dense, n * sizeof(u32));
-  if (!rc) rc = build_group_index_body(ctx, gk, gm, rep, dense, slots);
+  if (!rc) rc = build_group_index_body(ctx, contig, group, n, gidx_out, gk, gm, rep, dense, slots);
   cudaStreamSynchronize(ctx->stream);
   gvs_release(gk); gvs_release(gm); gvs_release(rep); gvs_release(dense);
   return rc;
 }
 
-int gvs_group_index_impl(gvs_ctx* ctx) { return build_group_index(ctx); }
+static int build_group_index(gvs_ctx* ctx) {
+  CKR(gvs_reserve(ctx, ctx->loc_gidx, ctx->n_loc * sizeof(u32)));
+  return gvs_group_index_rows(ctx, ctx->loc_contig.as<u32>(), ctx->loc_group.as<u32>(), ctx->n_loc, ctx->loc_gidx.as<u32>());
+}
 
 // ---- C ABI ---------------------------------------------------------------------------------
 extern "C" int gvs_db_load_loc(gvs_ctx* ctx, const uint64_t* db_kmer, uint64_t n_db, const uint64_t* loc_kmer,
@@ -188,6 +189,8 @@ extern "C" int gvs_db_load_loc(gvs_ctx* ctx, const uint64_t* db_kmer, uint64_t n
   gvs_release(dbk);
   if (rc) return rc;
   ctx->db_ready = true;
+  ctx->groups_ready = true;
+  ctx->gt_slots = 0;
   return 0;
 }
 

@@ -3,9 +3,6 @@
 #include "common.cuh"
 #define NOTYET(name) return gvs_fail(ctx, GVS_E_STATE, name ": not implemented yet")
 extern "C" {
-int gvs_db_build(gvs_ctx* ctx, const uint8_t*, const uint64_t*, uint32_t, int) { NOTYET("gvs_db_build"); }
-int gvs_diag_filter(gvs_ctx* ctx, const uint8_t*, const uint32_t*, uint64_t*, uint64_t*) { NOTYET("gvs_diag_filter"); }
-int gvs_best_get(gvs_ctx* ctx, uint32_t*, uint32_t*, uint32_t*, uint8_t*) { NOTYET("gvs_best_get"); }
 int gvs_group_hist(gvs_ctx* ctx, int, int32_t**) { NOTYET("gvs_group_hist"); }
 int gvs_hist_mode(gvs_ctx* ctx, int64_t*) { NOTYET("gvs_hist_mode"); }
 int gvs_bad_groups(gvs_ctx* ctx, const int64_t*, uint64_t*) { NOTYET("gvs_bad_groups"); }
@@ -19,7 +16,4 @@ int gvs_intervals_get(gvs_ctx* ctx, uint32_t*, uint32_t*, uint32_t*) { NOTYET("g
 int gvs_gaps(gvs_ctx* ctx, const uint32_t*, uint64_t*, uint64_t*) { NOTYET("gvs_gaps"); }
 int gvs_gaps_get(gvs_ctx* ctx, uint32_t*, uint32_t*, uint32_t*, uint32_t*) { NOTYET("gvs_gaps_get"); }
 int gvs_covprob_table(gvs_ctx* ctx, const int64_t*, const int64_t*, uint32_t, double, double, double*) { NOTYET("gvs_covprob_table"); }
-int gvs_synth_assembly(gvs_ctx* ctx, uint8_t*, const uint64_t*, uint32_t, double, double, uint64_t) { NOTYET("gvs_synth_assembly"); }
-int gvs_synth_reads_plan(gvs_ctx* ctx, const uint64_t*, uint32_t, uint32_t, uint64_t, double, double, uint32_t, uint32_t, uint64_t, uint64_t*, uint64_t*) { NOTYET("gvs_synth_reads_plan"); }
-int gvs_synth_reads_fill(gvs_ctx* ctx, const uint8_t*, uint8_t*, const uint64_t*, uint64_t) { NOTYET("gvs_synth_reads_fill"); }
 }

@@ -220,6 +220,26 @@ class Engine:
         self._ck(self.lib.gvs_reads_set(self.ctx, C.c_void_p(seq_ptr), C.c_void_p(off_ptr), n_reads, _ptr(chunk_first),
                                         _ptr(chunk_hap), len(chunk_hap), 1))
 
+    def set_reads_meta(self, read_len, chunk_first=None, chunk_hap=None):
+        """Read table without sequences ({hap}.rlen, workflow/src/rlen.nim:13-14)."""
+        read_len = _c(read_len, np.uint32)
+        n = len(read_len)
+        chunk_first = _c([0, n] if chunk_first is None else chunk_first, np.uint64)
+        chunk_hap = _c([0] * (len(chunk_first) - 1) if chunk_hap is None else chunk_hap, np.uint8)
+        self.n_reads = n
+        self._ck(self.lib.gvs_reads_meta(self.ctx, _ptr(read_len), n, _ptr(chunk_first), _ptr(chunk_hap), len(chunk_hap)))
+
+    def set_rows(self, which: int, read, pos, contig, start, group, n_contigs: Optional[int] = None):
+        """Rows parsed from a .sunkpos file (input of diag_filter_v3 / badsunks / process-by-contig)."""
+        cols = [_c(a, np.uint32) for a in (read, pos, contig, start, group)]
+        n = len(cols[0])
+        nc = len(self.contig_names) if n_contigs is None else n_contigs
+        self._ck(self.lib.gvs_rows_set(self.ctx, which, *[_ptr(a) for a in cols], n, nc))
+        if which == 0:
+            self.n_rows = n
+        else:
+            self.n_kept = n
+
     # ------------------------------------------------------------------------------------
     # stages
     # ------------------------------------------------------------------------------------

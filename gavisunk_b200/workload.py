@@ -1,0 +1,125 @@
+"""Synthetic workloads of BASELINE.json's configs, generated on the device.
+
+Used by bench.py and the GPU tests only.  torch is plumbing here: it owns the device buffers
+(assembly, reads, offsets) that are handed to libgavisunk_b200.so as raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+import torch
+
+from .engine import Engine
+
+# human chromosome lengths (Mbp, T2T-CHM13-like, chr1..22 + X), scaled to sum 3.1 Gbp
+_HUMAN_MBP = [248, 242, 201, 193, 182, 172, 160, 146, 150, 135, 135, 133, 114, 101, 100, 96, 84, 80, 62, 66, 45, 51, 154]
+
+
+@dataclass
+class Workload:
+    name: str
+    k: int
+    contig_names: List[str]
+    contig_len: np.ndarray          # per contig (both haps), uint64
+    contig_hap: np.ndarray          # uint8 per contig
+    asm: torch.Tensor               # uint8 device, hap1 contigs then hap2 contigs (+64 pad)
+    contig_off: torch.Tensor        # uint64 (as int64 tensor) device, n_contigs+1
+    reads: torch.Tensor = None      # uint8 device (+64 pad)
+    read_off: torch.Tensor = None   # int64 device, n_reads+1
+    n_reads: int = 0
+    total_bases: int = 0
+    chunk_first: np.ndarray = None
+    chunk_hap: np.ndarray = None
+    meta: dict = field(default_factory=dict)
+
+
+def _dev_ptr(t: torch.Tensor) -> int:
+    return int(t.data_ptr())
+
+
+def make_assembly(eng: Engine, contig_len_per_hap, snp_rate=1e-3, dup_frac=0.01, seed=1001, name="syn", device=None) -> Workload:
+    device = device or torch.device("cuda", eng.device)
+    cl = np.asarray(contig_len_per_hap, dtype=np.uint64)
+    nc = len(cl)
+    hap_len = int(cl.sum())
+    asm = torch.zeros(2 * hap_len + 64, dtype=torch.uint8, device=device)
+    eng._ck(eng.lib.gvs_synth_assembly(eng.ctx, C.c_void_p(_dev_ptr(asm)), cl.ctypes.data_as(C.c_void_p), nc,
+                                       float(snp_rate), float(dup_frac), int(seed)))
+    both = np.concatenate([cl, cl])
+    off = np.zeros(2 * nc + 1, dtype=np.int64)
+    off[1:] = np.cumsum(both.astype(np.int64))
+    names = [f"synH1_chr{i + 1}" for i in range(nc)] + [f"synH2_chr{i + 1}" for i in range(nc)]
+    hap = np.array([0] * nc + [1] * nc, dtype=np.uint8)
+    return Workload(name=name, k=eng.k, contig_names=names, contig_len=both, contig_hap=hap, asm=asm,
+                    contig_off=torch.from_numpy(off).to(device))
+
+
+def add_reads(eng: Engine, wl: Workload, coverage: float, n50: float = 50000.0, sigma: float = 0.8, len_min=1000,
+              len_max=1000000, seed=2001, nchunks=10, device=None) -> Workload:
+    """coverage = total read bases / haploid assembly size, split evenly across the two haps."""
+    device = device or wl.asm.device
+    nc = len(wl.contig_names) // 2
+    hap_len = int(wl.contig_len[:nc].sum())
+    mu = math.log(n50) - sigma * sigma           # length-weighted median of a log-normal = exp(mu + sigma^2)
+    mean_len = math.exp(mu + sigma * sigma / 2)
+    per_hap_bases = coverage * hap_len / 2
+    n_per_hap = max(1, int(round(per_hap_bases / mean_len)))
+    offs, totals = [], []
+    for hap in range(2):
+        ro = torch.zeros(n_per_hap + 1, dtype=torch.int64, device=device)
+        tot = C.c_uint64()
+        eng._ck(eng.lib.gvs_synth_reads_plan(eng.ctx, C.c_void_p(_dev_ptr(wl.contig_off)), hap * nc, (hap + 1) * nc,
+                                             n_per_hap, mu, sigma, len_min, len_max, seed + hap,
+                                             C.c_void_p(_dev_ptr(ro)), C.byref(tot)))
+        offs.append(ro)
+        totals.append(int(tot.value))
+        if hap == 0:
+            # hap-1 reads are filled right away: the plan state is per call
+            pad0 = (-totals[0]) % 16
+            total0 = totals[0]
+            est = int(total0 * 2.2) + 4096
+            reads = torch.zeros(est + 64, dtype=torch.uint8, device=device)
+            eng._ck(eng.lib.gvs_synth_reads_fill(eng.ctx, C.c_void_p(_dev_ptr(wl.asm)), C.c_void_p(_dev_ptr(reads)),
+                                                 C.c_void_p(_dev_ptr(ro)), n_per_hap))
+    total = totals[0] + totals[1]
+    if total + 64 > reads.numel():
+        bigger = torch.zeros(total + 64, dtype=torch.uint8, device=device)
+        bigger[:totals[0]] = reads[:totals[0]]
+        reads = bigger
+    ro2 = offs[1] + totals[0]
+    eng._ck(eng.lib.gvs_synth_reads_fill(eng.ctx, C.c_void_p(_dev_ptr(wl.asm)), C.c_void_p(_dev_ptr(reads)),
+                                         C.c_void_p(_dev_ptr(ro2)), n_per_hap))
+    read_off = torch.cat([offs[0][:-1], ro2]).contiguous()
+    n_reads = 2 * n_per_hap
+    cf, ch = [], []
+    for hap in range(2):
+        for c in range(nchunks):
+            cf.append(hap * n_per_hap + (c * n_per_hap) // nchunks)
+            ch.append(hap)
+    cf.append(n_reads)
+    wl.reads = reads[:total + 64] if reads.numel() > total + 64 else reads
+    wl.read_off = read_off
+    wl.n_reads = n_reads
+    wl.total_bases = total
+    wl.chunk_first = np.asarray(cf, dtype=np.uint64)
+    wl.chunk_hap = np.asarray(ch, dtype=np.uint8)
+    wl.meta.update(coverage=coverage, n50=n50, sigma=sigma, reads_per_hap=n_per_hap, nchunks=nchunks)
+    torch.cuda.synchronize(device)
+    return wl
+
+
+def human_contigs(total_mbp=3100.0):
+    s = sum(_HUMAN_MBP)
+    return [int(x / s * total_mbp * 1e6) for x in _HUMAN_MBP]
+
+
+def bind_reads(eng: Engine, wl: Workload):
+    eng.set_reads_device(_dev_ptr(wl.reads), _dev_ptr(wl.read_off), wl.n_reads, wl.chunk_first, wl.chunk_hap)
+
+
+def build_db(eng: Engine, wl: Workload):
+    eng.build_db_device(_dev_ptr(wl.asm), _dev_ptr(wl.contig_off), wl.contig_names)

@@ -119,6 +119,19 @@ int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* read_off, ui
                   const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks,
                   int on_device);
 
+/* Read table without sequences (the CLI shims that start from .sunkpos / .rlen files):
+ * read_len[n_reads] = column 2 of {hap}.rlen (workflow/src/rlen.nim:13-14), chunk layout as above. */
+int gvs_reads_meta(gvs_ctx* ctx, const uint32_t* read_len, uint64_t n_reads, const uint64_t* chunk_first,
+                   const uint8_t* chunk_hap, uint32_t n_chunks);
+/* Rows parsed from a .sunkpos file instead of produced by the previous stage: which = 0 replaces
+ * the output of gvs_match (input of gvs_diag_filter: workflow/src/diag_filter_v3.nim:63), which = 1
+ * replaces the output of gvs_diag_filter (input of gvs_group_hist / gvs_validate:
+ * badsunks_AR.py:20, process-by-contig_lowmem_AR.py:60).  Rows of one read must be contiguous.
+ * With a database loaded every (contig, group) must exist in it; without one the group index is
+ * derived from the rows (first appearance order) and n_contigs sizes the contig tables. */
+int gvs_rows_set(gvs_ctx* ctx, int which, const uint32_t* read_idx, const uint32_t* pos, const uint32_t* contig,
+                 const uint32_t* start, const uint32_t* group, uint64_t n_rows, uint32_t n_contigs);
+
 /* ------------------------------------------------------------------------------------------ */
 /* stages (must be called in this order; each consumes the previous stage's device results)    */
 /* ------------------------------------------------------------------------------------------ */
