@@ -278,6 +278,34 @@ class Engine:
                                        _ptr(out["dir"])))
         return out
 
+    def set_contigs(self, contig_hap: Sequence[int]):
+        ch = _c(contig_hap, np.uint8)
+        hh = np.array([nim_hash(n) for n in self.contig_names], dtype=np.uint32)
+        self._ck(self.lib.gvs_contigs_set(self.ctx, _ptr(ch), _ptr(hh) if len(hh) == len(ch) else None, len(ch)))
+
+    def run_all(self, contig_hap: Sequence[int], min_read_len: int = 10000, allreduce_hist=None, gather_forests=None):
+        """The fused hot path on the reads bound to this engine: match -> diag filter -> bad-SUNK
+        histogram -> validation -> contig-wide components -> intervals.  With several GPUs
+        `allreduce_hist(ptr, n_groups)` sums the int32 histogram across ranks in place and
+        `gather_forests(ptr, n_groups)` returns device pointers of the peers' parent arrays."""
+        self.match()
+        self.diag_filter(contig_hap)
+        hp = self.group_hist()
+        if allreduce_hist is not None:
+            allreduce_hist(hp, self.db_groups())
+        self.bad_groups()
+        self.validate(min_read_len)
+        pp = self.components_local()
+        if gather_forests is not None:
+            for peer in gather_forests(pp, self.db_groups()):
+                self.components_merge(peer)
+        return self.intervals()
+
+    def db_groups(self) -> int:
+        a, b = C.c_uint64(), C.c_uint64()
+        rc = self.lib.gvs_db_size(self.ctx, C.byref(a), C.byref(b))
+        return int(b.value) if rc == 0 else 0
+
     def group_hist(self, accumulate: bool = False) -> int:
         """badsunks_AR.py:20-27 histogram; returns the device pointer of the int32[n_groups] array."""
         p = C.c_void_p()

@@ -156,6 +156,12 @@ int gvs_diag_filter(gvs_ctx* ctx, const uint8_t* contig_hap, const uint32_t* con
 int gvs_best_get(gvs_ctx* ctx, uint32_t* read_idx, uint32_t* contig, uint32_t* ngood,
                  uint8_t* dir);
 
+/* Contig tables for callers that skip gvs_diag_filter (which sets them itself): contig_hap as
+ * above (badsunks_AR.py:28-33 "correct" = contig listed in the haplotype's .fai), contig_hash may
+ * be NULL. */
+int gvs_contigs_set(gvs_ctx* ctx, const uint8_t* contig_hap, const uint32_t* contig_hash,
+                    uint32_t n_contigs);
+
 /* badsunks_AR.py:20-52 histogram: rows per (contig, group) over the kept rows, accumulated into a
  * device array of n_groups int32 (index = group_index of gvs_db_export).  *hist_dev receives the
  * device pointer so that the caller can all-reduce it across GPUs (NCCL) before

@@ -1,0 +1,107 @@
+"""GPU parity of the post-match stages against the oracle's line-by-line restatement of
+badsunks_AR.py, process-by-contig_lowmem_AR.py and get_gaps.py (the scripts themselves cannot be
+imported: graph_tool / pyranges are absent; DESIGN.md "Oracle")."""
+from collections import defaultdict
+
+import numpy as np
+import pytest
+
+import gavisunk_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _pipeline_case(seed, contig_lens, cov, n50, min_len, k=20, snp=2e-3, dup=0.02, nchunks=3):
+    import torch
+    from gavisunk_b200.engine import Engine
+    from gavisunk_b200 import workload as W
+    eng = Engine(k)
+    wl = W.make_assembly(eng, contig_lens, snp_rate=snp, dup_frac=dup, seed=seed)
+    W.build_db(eng, wl)
+    W.add_reads(eng, wl, coverage=cov, n50=n50, sigma=0.6, len_min=200, len_max=400000, seed=seed + 1, nchunks=nchunks)
+    W.bind_reads(eng, wl)
+    iv = eng.run_all(wl.contig_hap, min_read_len=min_len)
+    return eng, wl, iv
+
+
+def _check_against_oracle(eng, wl, iv, min_len):
+    names = wl.contig_names
+    kept = eng.rows(1)
+    off = wl.read_off.cpu().numpy()
+    rname = lambda r: f"r{int(r):09d}"
+    rows = [(rname(r), int(p), names[c], int(s), int(g)) for r, p, c, s, g in
+            zip(kept["read"], kept["pos"], kept["contig"], kept["start"], kept["group"])]
+    rlen = {rname(r): int(off[r + 1] - off[r]) for r in range(wl.n_reads)}
+    nreads_hap = wl.n_reads // 2
+    hap_of_read = lambda r: 0 if r < nreads_hap else 1
+    nc = len(names) // 2
+    hapc = [set(names[:nc]), set(names[nc:])]
+    rows_h = [[], []]
+    for r, row in zip(kept["read"], rows):
+        rows_h[hap_of_read(int(r))].append(row)
+    # ---- bad SUNKs (badsunks_AR.py) ----
+    exp_bad = O.bad_sunks(rows_h[0], hapc[0], rows_h[1], hapc[1])
+    db = eng.db_export()
+    gidx_to = {}
+    for c, g, gi in zip(db["contig"], db["group"], db["gidx"]):
+        gidx_to[int(gi)] = (names[c], int(g))
+    got_bad = {gidx_to[int(g)] for g in eng.bad_list()}
+    assert got_bad == exp_bad
+    assert len(exp_bad) > 0
+    # ---- per-contig validation (process-by-contig_lowmem_AR.py) ----
+    pairs = eng.pairs()
+    got_inter = defaultdict(list)
+    for r, c, g in zip(pairs["read"], pairs["contig"], pairs["group"]):
+        got_inter[names[c]].append((int(g), rname(r)))
+    got_bed = defaultdict(list)
+    for c, s, e in zip(iv["contig"], iv["start"], iv["end"]):
+        got_bed[names[c]].append((names[c], int(s), int(e)))
+    by_contig = defaultdict(list)
+    for row in rows:
+        by_contig[row[2]].append(row)
+    n_valid_reads = 0
+    beds = {}
+    for ctg in names:
+        inter, bed = O.process_by_contig(by_contig.get(ctg, []), rlen, exp_bad, ctg, minlen=min_len) if ctg in by_contig else (None, None)
+        assert got_inter.get(ctg, []) == (inter or []), ctg
+        assert got_bed.get(ctg, []) == (bed or []), ctg
+        if bed is not None:
+            beds[ctg] = [(s, e) for _, s, e in bed]
+        n_valid_reads += len({r for _, r in (inter or [])})
+    assert n_valid_reads > 20
+    assert sum(len(v) for v in got_bed.values()) > 0
+    # ---- gaps (get_gaps.py) ----
+    gaps, nodata = eng.gaps(wl.contig_len.astype(np.uint32))
+    for hap in range(2):
+        fai = [(names[c], int(wl.contig_len[c])) for c in range(hap * nc, (hap + 1) * nc)]
+        eg, en = O.get_gaps(fai, beds)
+        gg = [(names[c], int(s), int(e)) for c, s, e in zip(gaps["contig"], gaps["start"], gaps["end"]) if names[c] in hapc[hap]]
+        gn = [(names[c], 0, int(wl.contig_len[c])) for c in nodata if names[c] in hapc[hap]]
+        assert gg == eg
+        assert gn == en
+    return n_valid_reads
+
+
+def test_pipeline_small_reads():
+    eng, wl, iv = _pipeline_case(seed=21, contig_lens=[400000, 250000, 3000], cov=24.0, n50=12000, min_len=3000)
+    _check_against_oracle(eng, wl, iv, 3000)
+
+
+def test_pipeline_reference_minlen():
+    """the reference's hard-coded 10 kb minimum read length (Q13) with longer reads"""
+    eng, wl, iv = _pipeline_case(seed=33, contig_lens=[900000], cov=20.0, n50=30000, min_len=10000, nchunks=4)
+    _check_against_oracle(eng, wl, iv, 10000)
+
+
+def test_pipeline_k31_dense():
+    eng, wl, iv = _pipeline_case(seed=5, contig_lens=[300000, 200000], cov=30.0, n50=15000, min_len=2000, k=31, snp=4e-3)
+    _check_against_oracle(eng, wl, iv, 2000)
+
+
+def test_validate_big_read_path():
+    """reads with more rows than fit shared memory go through the global-scratch kernel"""
+    eng, wl, iv = _pipeline_case(seed=77, contig_lens=[1500000], cov=8.0, n50=400000, min_len=10000, snp=3e-3, dup=0.0)
+    kept = eng.rows(1)
+    _, counts = np.unique(kept["read"], return_counts=True)
+    assert counts.max() > 512
+    _check_against_oracle(eng, wl, iv, 10000)
