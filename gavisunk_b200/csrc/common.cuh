@@ -54,7 +54,7 @@ struct gvs_ctx {
   DevBuf grp_contig, grp_start;                                  // per group (index = gidx)
   DevBuf tab_keys, tab_rows;                                     // open-addressed probe table
   u64 tab_slots = 0;                                             // power of two, buckets of 4
-  DevBuf filt;                                                   // 64-bit-word blocked Bloom filter
+  DevBuf filt;                                                   // 32-bit-word blocked Bloom filter
   u64 filt_words = 0;                                            // power of two
   DevBuf contig_hap, contig_hash, contig_len;
 
@@ -217,11 +217,19 @@ __host__ __device__ __forceinline__ u64 gvs_mix(u64 x) {
   x ^= x >> 32;
   return x;
 }
-// filter: word index from the low bits, two bit positions from a re-mix of the high half
-__host__ __device__ __forceinline__ u64 gvs_filt_word(u64 h, u64 filt_words) { return h & (filt_words - 1); }
-__host__ __device__ __forceinline__ u64 gvs_filt_bits(u64 h) {
-  u32 g = (u32)(h >> 32) * 0x85EBCA6Bu;
-  return (1ull << (g >> 26)) | (1ull << ((g >> 20) & 63));
+// filter: 32-bit hash of the canonical k-mer (two IMADs + two xorshift-multiply rounds); the word
+// index is h & mask, the two bit positions inside the 32-bit word come from one more multiply
+__host__ __device__ __forceinline__ u32 gvs_fhash(u64 key) {
+  u32 lo = (u32)key, hi = (u32)(key >> 32);
+  u32 h = (lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u + 0xC2B2AE3Du);
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  return h;
+}
+__host__ __device__ __forceinline__ u32 gvs_fbits(u32 h) {
+  u32 g = h * 0x297A2D39u;
+  return (1u << (g >> 27)) | (1u << ((g >> 22) & 31));
 }
 // table: bucket (4 slots = one 32-byte sector of keys) from bits 24.. of the hash
 __host__ __device__ __forceinline__ u64 gvs_tab_bucket(u64 h, u64 tab_slots) { return (h >> 24) & ((tab_slots >> 2) - 1); }

@@ -27,7 +27,7 @@ __global__ void k_tab_mark_db(const u64* __restrict__ kmer, u64 n, u64* keys, u3
     atomicOr(&rows[s], 0x80000000u);
   }
 }
-__global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slots, u64* filt, u64 filt_words) {
+__global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slots, u32* filt, u64 filt_words) {
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
     u64 key = keys[s];
     if (key == GVS_EMPTY_KEY) continue;
@@ -38,8 +38,8 @@ __global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slot
       continue;
     }
     rows[s] = r ? r - 1 : GVS_ROW_MISSING;
-    u64 h = gvs_mix(key);
-    atomicOr((unsigned long long*)&filt[gvs_filt_word(h, filt_words)], (unsigned long long)gvs_filt_bits(h));
+    u32 h = gvs_fhash(key);
+    atomicOr(&filt[h & (u32)(filt_words - 1)], gvs_fbits(h));
   }
 }
 
@@ -92,24 +92,24 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
   ctx->tab_slots = slots;
   CKR(gvs_reserve(ctx, ctx->tab_keys, slots * sizeof(u64)));
   CKR(gvs_reserve(ctx, ctx->tab_rows, slots * sizeof(u32)));
-  // filter: ~32 bits per key, between 2^14 and 2^23 words (64 MiB: stays L2-resident on B200)
-  u64 fw = next_pow2(cdiv((n_loc ? n_loc : 1) * 32, 64));
-  if (fw < (1ull << 14)) fw = 1ull << 14;
-  if (fw > (1ull << 23)) fw = 1ull << 23;
+  // filter: 32..64 bits per key in 32-bit words, capped at 2^24 words (64 MiB: L2-resident on B200)
+  u64 fw = next_pow2(n_loc ? n_loc : 1);
+  if (fw < (1ull << 12)) fw = 1ull << 12;
+  if (fw > (1ull << 24)) fw = 1ull << 24;
   ctx->filt_words = fw;
-  CKR(gvs_reserve(ctx, ctx->filt, fw * sizeof(u64)));
+  CKR(gvs_reserve(ctx, ctx->filt, fw * sizeof(u32)));
   u64* keys = ctx->tab_keys.as<u64>();
   u32* rows = ctx->tab_rows.as<u32>();
   LAUNCH(k_fill_u64, grid_for(ctx, slots, 256), 256, 0, keys, slots, GVS_EMPTY_KEY);
   LAUNCH(k_fill_u32, grid_for(ctx, slots, 256), 256, 0, rows, slots, 0u);
-  LAUNCH(k_fill_u64, grid_for(ctx, fw, 256), 256, 0, ctx->filt.as<u64>(), fw, 0ull);
+  LAUNCH(k_fill_u32, grid_for(ctx, fw, 256), 256, 0, ctx->filt.as<u32>(), fw, 0u);
   if (n_loc) LAUNCH(k_tab_insert_loc, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
   if (d_db_kmer) {
     if (n_db) LAUNCH(k_tab_mark_db, grid_for(ctx, n_db, 256), 256, 0, d_db_kmer, n_db, keys, rows, slots);
   } else if (n_loc) {
     LAUNCH(k_tab_mark_db, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
   }
-  LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u64>(), fw);
+  LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u32>(), fw);
   return 0;
 }
 

@@ -1,7 +1,7 @@
 // table.cuh -- device-side view of the SUNK probe structures (shared by build and probe kernels)
 //
 // Layout in HBM (DESIGN.md "Data layout"):
-//   filt      u64[filt_words]   word-blocked Bloom filter, 2 bits per key inside ONE 64-bit word;
+//   filt      u32[filt_words]   word-blocked Bloom filter, 2 bits per key inside ONE 32-bit word;
 //                               sized to stay L2-resident (<= 64 MiB), probed once per read base
 //   tab_keys  u64[tab_slots]    open-addressed canonical k-mers, buckets of 4 slots = one 32-byte
 //                               sector, load factor <= 0.5, EMPTY = all ones (k <= 31 => < 2^62)
@@ -11,8 +11,6 @@
 #include "common.cuh"
 
 struct TabView {
-  const u64* __restrict__ filt;
-  u64 filt_words;
   const u64* __restrict__ keys;
   const u32* __restrict__ rows;
   u64 slots;
