@@ -2,14 +2,22 @@
 """bench.py -- BASELINE.json's metric: ONT read Gbp/s SUNK-matched + distance-validated.
 
 One "step" = one pass of the whole hot path (match -> best-contig filter -> bad-SUNK histogram ->
-inter-SUNK distance validation -> contig-wide intervals -> gaps) over one batch of
-synthetic reads that is already resident in HBM, against a SUNK database built on the GPU.
+inter-SUNK distance validation -> contig-wide components -> intervals -> gaps) over
+one batch of synthetic reads, against a SUNK database built on the GPU from a synthetic diploid
+assembly.  `value` is measured with the reads already resident in HBM; `e2e` goes through the same
+public API (gavisunk_b200.engine.Engine) with HOST buffers, host->device copy of the reads and
+device->host read of the results inside the timed region.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload s150|h3100|tiny] [--impl reference]
 
-N > 1: launched by torchrun, one rank per GPU; reads are sharded (each rank owns its own shard of
-the same size: weak scaling), the SUNK table is replicated; NCCL all-reduces the group-hit
-histogram and all-gathers the union-find forests.
+N > 1: launched by torchrun, one rank per GPU; every rank owns its own shard of reads of the same
+size (weak scaling), the SUNK table is replicated; NCCL all-reduces the group-hit histogram and
+all-gathers the union-find forests (the only two exchanges on the path).
+
+--impl reference: the reference's own executables (oracle/_ref: kmerpos_annot3, diag_filter_v3,
+diag_filter_step2, unmodified prebuilt binaries) on the host cores, one process per chunk with all
+cores busy, followed by the CPU port of the Python stages (oracle/gavisunk_oracle.py; the
+reference's scripts need graph_tool / pyranges which are not installed) -- on a bounded sample.
 """
 from __future__ import annotations
 
@@ -17,8 +25,10 @@ import argparse
 import json
 import math
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -29,32 +39,32 @@ import numpy as np  # noqa: E402
 
 METRIC = "ont_read_gbp_per_s_sunk_matched_validated"
 UNIT = "Gbp/s"
+STAGES = ("probe", "emit", "diag", "hist", "validate", "intervals")
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="s150", choices=["tiny", "s150", "h3100"])
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--asm-mbp", type=float, default=None, help="override haploid assembly size (Mbp)")
     ap.add_argument("--coverage", type=float, default=None, help="override read coverage per GPU shard")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-mbp", type=float, default=None)
+    ap.add_argument("--cpu-sample-mbp", type=float, default=None, help="read Mbp per CPU process of the baseline sample")
     return ap.parse_args()
 
 
 WORKLOADS = {
-    # name: (haploid Mbp, contigs, coverage per shard, N50, description)
     "tiny": dict(mbp=2.0, human=False, cov=30.0, n50=20000.0,
                  desc="synthetic 2 Mbp x2 diploid + 30x ONT-like reads (smoke size)"),
     "s150": dict(mbp=150.0, human=False, cov=30.0, n50=50000.0,
                  desc="synthetic 150 Mbp single-chromosome x2 diploid assembly + 30x simulated ONT reads (N50 ~50 kb)"),
     "h3100": dict(mbp=3100.0, human=True, cov=3.75, n50=100000.0,
-                  desc="synthetic 3.1 Gbp x2 diploid assembly, 23 contigs + ONT-like reads N50 ~100 kb, 3.75x (=30x/8) per GPU shard"),
+                  desc="synthetic 3.1 Gbp x2 diploid assembly (23 contigs) + ONT-like reads N50 ~100 kb, 3.75x (=30x/8) per GPU shard"),
 }
 
 
@@ -71,42 +81,46 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            time.sleep(0.25)  # let the first sample land before the timed region starts
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.12)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t_begin is not None and not (t_begin <= ts <= t_end + 0.06):
+                continue
             p = [x.strip() for x in r.split(",")]
             if len(p) < 7:
                 continue
             try:
                 sm.append(float(p[0]))
                 mx.append(float(p[1]))
+                pw.append(float(p[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, p[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return dict(sm_mhz=(float(np.median(sm)) if sm else None), sm_max_mhz=(max(mx) if mx else None),
-                    reasons=sorted(reasons), samples=len(sm))
+                    power_w_max=(max(pw) if pw else None), reasons=sorted(reasons), samples=len(sm))
 
 
 def build_workload(args, eng, rank):
@@ -130,12 +144,55 @@ def build_workload(args, eng, rank):
     return wl
 
 
-def run_step(eng, wl, bind, dist_ctx=None):
-    """one pass of the hot path; returns a small dict of result sizes"""
+class Collectives:
+    """The two NCCL exchanges of the path: sum of the per-group hit histogram and
+    all-gather of the union-find parent arrays.  torch tensors alias the library's device buffers
+    through the CUDA array interface, so NCCL works in place on them."""
+
+    def __init__(self, world, dev):
+        import torch
+        self.world = world
+        self.dev = dev
+        self.torch = torch
+        self._gather = None
+
+    def _alias(self, ptr, n, typestr):
+        torch = self.torch
+
+        class _A:
+            pass
+        a = _A()
+        a.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(ptr, False), version=2)
+        return torch.as_tensor(a, device=self.dev)
+
+    def allreduce_hist(self, ptr, n_groups):
+        import torch.distributed as dist
+        if self.world == 1 or n_groups == 0:
+            return
+        t = self._alias(ptr, n_groups, "<i4")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def gather_forests(self, ptr, n_groups):
+        import torch.distributed as dist
+        if self.world == 1 or n_groups == 0:
+            return []
+        torch = self.torch
+        mine = self._alias(ptr, n_groups, "<i4")  # uint32 payload moved as int32
+        if self._gather is None or self._gather.numel() != self.world * n_groups:
+            self._gather = torch.empty(self.world * n_groups, dtype=torch.int32, device=self.dev)
+        dist.all_gather_into_tensor(self._gather, mine)
+        rank = dist.get_rank()
+        return [int(self._gather.data_ptr()) + 4 * n_groups * r for r in range(self.world) if r != rank]
+
+
+def run_step(eng, wl, bind, coll):
+    """one pass of the hot path; returns the result sizes"""
     bind()
-    n_rows = eng.match()
-    n_best, n_kept = eng.diag_filter(wl.contig_hap)
-    return dict(rows=n_rows, best=n_best, kept=n_kept)
+    iv = eng.run_all(wl.contig_hap, min_read_len=10000, allreduce_hist=coll.allreduce_hist,
+                     gather_forests=coll.gather_forests)
+    gaps, nodata = eng.gaps(wl.contig_len.astype(np.uint32))
+    return dict(rows=eng.n_rows, best=eng.n_best, kept=eng.n_kept, bad_groups=eng.n_bad, validated_pairs=eng.n_pairs,
+                intervals=int(len(iv["contig"])), gaps=int(len(gaps["contig"])), nodata=int(len(nodata))), iv, gaps
 
 
 def main_b200(args):
@@ -148,12 +205,13 @@ def main_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     eng = Engine(args.k, device=local, stream=torch.cuda.current_stream().cuda_stream)
     wl = build_workload(args, eng, rank)
     n_sunks, n_groups = eng.db_size()
+    coll = Collectives(world, dev)
 
     def barrier():
         if world > 1:
@@ -162,22 +220,24 @@ def main_b200(args):
 
     bind = lambda: W.bind_reads(eng, wl)
     # ---- HBM-resident timing ----
-    for _ in range(args.warmup):
-        res = run_step(eng, wl, bind)
+    for _ in range(max(args.warmup, 3)):
+        res, iv, gaps = run_step(eng, wl, bind, coll)
     launches0 = eng.launches
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = {}
+    tb = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        res = run_step(eng, wl, bind)
-        for st in ("probe", "emit", "diag"):
+        res, iv, gaps = run_step(eng, wl, bind, coll)
+        for st in STAGES:
             stage_ms.setdefault(st, []).append(eng.stage_ms(st))
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    te = time.perf_counter()
+    clocks = sampler.stop(tb, te)
     ms = e0.elapsed_time(e1)
     launches = eng.launches - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -190,7 +250,7 @@ def main_b200(args):
     total_bases = float(bases.item())
     value = total_bases * args.steps / (ms_max * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (k_probe) ----
+    # ---- roofline of the dominant kernel (k_probe2) ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -201,13 +261,19 @@ def main_b200(args):
     off = wl.read_off.cpu().numpy()
     lens = np.diff(off)
     windows = int(np.maximum(lens - k + 1, 0).sum())
-    probe_bytes = float(wl.total_bases) * 1.0 + windows * 16.0
+    probe_bytes = float(wl.total_bases) * 1.0 + windows * 16.0  # 1 B/base in + one 16 B slot per window
     probe_ms = float(np.mean(stage_ms["probe"]))
     achieved = probe_bytes / (probe_ms * 1e-3) / 1e9
-    roofline = dict(bound="hbm", kernel="k_probe", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=None, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "probe_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    roofline = dict(bound="hbm", kernel=f"k_probe2<{k}>", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                    traffic=traffic, peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                     alg_bytes_per_launch=probe_bytes, kernel_ms=probe_ms,
-                    kernel_share_of_step=probe_ms * args.steps / ms)
+                    kernel_share_of_step=probe_ms * args.steps / ms,
+                    whole_path_alg_gbs=(probe_bytes + 24.0 * res["rows"]) * args.steps / (ms * 1e-3) / 1e9)
 
     # ---- end to end through the public API with HOST buffers ----
     e2e = None
@@ -220,16 +286,16 @@ def main_b200(args):
         np_reads = h_reads.numpy()[:wl.total_bases]
         np_off = h_off.numpy().view(np.uint64)
         bind_h = lambda: eng.set_reads(np_reads, np_off, wl.chunk_first, wl.chunk_hap)
-        run_step(eng, wl, bind_h)
+        run_step(eng, wl, bind_h, coll)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         f0.record()
         d2h = 0
         for _ in range(args.e2e_steps):
-            r = run_step(eng, wl, bind_h)
-            kept = eng.rows(1)
-            d2h = sum(a.nbytes for a in kept.values())
+            r, iv2, gaps2 = run_step(eng, wl, bind_h, coll)  # intervals + gaps come back to the host
+            pairs = eng.pairs()                               # inter_outs rows (group, read)
+            d2h = sum(a.nbytes for a in pairs.values()) + sum(a.nbytes for a in iv2.values()) + sum(a.nbytes for a in gaps2.values())
         f1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -239,26 +305,28 @@ def main_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = dict(value=total_bases * args.e2e_steps / (float(t.item()) * 1e-3) / 1e9, unit=UNIT,
                    h2d_bytes_per_step=int(wl.total_bases + 8 * (wl.n_reads + 1)), d2h_bytes_per_step=int(d2h),
-                   steps=args.e2e_steps)
+                   steps=args.e2e_steps, ms_per_step=float(t.item()) / args.e2e_steps)
         del h_reads, h_off
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu_baseline = cpu_reference_sample(args, wl, eng)
+            cpu_baseline = cpu_reference_sample(args, wl, eng, per_proc_mbp=args.cpu_sample_mbp or 12.0)
         except Exception as ex:  # the baseline must never take the bench down
-            cpu_baseline = dict(error=str(ex)[:200])
+            cpu_baseline = dict(error=repr(ex)[:300])
 
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl.meta["desc"], "k": k, "asm_haploid_mbp": wl.meta["asm_mbp"],
                        "read_gbp_per_gpu": wl.total_bases / 1e9, "reads_per_gpu": wl.n_reads, "n_sunks": n_sunks,
-                       "n_groups": n_groups, "rows_per_step": res, "l2": "inputs larger than L2 (reads >> 126 MB)",
-                       "stages": ["match", "diag_filter"], "db_build_ms": wl.meta["db_build_ms"],
-                       "stage_ms": {s: float(np.mean(v)) for s, v in stage_ms.items()}},
+                       "n_groups": n_groups, "results_per_step": res, "l2": "inputs larger than L2 (reads >> 126 MB per step)",
+                       "stages": ["match", "diag_filter", "bad_sunks", "validate", "components", "intervals", "gaps"],
+                       "db_build_ms": wl.meta["db_build_ms"],
+                       "stage_ms": {s: float(np.mean(v)) for s, v in stage_ms.items()},
+                       "parallelism": f"reads sharded over {world} GPU(s), SUNK table replicated"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -267,13 +335,148 @@ def main_b200(args):
         dist.destroy_process_group()
 
 
-def cpu_reference_sample(args, wl, eng):
-    """placeholder until the reference arm lands"""
-    return None
+# --------------------------------------------------------------------------------------------
+# CPU reference (oracle/_ref executables + oracle port of the Python stages) on a bounded sample
+# --------------------------------------------------------------------------------------------
+def _write_db_files(eng, wl, workdir):
+    """jellyfish.db / kmer.loc / .fai text files in the reference's formats from the GPU-built db"""
+    import pandas as pd
+    db = eng.db_export()
+    k = eng.k
+    km = db["kmer"]
+    shifts = (2 * np.arange(k - 1, -1, -1)).astype(np.uint64)
+    codes = ((km[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    kmers = letters.view(f"S{k}").ravel().astype(str)
+    names = np.asarray(wl.contig_names)
+    dbp, locp = os.path.join(workdir, "jellyfish.db"), os.path.join(workdir, "kmer.loc")
+    pd.DataFrame({"k": kmers}).to_csv(dbp, header=False, index=False)
+    pd.DataFrame({"c": names[db["contig"]], "s": db["start"], "k": kmers, "g": db["group"]}).to_csv(
+        locp, sep="\t", header=False, index=False)
+    nc = len(wl.contig_names) // 2
+    fais = []
+    for hap in range(2):
+        fp = os.path.join(workdir, f"hap{hap + 1}.fai")
+        with open(fp, "w") as f:
+            for c in range(hap * nc, (hap + 1) * nc):
+                f.write(f"{wl.contig_names[c]}\t{int(wl.contig_len[c])}\t0\t60\t61\n")
+        fais.append(fp)
+    return dbp, locp, fais
+
+
+def cpu_reference_sample(args, wl, eng, per_proc_mbp=12.0):
+    """Times the reference pipeline on the host cores for a sample of the same workload:
+    one kmerpos_annot3 -> diag_filter_v3 -> diag_filter_step2 process chain per chunk, all cores
+    busy (snakemake --cores N), then the oracle port of badsunks / process-by-contig / get_gaps."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_runner as RR
+    import gavisunk_oracle as O
+    cores = os.cpu_count() or 1
+    if not RR.available():
+        return dict(error="oracle/_ref executables missing", cores=cores)
+    workdir = tempfile.mkdtemp(prefix="gvs_cpu_")
+    try:
+        dbp, locp, fais = _write_db_files(eng, wl, workdir)
+        off = wl.read_off.cpu().numpy()
+        nph = wl.n_reads // 2
+        per_hap_procs = max(1, cores // 2)
+        jobs, sample_bases, sample_reads, rlen = [], 0, 0, {}
+        want = int(per_proc_mbp * 1e6)
+        for hap in range(2):
+            r = hap * nph
+            for c in range(per_hap_procs):
+                r0 = r
+                while r < (hap + 1) * nph and off[r] - off[r0] < want:
+                    r += 1
+                if r == r0:
+                    break
+                seq = wl.reads[int(off[r0]):int(off[r])].cpu().numpy()
+                fp = os.path.join(workdir, f"hap{hap + 1}_{c}.fa")
+                with open(fp, "wb") as f:
+                    for i in range(r0, r):
+                        f.write(b">r%09d\n" % i)
+                        f.write(seq[int(off[i] - off[r0]):int(off[i + 1] - off[r0])].tobytes())
+                        f.write(b"\n")
+                        rlen["r%09d" % i] = int(off[i + 1] - off[i])
+                jobs.append(dict(workdir=workdir, tag=f"hap{hap + 1}_{c}", reads=fp, db=dbp, loc=locp, fai=fais[hap]))
+                sample_bases += int(off[r] - off[r0])
+                sample_reads += r - r0
+        t_load = RR.table_load_seconds(workdir, dbp, locp)
+        res, wall_elf = RR.run_chunks_parallel(jobs, cores)
+        # ---- Python stages (port): bad SUNKs, per-contig validation, gaps ----
+        from gavisunk_b200 import io as gio
+        # the pure-Python port is slow: it runs on every `py_every`-th chunk file and its time is
+        # scaled back up (stated in `sample`)
+        py_every = max(1, len(jobs) // 4)
+        t0 = time.perf_counter()
+        rows_h = [[], []]
+        for ji, (j, r) in enumerate(zip(jobs, res)):
+            if ji % py_every:
+                continue
+            hap = 0 if j["tag"].startswith("hap1") else 1
+            rows_h[hap] += gio.read_sunkpos(r["diag2"])
+        nc = len(wl.contig_names) // 2
+        hapc = [set(wl.contig_names[:nc]), set(wl.contig_names[nc:])]
+        bad = O.bad_sunks(rows_h[0], hapc[0], rows_h[1], hapc[1])
+        beds, n_iv = {}, 0
+        for hap in range(2):
+            byc = {}
+            for row in rows_h[hap]:
+                byc.setdefault(row[2], []).append(row)
+            for ctg, rr in byc.items():
+                inter, bed = O.process_by_contig(rr, rlen, bad, ctg)
+                if bed is not None:
+                    beds[ctg] = [(s, e) for _, s, e in bed]
+                    n_iv += len(bed)
+        for hap in range(2):
+            fai = [(wl.contig_names[c], int(wl.contig_len[c])) for c in range(hap * nc, (hap + 1) * nc)]
+            O.get_gaps(fai, beds)
+        n_py = len([1 for ji in range(len(jobs)) if ji % py_every == 0])
+        t_py = (time.perf_counter() - t0) * len(jobs) / max(n_py, 1)
+        wall = wall_elf + t_py
+        return dict(value=sample_bases / wall / 1e9, unit=UNIT, cores=cores, kind="reference",
+                    sample=(f"{sample_reads} reads / {sample_bases / 1e6:.0f} Mbp of the same workload in {len(jobs)} chunk files; "
+                            f"reference ELFs kmerpos_annot3+diag_filter_v3+diag_filter_step2 one process per chunk, {cores} at once "
+                            f"(wall {wall_elf:.1f} s incl. {t_load:.1f} s table load per process), then the single-process CPU port of "
+                            f"badsunks/process-by-contig/get_gaps (the reference's Python needs graph_tool/pyranges; timed on {n_py} of the "
+                            f"{len(jobs)} chunks and scaled: {t_py:.1f} s)"),
+                    wall_s=wall, elf_wall_s=wall_elf, table_load_s=t_load, python_port_s=t_py,
+                    scan_only_value=sample_bases / max(wall_elf - t_load, 1e-9) / 1e9, sample_intervals=n_iv)
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
 
 
 def main_reference(args):
-    print(json.dumps({"impl": "reference", "unavailable": "reference arm not wired yet"}))
+    """--impl reference: only rank 0 works; the workload (assembly, SUNK db, reads) is generated with
+    the same generator as the b200 arm (setup, untimed); every timed step runs the reference
+    executables + CPU port on the host cores."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from gavisunk_b200.engine import Engine
+    torch.cuda.set_device(0)
+    eng = Engine(args.k, device=0)
+    wl = build_workload(args, eng, 0)
+    steps = max(1, min(args.steps, 2))
+    vals, last = [], None
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(args, wl, eng, per_proc_mbp=args.cpu_sample_mbp or 4.0)
+    for _ in range(steps):
+        last = cpu_reference_sample(args, wl, eng, per_proc_mbp=args.cpu_sample_mbp or 12.0)
+        if "value" not in last:
+            print(json.dumps({"impl": "reference", "unavailable": last.get("error", "reference run failed")}))
+            return
+        vals.append(last["value"])
+    v = float(np.mean(vals))
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps,
+           "warmup": min(args.warmup, 1), "ms_per_step": last["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": wl.meta["desc"], "k": args.k, "asm_haploid_mbp": wl.meta["asm_mbp"]},
+           "cpu_baseline": dict(last, value=v),
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":
