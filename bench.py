@@ -144,47 +144,6 @@ def build_workload(args, eng, rank):
     return wl
 
 
-class Collectives:
-    """The two NCCL exchanges of the path: sum of the per-group hit histogram and
-    all-gather of the union-find parent arrays.  torch tensors alias the library's device buffers
-    through the CUDA array interface, so NCCL works in place on them."""
-
-    def __init__(self, world, dev):
-        import torch
-        self.world = world
-        self.dev = dev
-        self.torch = torch
-        self._gather = None
-
-    def _alias(self, ptr, n, typestr):
-        torch = self.torch
-
-        class _A:
-            pass
-        a = _A()
-        a.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(ptr, False), version=2)
-        return torch.as_tensor(a, device=self.dev)
-
-    def allreduce_hist(self, ptr, n_groups):
-        import torch.distributed as dist
-        if self.world == 1 or n_groups == 0:
-            return
-        t = self._alias(ptr, n_groups, "<i4")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-
-    def gather_forests(self, ptr, n_groups):
-        import torch.distributed as dist
-        if self.world == 1 or n_groups == 0:
-            return []
-        torch = self.torch
-        mine = self._alias(ptr, n_groups, "<i4")  # uint32 payload moved as int32
-        if self._gather is None or self._gather.numel() != self.world * n_groups:
-            self._gather = torch.empty(self.world * n_groups, dtype=torch.int32, device=self.dev)
-        dist.all_gather_into_tensor(self._gather, mine)
-        rank = dist.get_rank()
-        return [int(self._gather.data_ptr()) + 4 * n_groups * r for r in range(self.world) if r != rank]
-
-
 def run_step(eng, wl, bind, coll):
     """one pass of the hot path; returns the result sizes"""
     bind()
@@ -211,7 +170,8 @@ def main_b200(args):
     eng = Engine(args.k, device=local, stream=torch.cuda.current_stream().cuda_stream)
     wl = build_workload(args, eng, rank)
     n_sunks, n_groups = eng.db_size()
-    coll = Collectives(world, dev)
+    from gavisunk_b200.parallel import EngineExchange
+    coll = EngineExchange(dev)
 
     def barrier():
         if world > 1:

@@ -1,0 +1,101 @@
+"""Multi-GPU plumbing of the hot path: reads shard by chunk file, the SUNK table is
+replicated, and exactly two exchanges cross GPUs:
+
+  1. sum of the per-group hit histogram (badsunks_AR.py:24 counts rows of ALL chunks of a
+     haplotype) -- all-reduce of int32[n_groups];
+  2. the contig-wide component merge (process-by-contig_lowmem_AR.py:219-237 sees the reads of ALL
+     chunks) -- all-gather of the union-find parent arrays uint32[n_groups]; every rank then unions
+     its forest with each peer's (gvs_components_merge), so the result is replicated.
+
+torch.distributed is plumbing only (NCCL on GPUs; gloo in the CPU tests).  The tensors alias the
+library's device buffers, so the collectives run in place on them.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_chunks(n_chunks: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous blocks of chunk files per rank.  A chunk file is never split: kmerpos_annot3's
+    `prevLoc` carry (workflow/src/kmerpos_annot3.nim:82-84) and diag_filter_v3's sticky
+    Table capacity (Q9) live inside one chunk file, so whole chunks keep every rank bit-exact."""
+    out = []
+    base, extra = divmod(n_chunks, world)
+    lo = 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def shard_reads(chunk_first: Sequence[int], chunk_hap: Sequence[int], rank: int, world: int):
+    """-> (first read, last read + 1, local chunk_first, local chunk_hap) of this rank's shard"""
+    chunk_first = np.asarray(chunk_first, dtype=np.uint64)
+    chunk_hap = np.asarray(chunk_hap, dtype=np.uint8)
+    lo, hi = shard_chunks(len(chunk_hap), world)[rank]
+    r0, r1 = int(chunk_first[lo]), int(chunk_first[hi])
+    if hi == lo:  # more ranks than chunks: an empty shard still needs one (empty) chunk
+        return r0, r0, np.array([0, 0], dtype=np.uint64), np.array([0], dtype=np.uint8)
+    return r0, r1, (chunk_first[lo:hi + 1] - chunk_first[lo]).astype(np.uint64), chunk_hap[lo:hi].copy()
+
+
+class Exchange:
+    """The two collectives on torch tensors (any device / backend)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def allreduce_hist(self, hist):
+        """hist: int32[n_groups] tensor, summed in place across ranks"""
+        if self.world > 1 and hist.numel():
+            self.dist.all_reduce(hist, op=self.dist.ReduceOp.SUM, group=self.group)
+        return hist
+
+    def gather_forests(self, parent):
+        """parent: int32-typed view of uint32[n_groups]; returns the list of the peers' arrays
+        (views into one gathered tensor), own rank excluded"""
+        import torch
+        if self.world == 1 or parent.numel() == 0:
+            return []
+        n = parent.numel()
+        buf = torch.empty(self.world * n, dtype=parent.dtype, device=parent.device)
+        self.dist.all_gather_into_tensor(buf, parent, group=self.group) if parent.is_cuda else \
+            self.dist.all_gather(list(buf.view(self.world, n).unbind(0)), parent, group=self.group)
+        self._keep = buf
+        return [buf[r * n:(r + 1) * n] for r in range(self.world) if r != self.rank]
+
+
+def alias_device_array(ptr: int, n: int, typestr: str, device):
+    """torch tensor over a raw device pointer owned by libgavisunk_b200.so (CUDA array interface)"""
+    import torch
+
+    class _A:
+        pass
+    a = _A()
+    a.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(ptr, False), version=2)
+    return torch.as_tensor(a, device=device)
+
+
+class EngineExchange:
+    """Adapters with the signatures Engine.run_all expects (raw device pointers)."""
+
+    def __init__(self, device, group=None):
+        self.x = Exchange(group)
+        self.device = device
+
+    def allreduce_hist(self, ptr: int, n_groups: int):
+        if self.x.world > 1 and n_groups:
+            self.x.allreduce_hist(alias_device_array(ptr, n_groups, "<i4", self.device))
+
+    def gather_forests(self, ptr: int, n_groups: int):
+        if self.x.world == 1 or not n_groups:
+            return []
+        peers = self.x.gather_forests(alias_device_array(ptr, n_groups, "<i4", self.device))
+        return [int(p.data_ptr()) for p in peers]
