@@ -37,6 +37,7 @@ PROTOTYPES = {
     "gvs_rows_get": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
     "gvs_diag_filter": (C.c_int, [vp, vp, vp, u64p, u64p]),
     "gvs_best_get": (C.c_int, [vp, vp, vp, vp, vp]),
+    "gvs_filter_best": (C.c_int, [vp, vp, u64p]),
     "gvs_contigs_set": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "gvs_group_hist":(C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     "gvs_hist_mode": (C.c_int, [vp, i64p]),

@@ -507,3 +507,58 @@ extern "C" int gvs_best_get(gvs_ctx* ctx, uint32_t* read_idx, uint32_t* contig, 
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// diag_filter_step2 on its own (workflow/src/diag_filter_step2.nim:13-66): the best contig per read
+// comes from a `_diag.sunkpos` file instead of the vote; rows whose contig equals it survive.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_keep_by_table(u64 n, const u32* __restrict__ keep_excl, const u32* __restrict__ best_of_read,
+                                                       const u32* __restrict__ read, const u32* __restrict__ pos,
+                                                       const u32* __restrict__ contig, const u32* __restrict__ start,
+                                                       const u32* __restrict__ group, const u32* __restrict__ gidx, u32* o_read,
+                                                       u32* o_pos, u32* o_contig, u32* o_start, u32* o_group, u32* o_gidx) {
+  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  u32 c = contig[j];
+  if (best_of_read[read[j]] != c) return;
+  u32 o = keep_excl[j];
+  o_read[o] = read[j];
+  o_pos[o] = pos[j];
+  o_contig[o] = c;
+  o_start[o] = start[j];
+  o_group[o] = group[j];
+  o_gidx[o] = gidx[j];
+}
+
+extern "C" int gvs_filter_best(gvs_ctx* ctx, const uint32_t* best_contig_of_read, uint64_t* n_kept) {
+  if (!ctx || !best_contig_of_read) return GVS_E_ARG;
+  if (!ctx->match_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_filter_best before gvs_match / gvs_rows_set(0)");
+  CK(cudaSetDevice(ctx->device));
+  Rows& R = ctx->rows;
+  u64 n = R.n;
+  ctx->kept.n = 0;
+  ctx->n_best = 0;
+  CKR(to_dev(ctx, ctx->seg_best, best_contig_of_read, ctx->n_reads ? ctx->n_reads : 1));
+  CKR(gvs_reserve(ctx, ctx->flags_b, (n ? n : 1) * 4));
+  u32 nk = 0;
+  if (n) {
+    const u32* best = ctx->seg_best.as<u32>();
+    const u32 *read = R.read.as<u32>(), *contig = R.contig.as<u32>();
+    u32* ke = ctx->flags_b.as<u32>();
+    u32* kt = (u32*)(ctx->counters.as<u64>() + 13);
+    auto f = [best, read, contig] __device__(u64 j) -> u32 { return best[read[j]] == contig[j] ? 1u : 0u; };
+    auto g = [ke] __device__(u64 j, u32 ex, u32 v) { ke[j] = ex; };
+    CKR((device_scan<u32>(ctx, n, f, g, OpSum(), kt)));
+    CKR(read_dev(ctx, kt, &nk));
+    CKR(gvs_reserve_rows(ctx, ctx->kept, nk));
+    LAUNCH(k_keep_by_table, (unsigned)cdiv(n, 256), 256, 0, n, ke, best, read, R.pos.as<u32>(), contig, R.start.as<u32>(),
+           R.group.as<u32>(), R.gidx.as<u32>(), ctx->kept.read.as<u32>(), ctx->kept.pos.as<u32>(), ctx->kept.contig.as<u32>(),
+           ctx->kept.start.as<u32>(), ctx->kept.group.as<u32>(), ctx->kept.gidx.as<u32>());
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->kept.n = nk;
+  ctx->diag_ready = true;
+  ctx->val_ready = false;
+  if (n_kept) *n_kept = nk;
+  return 0;
+}

@@ -278,6 +278,14 @@ class Engine:
                                        _ptr(out["dir"])))
         return out
 
+    def filter_best(self, best_contig_of_read) -> int:
+        """diag_filter_step2 (workflow/src/diag_filter_step2.nim:13-66) with the best contigs given."""
+        b = _c(best_contig_of_read, np.uint32)
+        n = C.c_uint64()
+        self._ck(self.lib.gvs_filter_best(self.ctx, _ptr(b), C.byref(n)))
+        self.n_kept = int(n.value)
+        return self.n_kept
+
     def set_contigs(self, contig_hap: Sequence[int]):
         ch = _c(contig_hap, np.uint8)
         hh = np.array([nim_hash(n) for n in self.contig_names], dtype=np.uint32)
@@ -381,3 +389,68 @@ class Engine:
         self._ck(self.lib.gvs_covprob_table(self.ctx, _ptr(kbp), _ptr(cnt), len(kbp), float(genome_kbp), float(pn),
                                             _ptr(out)))
         return out
+
+
+# ----------------------------------------------------------------------------------------------
+# covprob host scalars (workflow/scripts/covprob.py:63-81): the reference solves
+# 1 - x + q p^r x^(r+1) = 0 with sympy and keeps the positive real root that is NOT 1/p; pn is the
+# probability of at least one error-free run of r bases in a window of n = 30 (Feller).  Two
+# scalars per run: computed on the host in float64, the 3500-entry table is the GPU kernel.
+# ----------------------------------------------------------------------------------------------
+def covprob_root(r: int, p: float = 0.94) -> float:
+    q = 1.0 - p
+    a = q * p ** r
+
+    def f(x):
+        return 1.0 - x + a * x ** (r + 1)
+
+    def df(x):
+        return -1.0 + a * (r + 1) * x ** r
+
+    xs = ((r + 1) * a) ** (-1.0 / r)  # minimiser of the convex f on x > 0; the two roots bracket it
+    pinv = 1.0 / p
+    if pinv > xs:
+        lo, hi = 1.0, xs
+    else:
+        lo, hi = xs, max(2.0, 4.0 * xs)
+        while f(hi) < 0:
+            hi *= 2.0
+    flo = f(lo)
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        fm = f(mid)
+        if (fm > 0) == (flo > 0):
+            lo, flo = mid, fm
+        else:
+            hi = mid
+    x = 0.5 * (lo + hi)
+    for _ in range(4):
+        x -= f(x) / df(x)
+    return x
+
+
+def covprob_pn(r: int, p: float = 0.94, n: int = 30) -> float:
+    q = 1.0 - p
+    x = covprob_root(r, p)
+    qn = ((1.0 - p * x) / (q * (r + 1 - r * x))) * (1.0 / (x ** (n + 1)))  # covprob.py:79
+    return float(1.0 - qn)
+
+
+def covprob_bins(read_lens):
+    """covprob.py:44-53: drop duplicate (name, len) rows, sort by length descending, kbp = int(len/1000),
+    value_counts(sort=False) -> bins in order of first appearance."""
+    seen, lens = set(), []
+    for nm, ln in read_lens:
+        if (nm, ln) in seen:
+            continue
+        seen.add((nm, ln))
+        lens.append(int(ln))
+    kbp, cnt, idx = [], [], {}
+    for ln in sorted(lens, reverse=True):
+        b = int(ln / 1000)
+        if b not in idx:
+            idx[b] = len(kbp)
+            kbp.append(b)
+            cnt.append(0)
+        cnt[idx[b]] += 1
+    return np.asarray(kbp, np.int64), np.asarray(cnt, np.int64)

@@ -156,6 +156,11 @@ int gvs_diag_filter(gvs_ctx* ctx, const uint8_t* contig_hap, const uint32_t* con
 int gvs_best_get(gvs_ctx* ctx, uint32_t* read_idx, uint32_t* contig, uint32_t* ngood,
                  uint8_t* dir);
 
+/* diag_filter_step2 on its own (workflow/src/diag_filter_step2.nim:13-66): best_contig_of_read[n_reads]
+ * parsed from a {hap}_{i}_diag.sunkpos file (0xFFFFFFFF = read has no best contig); keeps the rows of
+ * gvs_match / gvs_rows_set(0) whose contig equals it -> gvs_rows_get(1). */
+int gvs_filter_best(gvs_ctx* ctx, const uint32_t* best_contig_of_read, uint64_t* n_kept);
+
 /* Contig tables for callers that skip gvs_diag_filter (which sets them itself): contig_hap as
  * above (badsunks_AR.py:28-33 "correct" = contig listed in the haplotype's .fai), contig_hash may
  * be NULL. */

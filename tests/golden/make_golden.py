@@ -289,7 +289,28 @@ def rlen_case():
     return dict(reads=txt.decode("latin-1"), rlen=run_rlen(txt))
 
 
+def covprob_case():
+    """read-length distributions of the bundled ONT read indexes (.test/data/AMY_hap{1,2}.ONT.fa.gz.fai:
+    the reads themselves are missing from the snapshot) + the oracle's covprob table for SUNK_len 20
+    (anchors in SURVEY.md A.8 were cross-checked against sympy.solveset as covprob.py:68-81 uses it)"""
+    out = {}
+    T = "/root/reference/.test/data/"
+    for hap in (1, 2):
+        rl = [(l.split("\t")[0], int(l.split("\t")[1])) for l in open(f"{T}AMY_hap{hap}.ONT.fa.gz.fai")]
+        G = sum(int(l.split("\t")[1]) for l in open(f"{T}AMY.hap{hap}.fa.gz.fai")) / 1000
+        out[f"hap{hap}"] = dict(read_lens=rl, genome_kbp=G, table_r20=O.covprob_table(rl, G, 20))
+    return out
+
+
+def hg02723_asm():
+    """the bundled HG02723 AMY-locus assemblies (inputs of the README known answer, README.md:36-37)"""
+    T = "/root/reference/.test/data/HG02723/"
+    return dict(h1=open(T + "h1.fa").read(), h2=open(T + "h2.fa").read())
+
+
 def main():
+    save("covprob_amy", covprob_case())
+    save("hg02723_asm", hg02723_asm())
     save("kat_b1", kat_b1())
     save("kat_bytes", kat_bytes())
     save("rlen_b8", rlen_case())

@@ -1,0 +1,151 @@
+"""The CLI shims (gavisunk_b200.cli) reproduce the reference programs' files byte for byte: argv and
+formats of workflow/scripts/{kmerpos_annot3,rlen,diag_filter_v3,diag_filter_step2} against the ELF
+outputs in tests/golden, and the fused rule against the oracle's composition of all stages."""
+import io
+import os
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+import gavisunk_oracle as O
+from conftest import load_golden
+from gavisunk_b200 import cli, io as gio
+
+
+def test_rlen_shim(tmp_path):
+    case = load_golden("rlen_b8")
+    p = tmp_path / "reads.fa"
+    p.write_bytes(case["reads"].encode("latin-1"))
+    assert cli.main(["rlen", str(p), str(tmp_path / "o.rlen")]) == 0
+    assert (tmp_path / "o.rlen").read_text() == case["rlen"]
+
+
+def test_cli_errors_exit_nonzero(tmp_path):
+    assert cli.main(["rlen", str(tmp_path / "missing.fa"), str(tmp_path / "o.rlen")]) == 1
+    assert not (tmp_path / "o.rlen").exists()
+    assert cli.main(["nonsense"]) == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["kat_b1", "rand_k24"])
+def test_kmerpos_annot3_shim(tmp_path, name):
+    case = load_golden(name)
+    (tmp_path / "db.txt").write_text(case["db"])
+    (tmp_path / "loc.txt").write_text(case["loc"])
+    chunks = [dict(reads=case["reads"], sunkpos=case["out"])] if "reads" in case else case["chunks"][:2]
+    for i, ch in enumerate(chunks):
+        rp = tmp_path / (f"r{i}.fq" if i % 2 else f"r{i}.fa")
+        rp.write_bytes(ch["reads"].encode("latin-1"))
+        out = tmp_path / f"o{i}.sunkpos"
+        assert cli.main(["kmerpos_annot3", str(rp), str(tmp_path / "db.txt"), str(tmp_path / "loc.txt"), str(out)]) == 0
+        assert out.read_text() == ch["sunkpos"]
+
+
+@pytest.mark.gpu
+def test_diag_shims(tmp_path):
+    for case in load_golden("diag_cases")[:3]:
+        sp, fp, dp = tmp_path / "s.sunkpos", tmp_path / "h.fai", tmp_path / "s.diag"
+        sp.write_text(case["sunkpos"])
+        fp.write_text(case["fai"])
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            assert cli.main(["diag_filter_v3", str(sp), str(fp)]) == 0
+        assert buf.getvalue() == case["diag"], case["name"]
+        dp.write_text(case["diag"])
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            assert cli.main(["diag_filter_step2", str(sp), str(dp)]) == 0
+        assert buf.getvalue() == case["diag2"], case["name"]
+
+
+def _oracle_pipeline(contigs_h, reads_h, k):
+    """oracle composition of every stage; returns the file contents the fused rule must produce"""
+    contigs = contigs_h[0] + contigs_h[1]
+    names = [n for n, _ in contigs]
+    db = O.build_sunk_db(contigs, k)
+    loc = [(names[c], int(s), int(km), int(g)) for c, s, km, g in zip(db["contig"], db["start"], db["kmer"], db["group"])]
+    out = {"kmer.loc": "".join(f"{c}\t{s}\t{O.decode(km, k)}\t{g}\n" for c, s, km, g in loc)}
+    kept_h, rlen = [], {}
+    for hap in range(2):
+        hapc = {n for n, _ in contigs_h[hap]}
+        kept = []
+        for chunk in reads_h[hap]:
+            rows = O.match_chunk(chunk, db["kmer"], loc, k)
+            kept += O.diag_filter_step2(rows, O.diag_filter_v3(rows, hapc))
+            for n, s in chunk:
+                rlen[n] = len(s)
+        kept_h.append(kept)
+        out[f"hap{hap + 1}.sunkpos"] = gio.format_sunkpos(kept)
+    bad = O.bad_sunks(kept_h[0], {n for n, _ in contigs_h[0]}, kept_h[1], {n for n, _ in contigs_h[1]})
+    out["bad"] = {f"{c}:{g}" for c, g in bad}
+    for hap in range(2):
+        byc, beds, valid = {}, {}, []
+        for r in kept_h[hap]:
+            byc.setdefault(r[2], []).append(r)
+        for ctg, rr in byc.items():
+            inter, bed = O.process_by_contig(rr, rlen, bad, ctg)
+            out[f"inter:{ctg}"] = "".join(f"{g}\t{n}\n" for g, n in inter) if inter else ctg + "\n"
+            if bed is not None:
+                beds[ctg] = [(s, e) for _, s, e in bed]
+                valid += [f"{c}\t{s}\t{e}\n" for c, s, e in bed]
+        fai = [(n, len(s)) for n, s in contigs_h[hap]]
+        gaps, nodata = O.get_gaps(fai, beds)
+        out[f"hap{hap + 1}.valid.bed"] = sorted(valid)
+        out[f"hap{hap + 1}.gaps.bed"] = "".join(f"{c}\t{s}\t{e}\n" for c, s, e in gaps)
+        out[f"hap{hap + 1}.nodata.bed"] = "".join(f"{c}\t{s}\t{e}\n" for c, s, e in nodata)
+        out[f"hap{hap + 1}.gaps.slop.bed"] = "".join(f"{c}\t{s}\t{e}\n" for c, s, e in O.slop_gaps(gaps, dict(fai)))
+    return out
+
+
+@pytest.mark.gpu
+def test_fused_rule_files(tmp_path):
+    import torch
+    from gavisunk_b200.engine import Engine
+    from gavisunk_b200 import workload as W
+    k = 20
+    eng = Engine(k)
+    wl = W.make_assembly(eng, [260000, 90000, 4000], snp_rate=2e-3, dup_frac=0.05, seed=91)
+    W.add_reads(eng, wl, coverage=16.0, n50=16000, sigma=0.5, len_min=300, len_max=200000, seed=92, nchunks=2)
+    asm = wl.asm.cpu().numpy()
+    coff = wl.contig_off.cpu().numpy()
+    nc = len(wl.contig_names) // 2
+    contigs_h = [[(wl.contig_names[c], asm[coff[c]:coff[c + 1]].tobytes()) for c in range(h * nc, (h + 1) * nc)] for h in range(2)]
+    reads = wl.reads.cpu().numpy()
+    off = wl.read_off.cpu().numpy()
+    cf = wl.chunk_first
+    reads_h, files_h = [[], []], [[], []]
+    for ci in range(len(cf) - 1):
+        hap = int(wl.chunk_hap[ci])
+        chunk = [(f"read{r:07d}", reads[off[r]:off[r + 1]].tobytes()) for r in range(int(cf[ci]), int(cf[ci + 1]))]
+        reads_h[hap].append(chunk)
+        fp = tmp_path / f"hap{hap + 1}_{ci}.fa"
+        fp.write_bytes(b"".join(b">" + n.encode() + b"\n" + s + b"\n" for n, s in chunk))
+        files_h[hap].append(str(fp))
+    asm_files = []
+    for hap in range(2):
+        fp = tmp_path / f"hap{hap + 1}.fa"
+        fp.write_bytes(b"".join(b">" + n.encode() + b"\n" + s + b"\n" for n, s in contigs_h[hap]))
+        asm_files.append(str(fp))
+    outdir = tmp_path / "results"
+    rc = cli.main(["fused", "--k", str(k), "--hap1-asm", asm_files[0], "--hap2-asm", asm_files[1], "--hap1-reads", *files_h[0],
+                   "--hap2-reads", *files_h[1], "--outdir", str(outdir)])
+    assert rc == 0
+    exp = _oracle_pipeline(contigs_h, reads_h, k)
+    rd = lambda *p: open(os.path.join(outdir, *p)).read()
+    assert rd("mrsfast", "kmer.loc") == exp["kmer.loc"]
+    assert sorted(rd("db", "jellyfish.db").split()) == sorted(l.split("\t")[2] for l in exp["kmer.loc"].splitlines())
+    assert set(rd("sunkpos", "bad_sunks.txt").split()) == exp["bad"]
+    n_inter = 0
+    for hap in (1, 2):
+        assert rd("sunkpos", f"hap{hap}.sunkpos") == exp[f"hap{hap}.sunkpos"]
+        assert sorted(rd("final_out", f"hap{hap}.valid.bed").splitlines(True)) == exp[f"hap{hap}.valid.bed"]
+        for f in ("gaps.bed", "nodata.bed", "gaps.slop.bed"):
+            assert rd("final_out", f"hap{hap}.{f}") == exp[f"hap{hap}.{f}"], f
+    for key, val in exp.items():
+        if key.startswith("inter:"):
+            ctg = key[6:]
+            hap = 1 if ctg.startswith("synH1") else 2
+            assert rd("inter_outs", f"{ctg}_hap{hap}.tsv") == val, ctg
+            n_inter += val.count("\n")
+    assert n_inter > 100

@@ -59,26 +59,44 @@ def test_db_build_host_edge_cases():
     _check_db(eng5, contigs, 5)
 
 
-H1 = os.path.join(os.path.dirname(__file__), "golden", "hg02723_groups.json.gz")
+def _hg02723_contigs():
+    from conftest import load_golden
+    asm = load_golden("hg02723_asm")
+    return gio.read_fastx(asm["h1"].encode()) + gio.read_fastx(asm["h2"].encode())
 
 
 def test_db_build_readme_known_answer():
-    """README.md:36-37: gap AMY_h1 284861-324275 <=> adjacent SUNK-group starts 284861 / 324276.
-    The assemblies themselves are not shipped (they live in the reference's .test/data); the test
-    runs where they exist and otherwise checks the committed group table derived from them."""
-    h1 = "/root/reference/.test/data/HG02723/h1.fa"
-    h2 = "/root/reference/.test/data/HG02723/h2.fa"
-    if not os.path.exists(h1):
-        pytest.skip("bundled assemblies not present on this box")
+    """README.md:36-37: expected figure AMY_HG02723_hap1_AMY_h1_84861_524275 = gap AMY_h1 284861-324275
+    +-200 kb (tagONT.smk:249) <=> 284861 and 324276 are adjacent SUNK-group starts on AMY_h1.
+    Inputs: the reference's bundled HG02723 assemblies (tests/golden/hg02723_asm.json.gz)."""
     from gavisunk_b200.engine import Engine
+    contigs = _hg02723_contigs()
     eng = Engine(20)
-    contigs = gio.read_fastx(h1) + gio.read_fastx(h2)
     eng.build_db(contigs)
     db = eng.db_export()
-    ci = [n for n, _ in contigs].index("AMY_h1")
+    names = [n for n, _ in contigs]
+    ci = names.index("AMY_h1")
     groups = np.unique(db["group"][db["contig"] == ci])
     i = int(np.searchsorted(groups, 284861))
     assert groups[i] == 284861 and groups[i + 1] == 324276
+    assert np.diff(groups).max() == 324276 - 284861
+    per = {n: (int((db["contig"] == j).sum()), len(np.unique(db["group"][db["contig"] == j]))) for j, n in enumerate(names)}
+    assert per == {"AMY_h1": (4102, 205), "AMY_orphan_h1": (216, 12), "nonuniq_kmers": (5384, 246), "AMY_h2": (3959, 196)}
+    _check_db(eng, contigs, 20)
+
+
+@pytest.mark.parametrize("k", [16, 24, 31])
+def test_db_build_hg02723_k_sweep(k):
+    """SURVEY A.2 [probe]: AMY_h1 SUNKs/groups for k = 16 / 24 / 31"""
+    from gavisunk_b200.engine import Engine
+    contigs = _hg02723_contigs()
+    eng = Engine(k)
+    eng.build_db(contigs)
+    db = eng.db_export()
+    ci = [n for n, _ in contigs].index("AMY_h1")
+    sel = db["contig"] == ci
+    exp = {16: (3253, 206), 24: (6660, 456), 31: (11395, 448)}[k]
+    assert (int(sel.sum()), len(np.unique(db["group"][sel]))) == exp
 
 
 def test_match_on_device_generated_reads():

@@ -11,13 +11,12 @@ import pytest
 import gavisunk_oracle as O
 from gavisunk_b200 import io as gio
 
-H1 = "/root/reference/.test/data/HG02723/h1.fa"
-H2 = "/root/reference/.test/data/HG02723/h2.fa"
+from conftest import load_golden
 
 
-@pytest.mark.skipif(not os.path.exists(H1), reason="reference test data not present")
 def test_readme_gap_coordinate():
-    contigs = gio.read_fastx(H1) + gio.read_fastx(H2)
+    asm = load_golden("hg02723_asm")  # the reference's bundled HG02723 assemblies (.test/data/HG02723)
+    contigs = gio.read_fastx(asm["h1"].encode()) + gio.read_fastx(asm["h2"].encode())
     db = O.build_sunk_db(contigs, 20)
     names = [n for n, _ in contigs]
     ci = names.index("AMY_h1")
