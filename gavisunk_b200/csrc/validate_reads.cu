@@ -1,0 +1,417 @@
+// validate_reads.cu -- per-read inter-SUNK distance validation
+// (workflow/scripts/process-by-contig_lowmem_AR.py:50-207).
+//
+// One thread group per read: a warp for reads with <= 64 rows (8 reads per 256-thread block, no block
+// barriers), a 128-thread block with shared memory up to 512 rows, a 1024-thread block with global
+// scratch beyond.  Rows minus bad groups -> stable rank-sort by assembly start -> every pair (i<j)
+// tested with the integer form of the reference's float64 ratio test (0.9 < dpos/dstart < 1.1  <=>
+// 9*ds < 10*dp < 11*ds, exact for 32-bit inputs) -> orientation majority -> "multipos" clean-up ->
+// union-find over group IDs -> largest component (ties: the component holding the earliest vertex in
+// graph-tool's insertion order) -> output in vertex order.
+#include "common.cuh"
+
+#define VCAP_WARP 64      // rows per read handled by one warp
+#define VCAP 512          // rows per read handled in shared memory by one block
+#define VROW_BYTES 80     // bytes of working storage per row
+#define NOV 0xFFFFFFFFu
+#define NOT64 0xFFFFFFFFFFFFFFFFull
+
+struct VWork {
+  u32 *P, *S, *ID, *G;        // rows sorted by (assembly start, read position)
+  u32 *uP, *uS, *uID, *uG;    // rows after bad-group removal (any order)
+  u32 *deg, *fpart, *rep, *par, *csize;
+  u64 *key, *tv, *ct;
+  u8 *good, *multi, *pres, *left;
+};
+
+__device__ __forceinline__ void vwork_carve(VWork& w, u8* base, u32 cap) {
+  u64* q = (u64*)base;
+  w.key = q; q += cap;
+  w.tv = q; q += cap;
+  w.ct = q; q += cap;
+  u32* p = (u32*)q;
+  w.P = p; p += cap; w.S = p; p += cap; w.ID = p; p += cap; w.G = p; p += cap;
+  w.uP = p; p += cap; w.uS = p; p += cap; w.uID = p; p += cap; w.uG = p; p += cap;
+  w.deg = p; p += cap; w.fpart = p; p += cap; w.rep = p; p += cap; w.par = p; p += cap; w.csize = p; p += cap;
+  u8* b = (u8*)p;
+  w.good = b; b += cap; w.multi = b; b += cap; w.pres = b; b += cap; w.left = b; b += cap;
+}
+
+// 0.9 < dpos/dstart < 1.1 in float64 (process-by-contig_lowmem_AR.py:145-147) as exact integers (Q12)
+__device__ __forceinline__ bool pair_ok(u32 pi, u32 si, u32 pj, u32 sj) {
+  u64 ds = si > sj ? si - sj : sj - si;
+  u64 dp = pi > pj ? pi - pj : pj - pi;
+  return 9 * ds < 10 * dp && 10 * dp < 11 * ds;
+}
+
+__device__ __forceinline__ u32 uf_find(const volatile u32* par, u32 x) {
+  u32 p = par[x];
+  while (p != x) { x = p; p = par[x]; }
+  return x;
+}
+__device__ __forceinline__ void uf_union(u32* par, u32 a, u32 b) {
+  for (;;) {
+    a = uf_find(par, a);
+    b = uf_find(par, b);
+    if (a == b) return;
+    u32 hi = a > b ? a : b, lo = a > b ? b : a;
+    if (atomicCAS(&par[hi], hi, lo) == hi) return;
+  }
+}
+
+struct ValParams {
+  const u32 *read, *pos, *start, *group, *gidx;  // kept rows
+  const u32* seg_start;
+  u32 n_seg;
+  const u8* bad;             // per group index (null: nothing is bad)
+  const u64* read_off;       // read lengths from offsets ...
+  const u32* read_len;       // ... or explicit
+  u32 min_len;
+  u32* out_id;               // per kept row slot: validated IDs of the read, from its first row on
+  u32* out_gidx;
+  u32* seg_cnt;              // validated IDs per segment
+  u32 m_lo, m_hi;            // this launch handles reads with m_lo < rows <= m_hi
+  u8* gscratch;              // global-scratch variant: per block VROW_BYTES * big_cap
+  u32 big_cap;
+  u32* stats;                // [0] reads whose clean-up removed every edge (reference would raise)
+};
+
+// NT threads per read, GROUPS reads per block; GLOBAL: working arrays in global scratch
+template <int NT, int GROUPS, bool GLOBAL>
+__global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
+  extern __shared__ __align__(16) u8 smem[];
+  __shared__ u32 s_n0[GROUPS], s_n1[GROUPS], s_m[GROUPS], s_kept[GROUPS], s_bestroot[GROUPS], s_distinct[GROUPS];
+  __shared__ unsigned long long s_best[GROUPS];
+  const int grp = threadIdx.x / NT;
+  const int tid = threadIdx.x % NT;
+  auto gsync = [&]() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
+  };
+  VWork w;
+  const u32 cap = GLOBAL ? V.big_cap : (NT == 32 ? VCAP_WARP : VCAP);
+  if (GLOBAL) vwork_carve(w, V.gscratch + (u64)blockIdx.x * VROW_BYTES * cap, cap);
+  else vwork_carve(w, smem + (u64)grp * VROW_BYTES * cap, cap);
+
+  for (u32 s = blockIdx.x * GROUPS + grp; s < V.n_seg; s += gridDim.x * GROUPS) {
+    const u32 a = V.seg_start[s], b = V.seg_start[s + 1];
+    const u32 mrows = b - a;
+    if (mrows <= V.m_lo || mrows > V.m_hi) continue;  // another launch owns this read (group-uniform)
+    gsync();
+    if (tid == 0) { s_m[grp] = 0; s_n0[grp] = 0; s_n1[grp] = 0; s_kept[grp] = 0; s_best[grp] = 0; s_bestroot[grp] = NOV; s_distinct[grp] = 0; }
+    gsync();
+    // read length filter (hard-coded 10000 in the reference, :106-108; Q13)
+    const u32 rd = V.read[a];
+    const u32 rlen = V.read_len ? V.read_len[rd] : (u32)(V.read_off[rd + 1] - V.read_off[rd]);
+    const bool skip = rlen < V.min_len || mrows < 2;
+    // ---- rows minus bad groups (:70-72); order is restored by the sort below ----
+    if (!skip) {
+      for (u32 i = tid; i < mrows; i += NT) {
+        u32 gi = V.gidx[a + i];
+        if (V.bad && V.bad[gi]) continue;
+        u32 d = atomicAdd(&s_m[grp], 1u);
+        w.uP[d] = V.pos[a + i];
+        w.uS[d] = V.start[a + i];
+        w.uID[d] = V.group[a + i];
+        w.uG[d] = gi;
+      }
+    }
+    gsync();
+    const u32 m = s_m[grp];
+    if (skip || m < 2) {
+      if (tid == 0) V.seg_cnt[s] = 0;
+      continue;
+    }
+    // ---- sort by (start, pos): sort_values(['rname','start']) is stable and rows of a read come in
+    //      increasing pos (:100) ----
+    for (u32 i = tid; i < m; i += NT) {
+      u32 si = w.uS[i], pi = w.uP[i], rank = 0;
+      for (u32 j = 0; j < m; j++) {
+        u32 sj = w.uS[j];
+        rank += (sj < si) || (sj == si && w.uP[j] < pi);
+      }
+      w.P[rank] = pi;
+      w.S[rank] = si;
+      w.ID[rank] = w.uID[i];
+      w.G[rank] = w.uG[i];
+      w.deg[i] = 0; w.fpart[i] = NOV; w.par[i] = i; w.csize[i] = 0;
+      w.tv[i] = NOT64; w.ct[i] = NOT64;
+      w.good[i] = 0; w.multi[i] = 0; w.pres[i] = 0; w.left[i] = 0;
+    }
+    gsync();
+    // at least two distinct groups (:91-97)
+    for (u32 i = tid; i < m; i += NT)
+      if (w.ID[i] != w.ID[0]) s_distinct[grp] = 1;
+    gsync();
+    if (!s_distinct[grp]) {
+      if (tid == 0) V.seg_cnt[s] = 0;
+      continue;
+    }
+    const u64 cells = (u64)m * m;
+    // ---- pass A: masked pairs by sign (:140-152) ----
+    {
+      u32 n0 = 0, n1 = 0;
+      u32 i = tid / m, j = tid % m;
+      for (u64 c = tid; c < cells; c += NT) {
+        if (i < j && pair_ok(w.P[i], w.S[i], w.P[j], w.S[j])) {
+          if (w.P[i] > w.P[j]) n1++; else n0++;
+        }
+        j += NT;
+        while (j >= m) { j -= m; i++; }
+      }
+      for (int d = 16; d; d >>= 1) {
+        n0 += __shfl_xor_sync(0xFFFFFFFFu, n0, d);
+        n1 += __shfl_xor_sync(0xFFFFFFFFu, n1, d);
+      }
+      if ((tid & 31) == 0) {
+        if (n0) atomicAdd(&s_n0[grp], n0);
+        if (n1) atomicAdd(&s_n1[grp], n1);
+      }
+    }
+    gsync();
+    if (s_n0[grp] + s_n1[grp] < 1) {  // `if sum(mask) < 1: continue` (:148)
+      if (tid == 0) V.seg_cnt[s] = 0;
+      continue;
+    }
+    const bool orient = s_n1[grp] > s_n0[grp];  // np.unique sorted + argmax: a tie keeps 0 (:151-152)
+    // ---- pass B: incidence of every row in the oriented edge list (the (ID,pos) multiset M) ----
+    {
+      u32 i = tid / m, j = tid % m;
+      for (u64 c = tid; c < cells; c += NT) {
+        if (i < j && pair_ok(w.P[i], w.S[i], w.P[j], w.S[j]) && ((w.P[i] > w.P[j]) == orient)) {
+          atomicAdd(&w.deg[i], 1u);
+          atomicAdd(&w.deg[j], 1u);
+          w.left[i] = 1;
+          atomicMin(&w.fpart[j], i);
+        }
+        j += NT;
+        while (j >= m) { j -= m; i++; }
+      }
+    }
+    gsync();
+    // order of first appearance in M = [all left ends in edge order] + [all right ends in edge order]
+    for (u32 r = tid; r < m; r += NT)
+      w.key[r] = w.left[r] ? (u64)r : ((1ull << 63) | ((u64)w.fpart[r] * m + r));
+    gsync();
+    // ---- multipos (:161-181): IDs seen at more than one read position keep their most frequent one ----
+    for (u32 r = tid; r < m; r += NT) {
+      u32 id = w.ID[r], dr = w.deg[r];
+      u32 first = r;
+      bool multi = false, good = dr > 0;
+      for (u32 q = 0; q < m; q++) {
+        if (w.ID[q] != id) continue;
+        if (q < first) first = q;
+        if (q == r) continue;
+        u32 dq = w.deg[q];
+        if (dq == 0) continue;
+        multi = true;
+        if (dq > dr || (dq == dr && w.key[q] < w.key[r])) good = false;
+      }
+      w.rep[r] = first;
+      w.multi[r] = (multi && dr > 0) ? 1 : 0;
+      w.good[r] = good ? 1 : 0;
+    }
+    gsync();
+    // ---- pass C: surviving edges -> graph on IDs (:189-192) ----
+    {
+      u32 nk = 0;
+      u32 i = tid / m, j = tid % m;
+      for (u64 c = tid; c < cells; c += NT) {
+        if (i < j && pair_ok(w.P[i], w.S[i], w.P[j], w.S[j]) && ((w.P[i] > w.P[j]) == orient)) {
+          // dropped iff the left ID is multi-positioned, this is not its good row and the right row is
+          // not that ID's good row either (left end only: Q14)
+          bool drop = w.multi[i] && !w.good[i] && !(w.good[j] && w.ID[j] == w.ID[i]);
+          if (!drop) {
+            nk++;
+            u32 ri = w.rep[i], rj = w.rep[j];
+            u64 e = (u64)i * m + j;
+            w.pres[ri] = 1;
+            w.pres[rj] = 1;
+            atomicMin((unsigned long long*)&w.tv[ri], (unsigned long long)(2 * e));
+            atomicMin((unsigned long long*)&w.tv[rj], (unsigned long long)(2 * e + 1));
+            if (ri != rj) uf_union(w.par, ri, rj);
+          }
+        }
+        j += NT;
+        while (j >= m) { j -= m; i++; }
+      }
+      if (nk) atomicAdd(&s_kept[grp], nk);
+    }
+    gsync();
+    if (s_kept[grp] == 0) {  // graph-tool would raise on the empty graph; counted, read skipped (A.6 step 5)
+      if (tid == 0) {
+        V.seg_cnt[s] = 0;
+        atomicAdd(&V.stats[0], 1u);
+      }
+      continue;
+    }
+    // ---- components: size and earliest vertex ----
+    for (u32 r = tid; r < m; r += NT) {
+      if (w.rep[r] == r && w.pres[r]) {
+        u32 root = uf_find(w.par, r);
+        atomicAdd(&w.csize[root], 1u);
+        atomicMin((unsigned long long*)&w.ct[root], (unsigned long long)w.tv[r]);
+      }
+    }
+    gsync();
+    // largest component; ties -> lowest label = the one holding the earliest-inserted vertex
+    for (u32 r = tid; r < m; r += NT) {
+      if (w.rep[r] == r && w.pres[r] && w.par[r] == r) {
+        unsigned long long key = ((unsigned long long)w.csize[r] << 42) | ((1ull << 42) - 1 - w.ct[r]);
+        atomicMax(&s_best[grp], key);
+      }
+    }
+    gsync();
+    for (u32 r = tid; r < m; r += NT) {
+      if (w.rep[r] == r && w.pres[r] && w.par[r] == r) {
+        unsigned long long key = ((unsigned long long)w.csize[r] << 42) | ((1ull << 42) - 1 - w.ct[r]);
+        if (key == s_best[grp]) s_bestroot[grp] = r;
+      }
+    }
+    gsync();
+    const u32 broot = s_bestroot[grp];
+    // ---- output in vertex order (first appearance in the edge list, source before target) ----
+    for (u32 r = tid; r < m; r += NT) {
+      if (w.rep[r] == r && w.pres[r] && uf_find(w.par, r) == broot) {
+        u64 t = w.tv[r];
+        u32 rank = 0;
+        for (u32 q = 0; q < m; q++)
+          if (w.rep[q] == q && w.pres[q] && w.tv[q] < t && uf_find(w.par, q) == broot) rank++;
+        V.out_id[a + rank] = w.ID[r];
+        V.out_gidx[a + rank] = w.G[r];
+      }
+    }
+    if (tid == 0) V.seg_cnt[s] = w.csize[broot];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pairs_compact(const u32* __restrict__ seg_start, const u32* __restrict__ seg_cnt,
+                                                       const u32* __restrict__ seg_off, u32 n_seg, const u32* __restrict__ out_id,
+                                                       const u32* __restrict__ out_gidx, const u32* __restrict__ read,
+                                                       const u32* __restrict__ contig, u32* p_read, u32* p_contig, u32* p_group,
+                                                       u32* p_gidx) {
+  u32 wv = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (wv >= n_seg) return;
+  u32 c = seg_cnt[wv];
+  if (!c) return;
+  u32 a = seg_start[wv], o = seg_off[wv];
+  u32 rd = read[a], ct = contig[a];
+  for (u32 i = lane; i < c; i += 32) {
+    p_read[o + i] = rd;
+    p_contig[o + i] = ct;
+    p_group[o + i] = out_id[a + i];
+    p_gidx[o + i] = out_gidx[a + i];
+  }
+}
+
+extern "C" int gvs_validate(gvs_ctx* ctx, uint32_t min_read_len, uint64_t* n_pairs_out) {
+  if (!ctx) return GVS_E_ARG;
+  if (!ctx->diag_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_validate before gvs_diag_filter / gvs_rows_set(1)");
+  if (!ctx->read_off && !ctx->have_read_len) return gvs_fail(ctx, GVS_E_STATE, "gvs_validate: read lengths unknown");
+  CK(cudaSetDevice(ctx->device));
+  StageTimer tm(ctx, GVS_ST_VALIDATE);
+  ctx->val_ready = false;
+  ctx->n_pairs = 0;
+  if (n_pairs_out) *n_pairs_out = 0;
+  Rows& R = ctx->kept;
+  u64 n = R.n;
+  if (n == 0) {
+    ctx->val_ready = true;
+    return 0;
+  }
+  u64 n_seg = 0;
+  CKR(gvs_build_segments(ctx, R.read.as<u32>(), n, ctx->kseg_start, ctx->flags_c, &n_seg));
+  ctx->n_kseg = n_seg;
+  const u32* seg_start = ctx->kseg_start.as<u32>();
+  // scratch: out_id[n], out_gidx[n], seg_cnt[n_seg], seg_off[n_seg]
+  CKR(gvs_reserve(ctx, ctx->val_scratch, (2 * n + 2 * n_seg + 16) * 4));
+  u32* out_id = ctx->val_scratch.as<u32>();
+  u32* out_gidx = out_id + n;
+  u32* seg_cnt = out_gidx + n;
+  u32* seg_off = seg_cnt + n_seg;
+  // largest read (rows) decides which launches are needed
+  u32* mx_dev = (u32*)(ctx->counters.as<u64>() + 22);
+  {
+    auto f2 = [seg_start] __device__(u64 s) -> u32 { return seg_start[s + 1] - seg_start[s]; };
+    auto g2 = [] __device__(u64 s, u32 ex, u32 v) {};
+    CKR((device_scan<u32>(ctx, n_seg, f2, g2, OpMax(), mx_dev)));
+  }
+  u32 max_m = 0;
+  CKR(read_dev(ctx, mx_dev, &max_m));
+  u32* stats = (u32*)(ctx->counters.as<u64>() + 23);
+  CK(cudaMemsetAsync(stats, 0, 8, ctx->stream));
+  ValParams V;
+  V.read = R.read.as<u32>(); V.pos = R.pos.as<u32>(); V.start = R.start.as<u32>(); V.group = R.group.as<u32>();
+  V.gidx = R.gidx.as<u32>();
+  V.seg_start = seg_start; V.n_seg = (u32)n_seg;
+  V.bad = ctx->bad_ready ? ctx->bad_flag.as<u8>() : nullptr;
+  V.read_off = ctx->read_off; V.read_len = ctx->have_read_len ? ctx->read_len.as<u32>() : nullptr;
+  V.min_len = min_read_len;
+  V.out_id = out_id; V.out_gidx = out_gidx; V.seg_cnt = seg_cnt;
+  V.gscratch = nullptr; V.big_cap = 0; V.stats = stats;
+  static bool attr_set = false;
+  const size_t sm_warp = (size_t)VROW_BYTES * VCAP_WARP * 8, sm_blk = (size_t)VROW_BYTES * VCAP;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute((k_validate<32, 8, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+    CK(cudaFuncSetAttribute((k_validate<128, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
+    attr_set = true;
+  }
+  {  // reads with <= 64 rows: one warp each (includes the reads with < 2 rows, which just report 0)
+    V.m_lo = 0; V.m_hi = VCAP_WARP;
+    u64 grid = cdiv(n_seg, 8);
+    u64 capg = (u64)ctx->n_sm * 5;
+    if (grid > capg) grid = capg;
+    LAUNCH((k_validate<32, 8, false>), (unsigned)grid, 256, sm_warp, V);
+  }
+  if (max_m > VCAP_WARP) {
+    V.m_lo = VCAP_WARP; V.m_hi = VCAP;
+    u64 grid = n_seg;
+    u64 capg = (u64)ctx->n_sm * 5;
+    if (grid > capg) grid = capg;
+    LAUNCH((k_validate<128, 1, false>), (unsigned)grid, 128, sm_blk, V);
+  }
+  if (max_m > VCAP) {
+    u32 blocks = (u32)ctx->n_sm;
+    u32 bcap = (max_m + 15) & ~15u;
+    CKR(gvs_reserve(ctx, ctx->scan_tmp2, (u64)blocks * VROW_BYTES * bcap));
+    V.gscratch = ctx->scan_tmp2.as<u8>();
+    V.big_cap = bcap;
+    V.m_lo = VCAP; V.m_hi = 0xFFFFFFFFu;
+    LAUNCH((k_validate<1024, 1, true>), blocks, 1024, 0, V);
+  }
+  // compaction of the validated (ID, read) pairs
+  u32* tot = (u32*)(ctx->counters.as<u64>() + 25);
+  {
+    auto f = [seg_cnt] __device__(u64 s) -> u32 { return seg_cnt[s]; };
+    auto g = [seg_off] __device__(u64 s, u32 ex, u32 v) { seg_off[s] = ex; };
+    CKR((device_scan<u32>(ctx, n_seg, f, g, OpSum(), tot)));
+  }
+  u32 np = 0;
+  CKR(read_dev(ctx, tot, &np));
+  CKR(gvs_reserve(ctx, ctx->pair_read, (u64)np * 4));
+  CKR(gvs_reserve(ctx, ctx->pair_contig, (u64)np * 4));
+  CKR(gvs_reserve(ctx, ctx->pair_group, (u64)np * 4));
+  CKR(gvs_reserve(ctx, ctx->pair_gidx, (u64)np * 4));
+  if (np)
+    LAUNCH(k_pairs_compact, (unsigned)cdiv(n_seg * 32, 256), 256, 0, seg_start, seg_cnt, seg_off, (u32)n_seg, out_id, out_gidx,
+           R.read.as<u32>(), R.contig.as<u32>(), ctx->pair_read.as<u32>(), ctx->pair_contig.as<u32>(),
+           ctx->pair_group.as<u32>(), ctx->pair_gidx.as<u32>());
+  ctx->n_pairs = np;
+  ctx->val_ready = true;
+  if (n_pairs_out) *n_pairs_out = np;
+  return 0;
+}
+
+extern "C" int gvs_pairs_get(gvs_ctx* ctx, uint32_t* read_idx, uint32_t* contig, uint32_t* group, uint32_t* group_index) {
+  if (!ctx) return GVS_E_ARG;
+  if (!ctx->val_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_pairs_get before gvs_validate");
+  CK(cudaSetDevice(ctx->device));
+  u64 n = ctx->n_pairs;
+  if (n == 0) return 0;
+  if (read_idx) CK(cudaMemcpyAsync(read_idx, ctx->pair_read.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (contig) CK(cudaMemcpyAsync(contig, ctx->pair_contig.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (group) CK(cudaMemcpyAsync(group, ctx->pair_group.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (group_index) CK(cudaMemcpyAsync(group_index, ctx->pair_gidx.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
