@@ -146,17 +146,20 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       if (tid == 0) V.seg_cnt[s] = 0;
       continue;
     }
-    const u64 cells = (u64)m * m;
+    // All passes are row-centric: the thread that owns row r walks every other row q (shared-memory
+    // broadcast reads, no atomics on the pair data).  Pairs are always evaluated as (min, max) of the
+    // sorted order, i.e. exactly the reference's combination (i < j).
     // ---- pass A: masked pairs by sign (:140-152) ----
     {
       u32 n0 = 0, n1 = 0;
-      u32 i = tid / m, j = tid % m;
-      for (u64 c = tid; c < cells; c += NT) {
-        if (i < j && pair_ok(w.P[i], w.S[i], w.P[j], w.S[j])) {
-          if (w.P[i] > w.P[j]) n1++; else n0++;
+      for (u32 r = tid; r < m; r += NT) {
+        const u32 pr = w.P[r], sr = w.S[r];
+        for (u32 q = r + 1; q < m; q++) {
+          u32 pq = w.P[q];
+          if (pair_ok(pr, sr, pq, w.S[q])) {
+            if (pr > pq) n1++; else n0++;
+          }
         }
-        j += NT;
-        while (j >= m) { j -= m; i++; }
       }
       for (int d = 16; d; d >>= 1) {
         n0 += __shfl_xor_sync(0xFFFFFFFFu, n0, d);
@@ -173,24 +176,25 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       continue;
     }
     const bool orient = s_n1[grp] > s_n0[grp];  // np.unique sorted + argmax: a tie keeps 0 (:151-152)
-    // ---- pass B: incidence of every row in the oriented edge list (the (ID,pos) multiset M) ----
-    {
-      u32 i = tid / m, j = tid % m;
-      for (u64 c = tid; c < cells; c += NT) {
-        if (i < j && pair_ok(w.P[i], w.S[i], w.P[j], w.S[j]) && ((w.P[i] > w.P[j]) == orient)) {
-          atomicAdd(&w.deg[i], 1u);
-          atomicAdd(&w.deg[j], 1u);
-          w.left[i] = 1;
-          atomicMin(&w.fpart[j], i);
-        }
-        j += NT;
-        while (j >= m) { j -= m; i++; }
+    // ---- pass B: incidence of every row in the oriented edge list (the (ID,pos) multiset M) and its
+    //      order of first appearance in M = [all left ends in edge order] + [all right ends] ----
+    for (u32 r = tid; r < m; r += NT) {
+      const u32 pr = w.P[r], sr = w.S[r];
+      u32 deg = 0, fpart = NOV;
+      bool left = false;
+      for (u32 q = 0; q < m; q++) {
+        if (q == r) continue;
+        u32 pq = w.P[q];
+        if (!pair_ok(pr, sr, pq, w.S[q])) continue;
+        bool sign = q > r ? pr > pq : pq > pr;  // sign of the pair (min, max)
+        if (sign != orient) continue;
+        deg++;
+        if (q > r) left = true;
+        else if (fpart == NOV) fpart = q;  // first edge (q, r) with this row as the right end
       }
+      w.deg[r] = deg;
+      w.key[r] = left ? (u64)r : ((1ull << 63) | ((u64)fpart * m + r));
     }
-    gsync();
-    // order of first appearance in M = [all left ends in edge order] + [all right ends in edge order]
-    for (u32 r = tid; r < m; r += NT)
-      w.key[r] = w.left[r] ? (u64)r : ((1ull << 63) | ((u64)w.fpart[r] * m + r));
     gsync();
     // ---- multipos (:161-181): IDs seen at more than one read position keep their most frequent one ----
     for (u32 r = tid; r < m; r += NT) {
@@ -214,25 +218,37 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     // ---- pass C: surviving edges -> graph on IDs (:189-192) ----
     {
       u32 nk = 0;
-      u32 i = tid / m, j = tid % m;
-      for (u64 c = tid; c < cells; c += NT) {
-        if (i < j && pair_ok(w.P[i], w.S[i], w.P[j], w.S[j]) && ((w.P[i] > w.P[j]) == orient)) {
-          // dropped iff the left ID is multi-positioned, this is not its good row and the right row is
-          // not that ID's good row either (left end only: Q14)
-          bool drop = w.multi[i] && !w.good[i] && !(w.good[j] && w.ID[j] == w.ID[i]);
-          if (!drop) {
+      for (u32 r = tid; r < m; r += NT) {
+        const u32 pr = w.P[r], sr = w.S[r], idr = w.ID[r], repr_ = w.rep[r];
+        const bool mr = w.multi[r], gr = w.good[r];
+        u64 tmin = NOT64;  // first appearance of this row in the surviving edge list
+        for (u32 q = 0; q < m; q++) {
+          if (q == r) continue;
+          u32 pq = w.P[q];
+          if (!pair_ok(pr, sr, pq, w.S[q])) continue;
+          bool sign = q > r ? pr > pq : pq > pr;
+          if (sign != orient) continue;
+          // dropped iff the LEFT row's ID is multi-positioned, it is not that ID's good row and the
+          // right row is not that ID's good row either (left end only: Q14)
+          bool drop;
+          if (q > r) drop = mr && !gr && !(w.good[q] && w.ID[q] == idr);
+          else drop = w.multi[q] && !w.good[q] && !(gr && idr == w.ID[q]);
+          if (drop) continue;
+          if (q > r) {
             nk++;
-            u32 ri = w.rep[i], rj = w.rep[j];
-            u64 e = (u64)i * m + j;
-            w.pres[ri] = 1;
-            w.pres[rj] = 1;
-            atomicMin((unsigned long long*)&w.tv[ri], (unsigned long long)(2 * e));
-            atomicMin((unsigned long long*)&w.tv[rj], (unsigned long long)(2 * e + 1));
-            if (ri != rj) uf_union(w.par, ri, rj);
+            u64 e = 2 * ((u64)r * m + q);
+            if (e < tmin) tmin = e;
+            u32 rq = w.rep[q];
+            if (repr_ != rq) uf_union(w.par, repr_, rq);
+          } else {
+            u64 e = 2 * ((u64)q * m + r) + 1;
+            if (e < tmin) tmin = e;
           }
         }
-        j += NT;
-        while (j >= m) { j -= m; i++; }
+        if (tmin != NOT64) {
+          w.pres[repr_] = 1;
+          atomicMin((unsigned long long*)&w.tv[repr_], (unsigned long long)tmin);
+        }
       }
       if (nk) atomicAdd(&s_kept[grp], nk);
     }
