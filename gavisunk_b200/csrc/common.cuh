@@ -227,9 +227,27 @@ __host__ __device__ __forceinline__ u32 gvs_fhash(u64 key) {
   h ^= h >> 12;
   return h;
 }
-__host__ __device__ __forceinline__ u32 gvs_fbits(u32 h) {
-  u32 g = h * 0x297A2D39u;
-  return (1u << (g >> 27)) | (1u << ((g >> 22) & 31));
+// Blocked filter: a block is 4 x u32; a key sets bit (h >> 5i) & 31 of word i (h = gvs_fhash(key)).
+// The block is selected by the canonical form of a sub-mer of length K-J+1 of the key; a key is
+// inserted once per sub-mer offset (J times), so J consecutive read windows share one block.
+#define GVS_FJ(K) ((K) >= 4 ? 4 : 1)
+__host__ __device__ __forceinline__ u32 gvs_bhash(u64 sub) {
+  u32 lo = (u32)sub, hi = (u32)(sub >> 32);
+  u32 h = (lo * 0xCC9E2D51u) ^ (hi * 0x1B873593u + 0x7F4A7C15u);
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  return h;
+}
+// reverse complement of an L-mer in 2-bit big-endian packing
+__host__ __device__ __forceinline__ u64 gvs_revcomp(u64 x, int L) {
+  u64 y = ~x;
+  y = ((y >> 2) & 0x3333333333333333ull) | ((y & 0x3333333333333333ull) << 2);
+  y = ((y >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((y & 0x0F0F0F0F0F0F0F0Full) << 4);
+  y = ((y >> 8) & 0x00FF00FF00FF00FFull) | ((y & 0x00FF00FF00FF00FFull) << 8);
+  y = ((y >> 16) & 0x0000FFFF0000FFFFull) | ((y & 0x0000FFFF0000FFFFull) << 16);
+  y = (y >> 32) | (y << 32);
+  return y >> (64 - 2 * L);
 }
 // table: bucket (4 slots = one 32-byte sector of keys) from bits 24.. of the hash
 __host__ __device__ __forceinline__ u64 gvs_tab_bucket(u64 h, u64 tab_slots) { return (h >> 24) & ((tab_slots >> 2) - 1); }

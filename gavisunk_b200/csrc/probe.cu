@@ -229,8 +229,27 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           inval |= 0xFFFFu & ~((1u << nv) - 1);
         }
       }
-      u32 fword[16];
-      u32 fhash[16];
+      // Filter blocks: J consecutive windows share the (K-J+1)-mer that starts at the last of them, and
+      // every SUNK was inserted into the block of each of its J sub-mers (table.cu), so ONE 16-byte
+      // block load serves J windows: 0.25 scattered sectors per base instead of 1.
+      constexpr int J = GVS_FJ(K);
+      constexpr int L = K - J + 1;
+      constexpr int NG = 16 / J;
+      uint4 blk[NG];
+#pragma unroll
+      for (int g = 0; g < NG; g++) {
+        const int o = J * g + (J - 1);  // lane-relative base offset of the shared sub-mer
+        u64 sf = p_extract<L>(f0, f1, f2, o);
+        const int e = o + L;            // = J*g + K, inside [K, K+15] like the windows' own ends
+        const int c = (e + 15) / 16;
+        const int j0 = CMAX - c;
+        const int off = 16 * c - e;
+        u64 sr = (j0 == 0) ? p_extract<L>(r0, r1, r2, off) : p_extract<L>(r1, r2, r3, off);
+        u32 hb = gvs_bhash(sf < sr ? sf : sr);
+        const u32 gm = (1u << J) - 1;
+        bool any_valid = ((inval >> (J * g)) & gm) != gm;
+        blk[g] = any_valid ? __ldg((const uint4*)P.filt + (hb & P.filt_mask)) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
       for (int i = 0; i < 16; i++) {
         u64 f = p_extract<K>(f0, f1, f2, i);
@@ -241,23 +260,25 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         u64 r = (j0 == 0) ? p_extract<K>(r0, r1, r2, off) : p_extract<K>(r1, r2, r3, off);
         u64 canon = f < r ? f : r;
         u32 h = gvs_fhash(canon);
-        fhash[i] = h;
-        fword[i] = ((inval >> i) & 1) ? 0u : __ldg(P.filt + (h & P.filt_mask));
-      }
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        u32 m = gvs_fbits(fhash[i]);
-        if ((fword[i] & m) == m) cm |= 1u << i;
+        const uint4 b4 = blk[i / J];
+        u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
+                __funnelshift_r(b4.w, 0u, h >> 15);
+        cm |= (t & 1u) << i;
       }
       cm &= ~inval;
       if (S16) {  // bogus windows of (K-1)-long reads: last base read as A, always "valid"
         for (u32 s = S16; s; s &= s - 1) {
           int i = __ffs(s) - 1;
-          u64 canon = p_canon_at<K>(sm.fw, sm.rc, 16u * lane + i, true);
+          u32 p = 16u * lane + i;
+          u64 canon = p_canon_at<K>(sm.fw, sm.rc, p, true);
+          // its own first sub-mer (real bases only) selects the block
+          u64 sub = (p_extract<K>(sm.fw[p >> 4], sm.fw[(p >> 4) + 1], sm.fw[(p >> 4) + 2], p & 15) & ~3ull) >> (2 * (K - L));
+          u64 subr = gvs_revcomp(sub, L);
+          uint4 b4 = __ldg((const uint4*)P.filt + (gvs_bhash(sub < subr ? sub : subr) & P.filt_mask));
           u32 h = gvs_fhash(canon);
-          u32 m = gvs_fbits(h);
-          u32 wv = __ldg(P.filt + (h & P.filt_mask));
-          if ((wv & m) == m) cm |= 1u << i; else cm &= ~(1u << i);
+          u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
+                  __funnelshift_r(b4.w, 0u, h >> 15);
+          if (t & 1u) cm |= 1u << i; else cm &= ~(1u << i);
         }
       }
       cm |= (S16 << 16);  // remember which candidates are forced-A windows

@@ -2,12 +2,17 @@
 // (workflow/scripts/process-by-contig_lowmem_AR.py:50-207).
 //
 // One thread group per read: a warp for reads with <= 64 rows (8 reads per 256-thread block, no block
-// barriers), a 128-thread block with shared memory up to 512 rows, a 1024-thread block with global
-// scratch beyond.  Rows minus bad groups -> stable rank-sort by assembly start -> every pair (i<j)
-// tested with the integer form of the reference's float64 ratio test (0.9 < dpos/dstart < 1.1  <=>
-// 9*ds < 10*dp < 11*ds, exact for 32-bit inputs) -> orientation majority -> "multipos" clean-up ->
-// union-find over group IDs -> largest component (ties: the component holding the earliest vertex in
-// graph-tool's insertion order) -> output in vertex order.
+// barriers), a 256-thread block with shared memory up to 512 rows, a 1024-thread block with global
+// scratch beyond.  Rows minus bad groups -> rank-sort by (assembly start, read position) -> every
+// pair (i<j) tested with the integer form of the reference's float64 ratio test (0.9 < dpos/dstart <
+// 1.1  <=>  9*ds < 10*dp < 11*ds, exact for 32-bit inputs) -> orientation majority -> "multipos"
+// clean-up -> connected components of the graph on group IDs -> largest component (ties: the
+// component holding the earliest vertex in graph-tool's insertion order) -> output in vertex order.
+//
+// Every pass is row-centric and branch-free: the thread that owns row r walks all rows q with
+// shared-memory broadcast reads and predicated arithmetic; the pair predicate is recomputed instead
+// of stored (the edge list of a read is O(rows^2)).  Components come from min-label propagation over
+// the recomputed edge predicate (a few rounds: these graphs are dense), not from per-edge atomics.
 #include "common.cuh"
 
 #define VCAP_WARP 64      // rows per read handled by one warp
@@ -16,12 +21,15 @@
 #define NOV 0xFFFFFFFFu
 #define NOT64 0xFFFFFFFFFFFFFFFFull
 
+#define F_MULTI 1u   // the row's ID occurs at more than one read position among the oriented edges
+#define F_GOOD 2u    // ... and this row is the ID's most frequent position
+#define F_PRES 4u    // the row has at least one surviving edge
+
 struct VWork {
   u32 *P, *S, *ID, *G;        // rows sorted by (assembly start, read position)
   u32 *uP, *uS, *uID, *uG;    // rows after bad-group removal (any order)
-  u32 *deg, *fpart, *rep, *par, *csize;
+  u32 *deg, *rep, *label, *csize, *flags;
   u64 *key, *tv, *ct;
-  u8 *good, *multi, *pres, *left;
 };
 
 __device__ __forceinline__ void vwork_carve(VWork& w, u8* base, u32 cap) {
@@ -32,9 +40,7 @@ __device__ __forceinline__ void vwork_carve(VWork& w, u8* base, u32 cap) {
   u32* p = (u32*)q;
   w.P = p; p += cap; w.S = p; p += cap; w.ID = p; p += cap; w.G = p; p += cap;
   w.uP = p; p += cap; w.uS = p; p += cap; w.uID = p; p += cap; w.uG = p; p += cap;
-  w.deg = p; p += cap; w.fpart = p; p += cap; w.rep = p; p += cap; w.par = p; p += cap; w.csize = p; p += cap;
-  u8* b = (u8*)p;
-  w.good = b; b += cap; w.multi = b; b += cap; w.pres = b; b += cap; w.left = b; b += cap;
+  w.deg = p; p += cap; w.rep = p; p += cap; w.label = p; p += cap; w.csize = p; p += cap; w.flags = p; p += cap;
 }
 
 // 0.9 < dpos/dstart < 1.1 in float64 (process-by-contig_lowmem_AR.py:145-147) as exact integers (Q12)
@@ -42,21 +48,6 @@ __device__ __forceinline__ bool pair_ok(u32 pi, u32 si, u32 pj, u32 sj) {
   u64 ds = si > sj ? si - sj : sj - si;
   u64 dp = pi > pj ? pi - pj : pj - pi;
   return 9 * ds < 10 * dp && 10 * dp < 11 * ds;
-}
-
-__device__ __forceinline__ u32 uf_find(const volatile u32* par, u32 x) {
-  u32 p = par[x];
-  while (p != x) { x = p; p = par[x]; }
-  return x;
-}
-__device__ __forceinline__ void uf_union(u32* par, u32 a, u32 b) {
-  for (;;) {
-    a = uf_find(par, a);
-    b = uf_find(par, b);
-    if (a == b) return;
-    u32 hi = a > b ? a : b, lo = a > b ? b : a;
-    if (atomicCAS(&par[hi], hi, lo) == hi) return;
-  }
 }
 
 struct ValParams {
@@ -80,7 +71,7 @@ struct ValParams {
 template <int NT, int GROUPS, bool GLOBAL>
 __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
   extern __shared__ __align__(16) u8 smem[];
-  __shared__ u32 s_n0[GROUPS], s_n1[GROUPS], s_m[GROUPS], s_kept[GROUPS], s_bestroot[GROUPS], s_distinct[GROUPS];
+  __shared__ u32 s_n0[GROUPS], s_n1[GROUPS], s_m[GROUPS], s_kept[GROUPS], s_bestroot[GROUPS], s_flag[GROUPS];
   __shared__ unsigned long long s_best[GROUPS];
   const int grp = threadIdx.x / NT;
   const int tid = threadIdx.x % NT;
@@ -97,7 +88,7 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     const u32 mrows = b - a;
     if (mrows <= V.m_lo || mrows > V.m_hi) continue;  // another launch owns this read (group-uniform)
     gsync();
-    if (tid == 0) { s_m[grp] = 0; s_n0[grp] = 0; s_n1[grp] = 0; s_kept[grp] = 0; s_best[grp] = 0; s_bestroot[grp] = NOV; s_distinct[grp] = 0; }
+    if (tid == 0) { s_m[grp] = 0; s_n0[grp] = 0; s_n1[grp] = 0; s_kept[grp] = 0; s_best[grp] = 0; s_bestroot[grp] = NOV; s_flag[grp] = 0; }
     gsync();
     // read length filter (hard-coded 10000 in the reference, :106-108; Q13)
     const u32 rd = V.read[a];
@@ -124,41 +115,44 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     // ---- sort by (start, pos): sort_values(['rname','start']) is stable and rows of a read come in
     //      increasing pos (:100) ----
     for (u32 i = tid; i < m; i += NT) {
-      u32 si = w.uS[i], pi = w.uP[i], rank = 0;
+      const u32 si = w.uS[i], pi = w.uP[i];
+      u32 rank = 0;
       for (u32 j = 0; j < m; j++) {
-        u32 sj = w.uS[j];
-        rank += (sj < si) || (sj == si && w.uP[j] < pi);
+        u32 sj = w.uS[j], pj = w.uP[j];
+        rank += (sj < si) | ((sj == si) & (pj < pi));
       }
       w.P[rank] = pi;
       w.S[rank] = si;
       w.ID[rank] = w.uID[i];
       w.G[rank] = w.uG[i];
-      w.deg[i] = 0; w.fpart[i] = NOV; w.par[i] = i; w.csize[i] = 0;
-      w.tv[i] = NOT64; w.ct[i] = NOT64;
-      w.good[i] = 0; w.multi[i] = 0; w.pres[i] = 0; w.left[i] = 0;
+      w.csize[i] = 0;
+      w.tv[i] = NOT64;
+      w.ct[i] = NOT64;
     }
     gsync();
     // at least two distinct groups (:91-97)
-    for (u32 i = tid; i < m; i += NT)
-      if (w.ID[i] != w.ID[0]) s_distinct[grp] = 1;
+    {
+      const u32 id0 = w.ID[0];
+      u32 any = 0;
+      for (u32 i = tid; i < m; i += NT) any |= w.ID[i] != id0;
+      if (any) s_flag[grp] = 1;
+    }
     gsync();
-    if (!s_distinct[grp]) {
+    if (!s_flag[grp]) {
       if (tid == 0) V.seg_cnt[s] = 0;
       continue;
     }
-    // All passes are row-centric: the thread that owns row r walks every other row q (shared-memory
-    // broadcast reads, no atomics on the pair data).  Pairs are always evaluated as (min, max) of the
-    // sorted order, i.e. exactly the reference's combination (i < j).
-    // ---- pass A: masked pairs by sign (:140-152) ----
+    // ---- pass A: masked pairs by sign (:140-152); every unordered pair is seen twice ----
     {
       u32 n0 = 0, n1 = 0;
       for (u32 r = tid; r < m; r += NT) {
         const u32 pr = w.P[r], sr = w.S[r];
-        for (u32 q = r + 1; q < m; q++) {
-          u32 pq = w.P[q];
-          if (pair_ok(pr, sr, pq, w.S[q])) {
-            if (pr > pq) n1++; else n0++;
-          }
+        for (u32 q = 0; q < m; q++) {
+          u32 pq = w.P[q], sq = w.S[q];
+          u32 ok = pair_ok(pr, sr, pq, sq) & (q > r);
+          u32 sg = pr > pq;  // sign of (i, j) = pos_i > pos_j with i = r < j = q
+          n1 += ok & sg;
+          n0 += ok & (sg ^ 1u);
         }
       }
       for (int d = 16; d; d >>= 1) {
@@ -175,22 +169,20 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       if (tid == 0) V.seg_cnt[s] = 0;
       continue;
     }
-    const bool orient = s_n1[grp] > s_n0[grp];  // np.unique sorted + argmax: a tie keeps 0 (:151-152)
+    const u32 orient = s_n1[grp] > s_n0[grp];  // np.unique sorted + argmax: a tie keeps 0 (:151-152)
     // ---- pass B: incidence of every row in the oriented edge list (the (ID,pos) multiset M) and its
     //      order of first appearance in M = [all left ends in edge order] + [all right ends] ----
     for (u32 r = tid; r < m; r += NT) {
       const u32 pr = w.P[r], sr = w.S[r];
-      u32 deg = 0, fpart = NOV;
-      bool left = false;
+      u32 deg = 0, fpart = NOV, left = 0;
       for (u32 q = 0; q < m; q++) {
-        if (q == r) continue;
-        u32 pq = w.P[q];
-        if (!pair_ok(pr, sr, pq, w.S[q])) continue;
-        bool sign = q > r ? pr > pq : pq > pr;  // sign of the pair (min, max)
-        if (sign != orient) continue;
-        deg++;
-        if (q > r) left = true;
-        else if (fpart == NOV) fpart = q;  // first edge (q, r) with this row as the right end
+        u32 pq = w.P[q], sq = w.S[q];
+        u32 hi = q > r;
+        u32 sg = hi ? (pr > pq) : (pq > pr);  // sign of the pair ordered (min, max)
+        u32 e = pair_ok(pr, sr, pq, sq) & (q != r) & (sg == orient);
+        deg += e;
+        left |= e & hi;
+        fpart = (e & (hi ^ 1u) & (fpart == NOV)) ? q : fpart;  // first edge (q, r) with r as the right end
       }
       w.deg[r] = deg;
       w.key[r] = left ? (u64)r : ((1ull << 63) | ((u64)fpart * m + r));
@@ -198,57 +190,51 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     gsync();
     // ---- multipos (:161-181): IDs seen at more than one read position keep their most frequent one ----
     for (u32 r = tid; r < m; r += NT) {
-      u32 id = w.ID[r], dr = w.deg[r];
-      u32 first = r;
-      bool multi = false, good = dr > 0;
+      const u32 id = w.ID[r], dr = w.deg[r];
+      const u64 kr = w.key[r];
+      u32 first = r, multi = 0, good = dr > 0;
       for (u32 q = 0; q < m; q++) {
-        if (w.ID[q] != id) continue;
-        if (q < first) first = q;
-        if (q == r) continue;
+        u32 same = (w.ID[q] == id);
         u32 dq = w.deg[q];
-        if (dq == 0) continue;
-        multi = true;
-        if (dq > dr || (dq == dr && w.key[q] < w.key[r])) good = false;
+        first = (same & (q < first)) ? q : first;
+        u32 other = same & (q != r) & (dq > 0);
+        multi |= other;
+        u32 beats = other & ((dq > dr) | ((dq == dr) & (w.key[q] < kr)));
+        good &= beats ^ 1u;
       }
       w.rep[r] = first;
-      w.multi[r] = (multi && dr > 0) ? 1 : 0;
-      w.good[r] = good ? 1 : 0;
+      w.flags[r] = ((multi & (dr > 0)) ? F_MULTI : 0u) | (good ? F_GOOD : 0u);
     }
     gsync();
-    // ---- pass C: surviving edges -> graph on IDs (:189-192) ----
+    // ---- pass C: surviving edges (:189-192): presence, first appearance, first label ----
+    // edge (lo, hi) is dropped iff the LEFT row's ID is multi-positioned, lo is not that ID's good row and
+    // hi is not that ID's good row either (left end only: Q14)
     {
       u32 nk = 0;
       for (u32 r = tid; r < m; r += NT) {
-        const u32 pr = w.P[r], sr = w.S[r], idr = w.ID[r], repr_ = w.rep[r];
-        const bool mr = w.multi[r], gr = w.good[r];
-        u64 tmin = NOT64;  // first appearance of this row in the surviving edge list
+        const u32 pr = w.P[r], sr = w.S[r], idr = w.ID[r], fr = w.flags[r];
+        u64 tmin = NOT64;
+        u32 lab = NOV;
         for (u32 q = 0; q < m; q++) {
-          if (q == r) continue;
-          u32 pq = w.P[q];
-          if (!pair_ok(pr, sr, pq, w.S[q])) continue;
-          bool sign = q > r ? pr > pq : pq > pr;
-          if (sign != orient) continue;
-          // dropped iff the LEFT row's ID is multi-positioned, it is not that ID's good row and the
-          // right row is not that ID's good row either (left end only: Q14)
-          bool drop;
-          if (q > r) drop = mr && !gr && !(w.good[q] && w.ID[q] == idr);
-          else drop = w.multi[q] && !w.good[q] && !(gr && idr == w.ID[q]);
-          if (drop) continue;
-          if (q > r) {
-            nk++;
-            u64 e = 2 * ((u64)r * m + q);
-            if (e < tmin) tmin = e;
-            u32 rq = w.rep[q];
-            if (repr_ != rq) uf_union(w.par, repr_, rq);
-          } else {
-            u64 e = 2 * ((u64)q * m + r) + 1;
-            if (e < tmin) tmin = e;
-          }
+          u32 pq = w.P[q], sq = w.S[q], idq = w.ID[q], fq = w.flags[q];
+          u32 hi = q > r;
+          u32 sg = hi ? (pr > pq) : (pq > pr);
+          u32 e = pair_ok(pr, sr, pq, sq) & (q != r) & (sg == orient);
+          u32 fl = hi ? fr : fq, fh = hi ? fq : fr;  // flags of the left / right row of the pair
+          u32 drop = ((fl & F_MULTI) != 0) & ((fl & F_GOOD) == 0) & (((fh & F_GOOD) == 0) | (idq != idr));
+          u32 kept = e & (drop ^ 1u);
+          u32 lo_row = hi ? r : q, hi_row = hi ? q : r;
+          u64 et = 2 * ((u64)lo_row * m + hi_row) + (hi ^ 1u);  // source before target
+          tmin = (kept && et < tmin) ? et : tmin;
+          nk += kept & hi;
+          u32 rq = w.rep[q];
+          lab = (kept && rq < lab) ? rq : lab;
         }
-        if (tmin != NOT64) {
-          w.pres[repr_] = 1;
-          atomicMin((unsigned long long*)&w.tv[repr_], (unsigned long long)tmin);
-        }
+        u32 present = tmin != NOT64;
+        u32 rr = w.rep[r];
+        w.flags[r] = fr | (present ? F_PRES : 0u);
+        w.label[r] = present ? (rr < lab ? rr : lab) : NOV;
+        if (present) atomicMin((unsigned long long*)&w.tv[rr], (unsigned long long)tmin);
       }
       if (nk) atomicAdd(&s_kept[grp], nk);
     }
@@ -260,25 +246,64 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       }
       continue;
     }
-    // ---- components: size and earliest vertex ----
-    for (u32 r = tid; r < m; r += NT) {
-      if (w.rep[r] == r && w.pres[r]) {
-        u32 root = uf_find(w.par, r);
-        atomicAdd(&w.csize[root], 1u);
-        atomicMin((unsigned long long*)&w.ct[root], (unsigned long long)w.tv[r]);
+    // ---- components: min-label propagation over surviving edges and same-ID rows until stable ----
+    for (int round = 0; round < 4096; round++) {
+      if (tid == 0) s_flag[grp] = 0;
+      gsync();
+      u32 changed = 0;
+      for (u32 r = tid; r < m; r += NT) {
+        const u32 fr = w.flags[r];
+        if (!(fr & F_PRES)) continue;
+        const u32 pr = w.P[r], sr = w.S[r], idr = w.ID[r];
+        u32 lab = w.label[r];
+        const u32 lab0 = lab;
+        for (u32 q = 0; q < m; q++) {
+          u32 pq = w.P[q], sq = w.S[q], idq = w.ID[q], fq = w.flags[q];
+          u32 hi = q > r;
+          u32 sg = hi ? (pr > pq) : (pq > pr);
+          u32 e = pair_ok(pr, sr, pq, sq) & (q != r) & (sg == orient);
+          u32 fl = hi ? fr : fq, fh = hi ? fq : fr;
+          u32 drop = ((fl & F_MULTI) != 0) & ((fl & F_GOOD) == 0) & (((fh & F_GOOD) == 0) | (idq != idr));
+          u32 link = (e & (drop ^ 1u)) | ((idq == idr) & ((fq & F_PRES) != 0));  // edge, or same vertex
+          u32 lq = w.label[q];  // may already be this round's value: only speeds convergence up
+          lab = (link && lq < lab) ? lq : lab;
+        }
+        if (lab != lab0) {
+          w.label[r] = lab;
+          changed = 1;
+        }
       }
+      if (changed) s_flag[grp] = 1;
+      gsync();
+      if (!s_flag[grp]) break;
+      gsync();
+    }
+    // ---- component sizes (distinct IDs) and earliest vertex ----
+    for (u32 r = tid; r < m; r += NT) {
+      u32 fr = w.flags[r];
+      if (!(fr & F_PRES)) continue;
+      // the first present row of an ID represents the vertex
+      const u32 idr = w.ID[r];
+      u32 firstp = r;
+      for (u32 q = 0; q < r; q++)
+        if (w.ID[q] == idr && (w.flags[q] & F_PRES)) { firstp = q; break; }
+      if (firstp != r) continue;
+      u32 lab = w.label[r];
+      atomicAdd(&w.csize[lab], 1u);
+      atomicMin((unsigned long long*)&w.ct[lab], (unsigned long long)w.tv[w.rep[r]]);
+      w.flags[r] = fr | 8u;  // vertex representative
     }
     gsync();
     // largest component; ties -> lowest label = the one holding the earliest-inserted vertex
     for (u32 r = tid; r < m; r += NT) {
-      if (w.rep[r] == r && w.pres[r] && w.par[r] == r) {
+      if (w.csize[r]) {
         unsigned long long key = ((unsigned long long)w.csize[r] << 42) | ((1ull << 42) - 1 - w.ct[r]);
         atomicMax(&s_best[grp], key);
       }
     }
     gsync();
     for (u32 r = tid; r < m; r += NT) {
-      if (w.rep[r] == r && w.pres[r] && w.par[r] == r) {
+      if (w.csize[r]) {
         unsigned long long key = ((unsigned long long)w.csize[r] << 42) | ((1ull << 42) - 1 - w.ct[r]);
         if (key == s_best[grp]) s_bestroot[grp] = r;
       }
@@ -287,11 +312,10 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     const u32 broot = s_bestroot[grp];
     // ---- output in vertex order (first appearance in the edge list, source before target) ----
     for (u32 r = tid; r < m; r += NT) {
-      if (w.rep[r] == r && w.pres[r] && uf_find(w.par, r) == broot) {
-        u64 t = w.tv[r];
+      if ((w.flags[r] & 8u) && w.label[r] == broot) {
+        const u64 t = w.tv[w.rep[r]];
         u32 rank = 0;
-        for (u32 q = 0; q < m; q++)
-          if (w.rep[q] == q && w.pres[q] && w.tv[q] < t && uf_find(w.par, q) == broot) rank++;
+        for (u32 q = 0; q < m; q++) rank += ((w.flags[q] & 8u) != 0) & (w.label[q] == broot) & (w.tv[w.rep[q]] < t);
         V.out_id[a + rank] = w.ID[r];
         V.out_gidx[a + rank] = w.G[r];
       }
@@ -369,7 +393,7 @@ extern "C" int gvs_validate(gvs_ctx* ctx, uint32_t min_read_len, uint64_t* n_pai
   const size_t sm_warp = (size_t)VROW_BYTES * VCAP_WARP * 8, sm_blk = (size_t)VROW_BYTES * VCAP;
   if (!attr_set) {
     CK(cudaFuncSetAttribute((k_validate<32, 8, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
-    CK(cudaFuncSetAttribute((k_validate<128, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
+    CK(cudaFuncSetAttribute((k_validate<256, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
     attr_set = true;
   }
   {  // reads with <= 64 rows: one warp each (includes the reads with < 2 rows, which just report 0)
@@ -384,7 +408,7 @@ extern "C" int gvs_validate(gvs_ctx* ctx, uint32_t min_read_len, uint64_t* n_pai
     u64 grid = n_seg;
     u64 capg = (u64)ctx->n_sm * 5;
     if (grid > capg) grid = capg;
-    LAUNCH((k_validate<128, 1, false>), (unsigned)grid, 128, sm_blk, V);
+    LAUNCH((k_validate<256, 1, false>), (unsigned)grid, 256, sm_blk, V);
   }
   if (max_m > VCAP) {
     u32 blocks = (u32)ctx->n_sm;
