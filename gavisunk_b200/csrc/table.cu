@@ -27,7 +27,9 @@ __global__ void k_tab_mark_db(const u64* __restrict__ kmer, u64 n, u64* keys, u3
     atomicOr(&rows[s], 0x80000000u);
   }
 }
-__global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slots, u32* filt, u64 filt_words) {
+__global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slots, u32* filt, u64 filt_blocks, int k) {
+  const int J = GVS_FJ(k), L = k - J + 1;
+  const u64 lmask = (L >= 32) ? ~0ull : ((1ull << (2 * L)) - 1);
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
     u64 key = keys[s];
     if (key == GVS_EMPTY_KEY) continue;
@@ -38,8 +40,17 @@ __global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slot
       continue;
     }
     rows[s] = r ? r - 1 : GVS_ROW_MISSING;
+    // one insertion per sub-mer offset: J consecutive read windows then share a single block
     u32 h = gvs_fhash(key);
-    atomicOr(&filt[h & (u32)(filt_words - 1)], gvs_fbits(h));
+    for (int j = 0; j < J; j++) {
+      u64 sub = (key >> (2 * (J - 1 - j))) & lmask;
+      u64 rc = gvs_revcomp(sub, L);
+      u64 blk = gvs_bhash(sub < rc ? sub : rc) & (filt_blocks - 1);
+      atomicOr(&filt[4 * blk + 0], 1u << (h & 31));
+      atomicOr(&filt[4 * blk + 1], 1u << ((h >> 5) & 31));
+      atomicOr(&filt[4 * blk + 2], 1u << ((h >> 10) & 31));
+      atomicOr(&filt[4 * blk + 3], 1u << ((h >> 15) & 31));
+    }
   }
 }
 
@@ -92,24 +103,25 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
   ctx->tab_slots = slots;
   CKR(gvs_reserve(ctx, ctx->tab_keys, slots * sizeof(u64)));
   CKR(gvs_reserve(ctx, ctx->tab_rows, slots * sizeof(u32)));
-  // filter: 32..64 bits per key in 32-bit words, capped at 2^24 words (64 MiB: L2-resident on B200)
-  u64 fw = next_pow2(n_loc ? n_loc : 1);
-  if (fw < (1ull << 12)) fw = 1ull << 12;
-  if (fw > (1ull << 24)) fw = 1ull << 24;
-  ctx->filt_words = fw;
-  CKR(gvs_reserve(ctx, ctx->filt, fw * sizeof(u32)));
+  // blocked filter: 16-byte blocks, J insertions per key, ~12 entries per block (FP ~1 %), power of
+  // two; 32 MiB for 5.9 M SUNKs (L2-resident), capped at 2^27 blocks (2 GiB) for human-size databases
+  u64 fw = next_pow2(cdiv((n_loc ? n_loc : 1) * (u64)GVS_FJ(ctx->k), 12));
+  if (fw < (1ull << 10)) fw = 1ull << 10;
+  if (fw > (1ull << 27)) fw = 1ull << 27;
+  ctx->filt_words = fw;  // number of blocks
+  CKR(gvs_reserve(ctx, ctx->filt, fw * 16));
   u64* keys = ctx->tab_keys.as<u64>();
   u32* rows = ctx->tab_rows.as<u32>();
   LAUNCH(k_fill_u64, grid_for(ctx, slots, 256), 256, 0, keys, slots, GVS_EMPTY_KEY);
   LAUNCH(k_fill_u32, grid_for(ctx, slots, 256), 256, 0, rows, slots, 0u);
-  LAUNCH(k_fill_u32, grid_for(ctx, fw, 256), 256, 0, ctx->filt.as<u32>(), fw, 0u);
+  LAUNCH(k_fill_u32, grid_for(ctx, fw * 4, 256), 256, 0, ctx->filt.as<u32>(), fw * 4, 0u);
   if (n_loc) LAUNCH(k_tab_insert_loc, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
   if (d_db_kmer) {
     if (n_db) LAUNCH(k_tab_mark_db, grid_for(ctx, n_db, 256), 256, 0, d_db_kmer, n_db, keys, rows, slots);
   } else if (n_loc) {
     LAUNCH(k_tab_mark_db, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
   }
-  LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u32>(), fw);
+  LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u32>(), fw, ctx->k);
   return 0;
 }
 
