@@ -6,21 +6,24 @@
 // stalls its neighbours):
 //   * each warp owns a contiguous span of 512-window tiles and walks it with a private cursor into
 //     read_off (no per-tile binary search)
-//   * per tile: ONE coalesced 128-bit load per lane (+2 lanes of halo) of ASCII bases, packed to
-//     2 bits per base twice in shared memory: forward (big-endian) and reverse-complement tile, so
-//     that both strands of a window are constant-shift funnel extractions (no rolling state, no
-//     warm-up of k-1 bases per strip)
-//   * canonical = min(fwd, rc); 32-bit hash -> one 4-byte word of the L2-resident blocked Bloom
-//     filter per window, 16 independent loads in flight per lane
-//   * filter-positive windows (~1 %) are compacted into a per-warp queue in position order and
-//     looked up in the exact table (32-byte bucket in HBM) 32 at a time
-//   * hits are appended to the global hit list with one atomicAdd per tile; (count, offset) per
-//     tile lets a later pass restore global position order
+//   * per tile ONE coalesced 16-byte cp.async per lane brings the ASCII bases into shared memory two
+//     tiles ahead of the compute (the copy of tile T+2 is in flight while tile T is processed); the
+//     bases are packed to 2 bits twice -- forward (big-endian) and reverse complement -- into a
+//     two-tile ring, so the 32-base halo of a tile is simply the head of the next ring slot and both
+//     strands of every window are constant-shift funnel extractions (no rolling state)
+//   * canonical = min(fwd, rc); J = 4 consecutive windows share the (K-3)-mer that starts at the last
+//     of them, and every SUNK was inserted into the filter block of each of its 4 sub-mers, so ONE
+//     16-byte block of the L2-resident blocked Bloom filter serves 4 windows (0.25 scattered sectors
+//     per base); 4 bits per key, one per 32-bit word of the block
+//   * filter-positive windows (~1 %) are compacted into a per-warp queue in position order and looked
+//     up in the exact table (32-byte bucket in HBM) 32 at a time
+//   * hits are appended to the global hit list with one atomicAdd per tile; (count, offset) per tile
+//     lets a later pass restore global position order
 #include "table.cuh"
 
-#define PW_WARPS 8                       // warps per block
-#define PW_TILE 512                      // window starts per warp tile
-#define PW_NW 34                         // packed words per tile (512 + 32 bases)
+#define PW_WARPS 8     // warps per block
+#define PW_TILE 512    // window starts per warp tile
+#define PW_RING 64     // packed words in the ring: two tile slots of 32 words (16 bases each)
 #define PW_MAXB 32
 
 #define FLAG_KEYERROR 1u
@@ -46,36 +49,46 @@ __device__ __forceinline__ u32 p_rc16(u32 w) {
   u32 x = __brev(~w);
   return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
 }
-__device__ __forceinline__ u32 p_load16(const u8* __restrict__ seq, u64 g, u64 total) {
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (g + 16 <= total) {
-    v = __ldg((const uint4*)(seq + g));
-  } else if (g < total) {
-    u32 w[4] = {0, 0, 0, 0};
-    for (int i = 0; i < 16 && g + i < total; i++) w[i >> 2] |= (u32)seq[g + i] << (8 * (i & 3));
-    v = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  return p_pack16_be(v);
-}
-// 2K bits starting at base offset `off` (0..15) of the big-endian string a:b:c
-template <int K>
+// 2*LEN bits starting at base offset `off` (0..15) of the big-endian string a:b:c
+template <int LEN>
 __device__ __forceinline__ u64 p_extract(u32 a, u32 b, u32 c, int off) {
   int s = 2 * off;
   u32 hi = __funnelshift_l(b, a, s);
   u32 lo = __funnelshift_l(c, b, s);
   u64 v = ((u64)hi << 32) | lo;
-  return v >> (64 - 2 * K);
+  return v >> (64 - 2 * LEN);
 }
-// canonical k-mer of window p (0..511) from the shared tiles, optionally with the last base forced
-// to A (the bogus window of a (k-1)-long read, Q6)
+
+struct WarpSmem {
+  u32 fw[PW_RING];   // forward packed words, ring index = (slot base + word) & 63
+  u32 rc[PW_RING];   // rc[i] = reverse complement of fw[i] (same index)
+  uint4 raw[32];     // cp.async landing zone: 16 ASCII bases per lane
+  u32 bound[20];
+  u32 shrt[20];
+  u32 bpos[PW_MAXB];
+  u32 bidx[PW_MAXB];
+  u32 q_row[PW_TILE];
+  u16 q_p[PW_TILE];
+};
+
+// forward / reverse-complement k-mer of window p (0..511) of the tile whose ring base is `rb`
 template <int K>
-__device__ __forceinline__ u64 p_canon_at(const u32* fw, const u32* rc, u32 p, bool force_last_a) {
-  u32 wi = p >> 4;
-  u64 f = p_extract<K>(fw[wi], fw[wi + 1], fw[wi + 2], p & 15);
-  u32 q = PW_NW * 16 - p - K;
-  u32 qi = q >> 4;
-  u64 r = p_extract<K>(rc[qi], rc[qi + 1], rc[qi + 2], q & 15);
-  if (force_last_a) {
+__device__ __forceinline__ u64 p_fwd_at(const WarpSmem& sm, u32 rb, u32 p) {
+  u32 wi = rb + (p >> 4);
+  return p_extract<K>(sm.fw[wi & 63], sm.fw[(wi + 1) & 63], sm.fw[(wi + 2) & 63], p & 15);
+}
+template <int K>
+__device__ __forceinline__ u64 p_rc_at(const WarpSmem& sm, u32 rb, u32 p) {
+  // the window ends at base e = p + K (exclusive); its reverse complement starts inside the rc of
+  // word c-1 (c = ceil(e/16)) at base offset 16c - e and continues through DEscending word indices
+  u32 e = p + K, c = (e + 15) >> 4;
+  u32 wi = rb + c - 1;
+  return p_extract<K>(sm.rc[wi & 63], sm.rc[(wi - 1) & 63], sm.rc[(wi - 2) & 63], 16 * c - e);
+}
+template <int K>
+__device__ __forceinline__ u64 p_canon_at(const WarpSmem& sm, u32 rb, u32 p, bool force_last_a) {
+  u64 f = p_fwd_at<K>(sm, rb, p), r = p_rc_at<K>(sm, rb, p);
+  if (force_last_a) {  // the bogus window of a (k-1)-long read: last base read as A (Q6)
     f &= ~3ull;
     r |= 3ull << (2 * (K - 1));
   }
@@ -102,16 +115,27 @@ struct Probe2Params {
   u64* tile_off;
 };
 
-struct WarpSmem {
-  u32 fw[PW_NW + 4];
-  u32 rc[PW_NW + 4];
-  u32 bound[20];
-  u32 shrt[20];
-  u32 bpos[PW_MAXB];
-  u32 bidx[PW_MAXB];
-  u32 q_row[PW_TILE];
-  u16 q_p[PW_TILE];
-};
+// asynchronous copy of the 32 x 16 ASCII bases of `tile` into sm.raw (zero beyond the end)
+__device__ __forceinline__ void p_stage_issue(WarpSmem& sm, const u8* __restrict__ seq, u64 tile, u64 total, int lane) {
+  u64 g = tile * PW_TILE + 16ull * lane;
+  if (g + 16 <= total) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.raw[lane]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(seq + g) : "memory");
+  } else {
+    u32 w[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16 && g + i < total; i++) w[i >> 2] |= (u32)seq[g + i] << (8 * (i & 3));
+    sm.raw[lane] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+// pack the landed bases into ring slot `rb` (forward + reverse complement)
+__device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, int lane) {
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  uint4 v = sm.raw[lane];
+  u32 w = p_pack16_be(v);
+  sm.fw[(rb + lane) & 63] = w;
+  sm.rc[(rb + lane) & 63] = p_rc16(w);
+}
 
 template <int K>
 __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params P) {
@@ -119,17 +143,18 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
   const int lane = threadIdx.x & 31;
   WarpSmem& sm = sm_all[threadIdx.x >> 5];
   const u64 warp = (u64)blockIdx.x * PW_WARPS + (threadIdx.x >> 5);
-  u64 tile = warp * P.tiles_per_warp;
-  u64 tile_end = tile + P.tiles_per_warp;
+  const u64 tile0 = warp * P.tiles_per_warp;
+  u64 tile_end = tile0 + P.tiles_per_warp;
   if (tile_end > P.n_tiles) tile_end = P.n_tiles;
-  if (tile >= tile_end) return;
+  if (tile0 >= tile_end) return;
   constexpr int CMAX = (K + 15 + 15) / 16;
-  constexpr u32 LT_MASK_ALL = 0xFFFFFFFFu;
+  constexpr u32 ALL = 0xFFFFFFFFu;
 
-  // cursor: first boundary index j >= 1 with read_off[j] > tile start
+  // cursor: first boundary index j >= 1 with read_off[j] > tile start; prev_off = start of the read
+  // that contains the tile start
   u64 cur;
   {
-    u64 ts0 = tile * PW_TILE;
+    u64 ts0 = tile0 * PW_TILE;
     u64 lo = 1, hi = P.n_reads;
     while (lo < hi) {
       u64 mid = (lo + hi) >> 1;
@@ -138,27 +163,28 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
     cur = lo;
   }
   u64 next_off = __ldg(P.read_off + cur);
-  if (lane < 4) { sm.rc[PW_NW + lane] = 0; sm.fw[PW_NW + lane] = 0; }
+  u64 prev_off = __ldg(P.read_off + cur - 1);
 
-  for (; tile < tile_end; tile++) {
+  // prologue: tiles T0 and T0+1 into ring slots 0 and 1
+  p_stage_issue(sm, P.seq, tile0, P.total, lane);
+  p_stage_finish(sm, 0, lane);
+  p_stage_issue(sm, P.seq, tile0 + 1, P.total, lane);
+  p_stage_finish(sm, 32, lane);
+  __syncwarp();
+
+  for (u64 tile = tile0; tile < tile_end; tile++) {
     const u64 ts = tile * PW_TILE;
-    // ---- stage: ASCII -> forward and reverse-complement packed tiles ----
-    {
-      u32 w = p_load16(P.seq, ts + 16ull * lane, P.total);
-      sm.fw[lane] = w;
-      sm.rc[PW_NW - 1 - lane] = p_rc16(w);
-      if (lane < 2) {
-        u32 w2 = p_load16(P.seq, ts + 512 + 16ull * lane, P.total);
-        sm.fw[32 + lane] = w2;
-        sm.rc[PW_NW - 1 - 32 - lane] = p_rc16(w2);
-      }
-    }
+    const u32 rb = (u32)((tile - tile0) & 1) * 32;  // ring base of this tile
+    // prefetch tile T+2 (lands in sm.raw while this tile is processed)
+    p_stage_issue(sm, P.seq, tile + 2, P.total, lane);
+
     // ---- read boundaries in (ts, ts + 512 + K - 2] ----
     const u64 limit = ts + PW_TILE + (K > 1 ? K - 1 : 1);
     const u64 cur0 = cur;
     u32 nb = 0;
-    bool has_bound = next_off < limit;
-    bool start_short = false;
+    const bool has_bound = next_off < limit;
+    // the read that starts exactly at ts (its boundary belongs to the previous tile) may be (K-1) long
+    const bool start_short = K >= 2 && prev_off == ts && next_off - prev_off == (u64)(K - 1);
     if (has_bound) {
       if (lane < 20) { sm.bound[lane] = 0; sm.shrt[lane] = 0; }
       __syncwarp();
@@ -167,7 +193,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         u64 o = (j <= P.n_reads) ? __ldg(P.read_off + j) : ~0ull;
         bool inr = o < limit;
         bool intile = inr && (o - ts) < PW_TILE;
-        u32 bal_tile = __ballot_sync(LT_MASK_ALL, intile);
+        u32 bal_tile = __ballot_sync(ALL, intile);
         if (inr) {
           u32 rel = (u32)(o - ts);
           atomicOr(&sm.bound[rel >> 5], 1u << (rel & 31));
@@ -179,26 +205,25 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           }
         }
         nb += __popc(bal_tile);
-        u32 bal_adv = __ballot_sync(LT_MASK_ALL, o <= ts + PW_TILE);
+        u32 bal_adv = __ballot_sync(ALL, o <= ts + PW_TILE);
         cur += __popc(bal_adv);
-        u32 bal_in = __ballot_sync(LT_MASK_ALL, inr);
-        if (bal_in != LT_MASK_ALL) break;
+        u32 bal_in = __ballot_sync(ALL, inr);
+        if (bal_in != ALL) break;
         j += 32;
       }
       next_off = (cur <= P.n_reads) ? __ldg(P.read_off + cur) : ~0ull;
+      prev_off = __ldg(P.read_off + cur - 1);
+      __syncwarp();
     }
-    if (K >= 2 && lane == 0) {  // the read that starts exactly at ts (its boundary belongs to the previous tile)
-      u64 o = __ldg(P.read_off + cur0 - 1);
-      if (o == ts && __ldg(P.read_off + cur0) - o == (u64)(K - 1)) start_short = true;
-    }
-    __syncwarp();
 
     // ---- per lane: 16 windows, both strands by constant-shift extraction ----
     u32 cm = 0;  // candidate (filter-positive) windows of this lane
     {
-      const u32 f0 = sm.fw[lane], f1 = sm.fw[lane + 1], f2 = sm.fw[lane + 2];
-      const int rbase = PW_NW - lane - CMAX;
-      const u32 r0 = sm.rc[rbase], r1 = sm.rc[rbase + 1], r2 = sm.rc[rbase + 2], r3 = sm.rc[rbase + 3];
+      const u32 wb = rb + lane;
+      const u32 f0 = sm.fw[wb & 63], f1 = sm.fw[(wb + 1) & 63], f2 = sm.fw[(wb + 2) & 63];
+      // rc words in DEscending ring order: r_j = rc of forward word (lane + CMAX - 1 - j)
+      const u32 r0 = sm.rc[(wb + CMAX - 1) & 63], r1 = sm.rc[(wb + CMAX - 2) & 63], r2 = sm.rc[(wb + CMAX - 3) & 63],
+                r3 = sm.rc[(wb + CMAX - 4) & 63];
       // validity: no boundary inside (p, p+K-1], p < total
       u32 inval = 0, S16 = 0;
       if (has_bound) {
@@ -231,7 +256,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
       }
       // Filter blocks: J consecutive windows share the (K-J+1)-mer that starts at the last of them, and
       // every SUNK was inserted into the block of each of its J sub-mers (table.cu), so ONE 16-byte
-      // block load serves J windows: 0.25 scattered sectors per base instead of 1.
+      // block load serves J windows.
       constexpr int J = GVS_FJ(K);
       constexpr int L = K - J + 1;
       constexpr int NG = 16 / J;
@@ -270,9 +295,9 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         for (u32 s = S16; s; s &= s - 1) {
           int i = __ffs(s) - 1;
           u32 p = 16u * lane + i;
-          u64 canon = p_canon_at<K>(sm.fw, sm.rc, p, true);
+          u64 canon = p_canon_at<K>(sm, rb, p, true);
           // its own first sub-mer (real bases only) selects the block
-          u64 sub = (p_extract<K>(sm.fw[p >> 4], sm.fw[(p >> 4) + 1], sm.fw[(p >> 4) + 2], p & 15) & ~3ull) >> (2 * (K - L));
+          u64 sub = (p_fwd_at<K>(sm, rb, p) & ~3ull) >> (2 * (K - L));
           u64 subr = gvs_revcomp(sub, L);
           uint4 b4 = __ldg((const uint4*)P.filt + (gvs_bhash(sub < subr ? sub : subr) & P.filt_mask));
           u32 h = gvs_fhash(canon);
@@ -284,16 +309,16 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
       cm |= (S16 << 16);  // remember which candidates are forced-A windows
     }
     // ---- queue candidates in position order ----
-    u32 ncand_lane = __popc(cm & 0xFFFFu);
-    u32 incl = ncand_lane;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      u32 o = __shfl_up_sync(LT_MASK_ALL, incl, d);
-      if (lane >= d) incl += o;
-    }
-    const u32 ncand = __shfl_sync(LT_MASK_ALL, incl, 31);
     u32 nh = 0;
-    if (ncand) {
+    if (__any_sync(ALL, (cm & 0xFFFFu) != 0)) {
+      u32 ncand_lane = __popc(cm & 0xFFFFu);
+      u32 incl = ncand_lane;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(ALL, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const u32 ncand = __shfl_sync(ALL, incl, 31);
       u32 qo = incl - ncand_lane;
       for (u32 s = cm & 0xFFFFu; s; s &= s - 1) {
         int i = __ffs(s) - 1;
@@ -307,7 +332,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         if (base + lane < ncand) {
           u32 e = sm.q_p[base + lane];
           pp = e & 0x7FFFu;
-          u64 canon = p_canon_at<K>(sm.fw, sm.rc, pp, (e >> 15) != 0);
+          u64 canon = p_canon_at<K>(sm, rb, pp, (e >> 15) != 0);
           row = tab_lookup(P.tab, canon, gvs_mix(canon));
           if (row == GVS_ROW_MISSING) {
             atomicOr(P.flags, FLAG_KEYERROR);
@@ -316,7 +341,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
             row = GVS_NOHIT;
           }
         }
-        u32 bal = __ballot_sync(LT_MASK_ALL, row != GVS_NOHIT);
+        u32 bal = __ballot_sync(ALL, row != GVS_NOHIT);
         __syncwarp();
         if (row != GVS_NOHIT) {
           u32 d = nh + __popc(bal & ((1u << lane) - 1));
@@ -334,11 +359,11 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         obase = atomicAdd(P.cursor, (unsigned long long)nh);
         if (obase + nh > P.hit_cap) atomicOr(P.flags, FLAG_OVERFLOW);
       }
-      P.tile_cnt[tile] = nh;
-      P.tile_off[tile] = obase;
+      __stcs(P.tile_cnt + tile, nh);
+      __stcs((unsigned long long*)P.tile_off + tile, (unsigned long long)obase);
     }
     if (nh) {
-      obase = __shfl_sync(LT_MASK_ALL, obase, 0);
+      obase = __shfl_sync(ALL, obase, 0);
       for (u32 idx = lane; idx < nh; idx += 32) {
         u64 o = obase + idx;
         if (o >= P.hit_cap) break;
@@ -372,6 +397,9 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         P.hit_row[o] = sm.q_row[idx];
       }
     }
+    // ---- tile T is done: its ring slot receives tile T+2 ----
+    __syncwarp();
+    p_stage_finish(sm, rb, lane);
     __syncwarp();
   }
 }
