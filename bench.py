@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="s150", choices=["tiny", "s150", "h3100"])
+    ap.add_argument("--workload", default="h3100", choices=["tiny", "s150", "h3100"])
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--asm-mbp", type=float, default=None, help="override haploid assembly size (Mbp)")
     ap.add_argument("--coverage", type=float, default=None, help="override read coverage per GPU shard")
@@ -298,10 +298,15 @@ def main_b200(args):
 # --------------------------------------------------------------------------------------------
 # CPU reference (oracle/_ref executables + oracle port of the Python stages) on a bounded sample
 # --------------------------------------------------------------------------------------------
-def _write_db_files(eng, wl, workdir):
-    """jellyfish.db / kmer.loc / .fai text files in the reference's formats from the GPU-built db"""
+def _write_db_files(eng, wl, workdir, contig_sel=None):
+    """jellyfish.db / kmer.loc / .fai text files in the reference's formats from the GPU-built db
+    (contig_sel: only the .loc rows of these contigs -- the sample of a database too large for the
+    reference's 278 B/SUNK hash tables and ~2 us/SUNK text load)"""
     import pandas as pd
     db = eng.db_export()
+    if contig_sel is not None:
+        m = np.isin(db["contig"], np.asarray(sorted(contig_sel), dtype=np.uint32))
+        db = {c: v[m] for c, v in db.items()}
     k = eng.k
     km = db["kmer"]
     shifts = (2 * np.arange(k - 1, -1, -1)).astype(np.uint64)
@@ -336,7 +341,34 @@ def cpu_reference_sample(args, wl, eng, per_proc_mbp=12.0):
         return dict(error="oracle/_ref executables missing", cores=cores)
     workdir = tempfile.mkdtemp(prefix="gvs_cpu_")
     try:
-        dbp, locp, fais = _write_db_files(eng, wl, workdir)
+        n_sunks, _ = eng.db_size()
+        contig_sel, sample_note = None, ""
+        if n_sunks > 8_000_000:
+            # whole-genome database: the reference would need ~33 GB and ~4 min of text parsing per process.
+            # Sample = a contiguous run of contigs of ~150 Mbp per haplotype: their .loc rows + reads drawn
+            # from them by the same generator (same length / error model).
+            import copy
+            from gavisunk_b200 import workload as W
+            nc = len(wl.contig_names) // 2
+            lens = wl.contig_len[:nc].astype(np.int64)
+            best = (0, 1)
+            for lo in range(nc):
+                for hi in range(lo + 1, nc + 1):
+                    if abs(int(lens[lo:hi].sum()) - 150_000_000) < abs(int(lens[best[0]:best[1]].sum()) - 150_000_000):
+                        best = (lo, hi)
+            lo, hi = best
+            sub_len = int(lens[lo:hi].sum())
+            swl = copy.copy(wl)
+            swl.meta = dict(wl.meta)
+            cov = per_proc_mbp * 1e6 * cores * 1.15 / sub_len
+            W.add_reads(eng, swl, coverage=cov, n50=wl.meta.get("n50", 50000.0), sigma=wl.meta.get("sigma", 0.8), len_min=1000,
+                        len_max=1000000, seed=777, nchunks=1, contig_range=(lo, hi))
+            contig_sel = set(range(lo, hi)) | set(range(nc + lo, nc + hi))
+            sample_note = (f"database restricted to contigs {wl.contig_names[lo]}..{wl.contig_names[hi - 1]} of both haplotypes "
+                           f"({sub_len / 1e6:.0f} Mbp x2; the full {n_sunks / 1e6:.0f} M-SUNK table needs ~33 GB and minutes of text "
+                           "parsing per reference process), reads drawn from them by the same generator; ")
+            wl = swl
+        dbp, locp, fais = _write_db_files(eng, wl, workdir, contig_sel)
         off = wl.read_off.cpu().numpy()
         nph = wl.n_reads // 2
         per_hap_procs = max(1, cores // 2)
@@ -395,7 +427,7 @@ def cpu_reference_sample(args, wl, eng, per_proc_mbp=12.0):
         t_py = (time.perf_counter() - t0) * len(jobs) / max(n_py, 1)
         wall = wall_elf + t_py
         return dict(value=sample_bases / wall / 1e9, unit=UNIT, cores=cores, kind="reference",
-                    sample=(f"{sample_reads} reads / {sample_bases / 1e6:.0f} Mbp of the same workload in {len(jobs)} chunk files; "
+                    sample=(sample_note + f"{sample_reads} reads / {sample_bases / 1e6:.0f} Mbp of the same workload in {len(jobs)} chunk files; "
                             f"reference ELFs kmerpos_annot3+diag_filter_v3+diag_filter_step2 one process per chunk, {cores} at once "
                             f"(wall {wall_elf:.1f} s incl. {t_load:.1f} s table load per process), then the single-process CPU port of "
                             f"badsunks/process-by-contig/get_gaps (the reference's Python needs graph_tool/pyranges; timed on {n_py} of the "

@@ -55,7 +55,9 @@ struct gvs_ctx {
   DevBuf tab_keys, tab_rows;                                     // open-addressed probe table
   u64 tab_slots = 0;                                             // power of two, buckets of 4
   DevBuf filt;                                                   // 32-bit-word blocked Bloom filter
-  u64 filt_words = 0;                                            // power of two
+  u64 filt_words = 0;                                            // number of 16-byte blocks, power of two
+  DevBuf filt1;                                                  // presence filter of the sub-mers (large databases)
+  u64 filt1_words = 0;                                           // 0 = single-level filter
   DevBuf contig_hap, contig_hash, contig_len;
 
   // ---- reads ----
@@ -238,6 +240,16 @@ __host__ __device__ __forceinline__ u32 gvs_bhash(u64 sub) {
   h *= 0x85EBCA6Bu;
   h ^= h >> 13;
   return h;
+}
+// Presence filter in front of the blocked filter when the latter outgrows L2 (whole-genome databases):
+// one 32-bit word per sub-mer hash, 2 bits; answers "is this (K-J+1)-mer a sub-mer of any SUNK" from L2
+// so that only ~20 % of the window groups go on to their 16-byte block in HBM.
+__host__ __device__ __forceinline__ u32 gvs_p1_word(u32 hb, u32 mask) { return ((hb * 0x9E3779B1u) >> 7) & mask; }
+__host__ __device__ __forceinline__ u32 gvs_p1_bits(u32 hb) {
+  u32 g = hb * 0x85EBCA6Bu;
+  g ^= g >> 15;
+  g *= 0xC2B2AE35u;
+  return (1u << (g >> 27)) | (1u << ((g >> 22) & 31));
 }
 // reverse complement of an L-mer in 2-bit big-endian packing
 __host__ __device__ __forceinline__ u64 gvs_revcomp(u64 x, int L) {

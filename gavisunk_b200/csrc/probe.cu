@@ -104,6 +104,8 @@ struct Probe2Params {
   u64 tiles_per_warp;
   const u32* __restrict__ filt;
   u32 filt_mask;
+  const u32* __restrict__ filt1;  // presence filter (TWO-level variant)
+  u32 filt1_mask;
   TabView tab;
   u32* hit_read;
   u32* hit_w;
@@ -137,7 +139,7 @@ __device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, int lane) {
   sm.rc[(rb + lane) & 63] = p_rc16(w);
 }
 
-template <int K>
+template <int K, bool TWO>
 __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params P) {
   __shared__ WarpSmem sm_all[PW_WARPS];
   const int lane = threadIdx.x & 31;
@@ -273,6 +275,10 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         u32 hb = gvs_bhash(sf < sr ? sf : sr);
         const u32 gm = (1u << J) - 1;
         bool any_valid = ((inval >> (J * g)) & gm) != gm;
+        if (TWO && any_valid) {  // whole-genome tables: L2-resident presence test before the HBM block
+          u32 m1 = gvs_p1_bits(hb);
+          any_valid = (__ldg(P.filt1 + gvs_p1_word(hb, P.filt1_mask)) & m1) == m1;
+        }
         blk[g] = any_valid ? __ldg((const uint4*)P.filt + (hb & P.filt_mask)) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
@@ -406,11 +412,11 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
 
 typedef void (*probe_fn)(const Probe2Params);
 template <int K>
-static probe_fn probe_entry() { return k_probe2<K>; }
+static probe_fn probe_entry(bool two) { return two ? k_probe2<K, true> : k_probe2<K, false>; }
 
-static probe_fn probe_table(int k) {
+static probe_fn probe_table(int k, bool two) {
   switch (k) {
-#define PK(n) case n: return probe_entry<n>();
+#define PK(n) case n: return probe_entry<n>(two);
     PK(1) PK(2) PK(3) PK(4) PK(5) PK(6) PK(7) PK(8) PK(9) PK(10) PK(11) PK(12) PK(13) PK(14) PK(15) PK(16)
     PK(17) PK(18) PK(19) PK(20) PK(21) PK(22) PK(23) PK(24) PK(25) PK(26) PK(27) PK(28) PK(29) PK(30) PK(31)
 #undef PK
@@ -427,7 +433,7 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_tiles_out) {
   CKR(gvs_reserve(ctx, ctx->tile_cnt, n_tiles * 4));
   CKR(gvs_reserve(ctx, ctx->tile_off, n_tiles * 8));
   CKR(gvs_reserve(ctx, ctx->tile_dst, n_tiles * 8));
-  probe_fn fn = probe_table(ctx->k);
+  probe_fn fn = probe_table(ctx->k, ctx->filt1_words != 0);
   if (!fn) return gvs_fail(ctx, GVS_E_ARG, "no probe kernel for k=%d", ctx->k);
   u64* counters = ctx->counters.as<u64>();
   Probe2Params P;
@@ -443,6 +449,8 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_tiles_out) {
   blocks = cdiv(cdiv(n_tiles, P.tiles_per_warp), PW_WARPS);
   P.filt = ctx->filt.as<u32>();
   P.filt_mask = (u32)(ctx->filt_words - 1);
+  P.filt1 = ctx->filt1_words ? ctx->filt1.as<u32>() : nullptr;
+  P.filt1_mask = (u32)(ctx->filt1_words ? ctx->filt1_words - 1 : 0);
   P.tab.keys = ctx->tab_keys.as<u64>();
   P.tab.rows = ctx->tab_rows.as<u32>();
   P.tab.slots = ctx->tab_slots;

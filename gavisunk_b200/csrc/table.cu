@@ -27,7 +27,8 @@ __global__ void k_tab_mark_db(const u64* __restrict__ kmer, u64 n, u64* keys, u3
     atomicOr(&rows[s], 0x80000000u);
   }
 }
-__global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slots, u32* filt, u64 filt_blocks, int k) {
+__global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slots, u32* filt, u64 filt_blocks, int k,
+                               u32* filt1, u32 filt1_mask) {
   const int J = GVS_FJ(k), L = k - J + 1;
   const u64 lmask = (L >= 32) ? ~0ull : ((1ull << (2 * L)) - 1);
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
@@ -45,7 +46,9 @@ __global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slot
     for (int j = 0; j < J; j++) {
       u64 sub = (key >> (2 * (J - 1 - j))) & lmask;
       u64 rc = gvs_revcomp(sub, L);
-      u64 blk = gvs_bhash(sub < rc ? sub : rc) & (filt_blocks - 1);
+      u32 hb = gvs_bhash(sub < rc ? sub : rc);
+      u64 blk = hb & (filt_blocks - 1);
+      if (filt1) atomicOr(&filt1[gvs_p1_word(hb, filt1_mask)], gvs_p1_bits(hb));
       atomicOr(&filt[4 * blk + 0], 1u << (h & 31));
       atomicOr(&filt[4 * blk + 1], 1u << ((h >> 5) & 31));
       atomicOr(&filt[4 * blk + 2], 1u << ((h >> 10) & 31));
@@ -110,6 +113,12 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
   if (fw > (1ull << 27)) fw = 1ull << 27;
   ctx->filt_words = fw;  // number of blocks
   CKR(gvs_reserve(ctx, ctx->filt, fw * 16));
+  // blocked filter beyond L2 reach (> 48 MiB): put a 64 MiB presence filter of the sub-mers in front
+  ctx->filt1_words = (fw * 16 > (48ull << 20)) ? (1ull << 24) : 0;
+  if (ctx->filt1_words) {
+    CKR(gvs_reserve(ctx, ctx->filt1, ctx->filt1_words * 4));
+    LAUNCH(k_fill_u32, grid_for(ctx, ctx->filt1_words, 256), 256, 0, ctx->filt1.as<u32>(), ctx->filt1_words, 0u);
+  }
   u64* keys = ctx->tab_keys.as<u64>();
   u32* rows = ctx->tab_rows.as<u32>();
   LAUNCH(k_fill_u64, grid_for(ctx, slots, 256), 256, 0, keys, slots, GVS_EMPTY_KEY);
@@ -121,7 +130,8 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
   } else if (n_loc) {
     LAUNCH(k_tab_mark_db, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
   }
-  LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u32>(), fw, ctx->k);
+  LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u32>(), fw, ctx->k,
+         ctx->filt1_words ? ctx->filt1.as<u32>() : (u32*)nullptr, (u32)(ctx->filt1_words ? ctx->filt1_words - 1 : 0));
   return 0;
 }
 

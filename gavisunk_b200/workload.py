@@ -59,11 +59,13 @@ def make_assembly(eng: Engine, contig_len_per_hap, snp_rate=1e-3, dup_frac=0.01,
 
 
 def add_reads(eng: Engine, wl: Workload, coverage: float, n50: float = 50000.0, sigma: float = 0.8, len_min=1000,
-              len_max=1000000, seed=2001, nchunks=10, device=None) -> Workload:
-    """coverage = total read bases / haploid assembly size, split evenly across the two haps."""
+              len_max=1000000, seed=2001, nchunks=10, device=None, contig_range=None) -> Workload:
+    """coverage = total read bases / haploid size of the sampled contigs, split evenly across the two
+    haps.  contig_range=(lo, hi): draw reads only from contigs lo..hi-1 of each haplotype."""
     device = device or wl.asm.device
     nc = len(wl.contig_names) // 2
-    hap_len = int(wl.contig_len[:nc].sum())
+    c_lo, c_hi = contig_range if contig_range is not None else (0, nc)
+    hap_len = int(wl.contig_len[c_lo:c_hi].sum())
     mu = math.log(n50) - sigma * sigma           # length-weighted median of a log-normal = exp(mu + sigma^2)
     mean_len = math.exp(mu + sigma * sigma / 2)
     per_hap_bases = coverage * hap_len / 2
@@ -72,7 +74,7 @@ def add_reads(eng: Engine, wl: Workload, coverage: float, n50: float = 50000.0, 
     for hap in range(2):
         ro = torch.zeros(n_per_hap + 1, dtype=torch.int64, device=device)
         tot = C.c_uint64()
-        eng._ck(eng.lib.gvs_synth_reads_plan(eng.ctx, C.c_void_p(_dev_ptr(wl.contig_off)), hap * nc, (hap + 1) * nc,
+        eng._ck(eng.lib.gvs_synth_reads_plan(eng.ctx, C.c_void_p(_dev_ptr(wl.contig_off)), hap * nc + c_lo, hap * nc + c_hi,
                                              n_per_hap, mu, sigma, len_min, len_max, seed + hap,
                                              C.c_void_p(_dev_ptr(ro)), C.byref(tot)))
         offs.append(ro)
