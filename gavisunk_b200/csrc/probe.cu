@@ -117,12 +117,39 @@ struct Probe2Params {
   u64* tile_off;
 };
 
+// L2 residency: the reads stream through once (evict_first), the filter that every window group touches
+// must survive that stream (evict_last).  Without the hints the 4-12 GB read stream keeps evicting the
+// 32-64 MiB filter and every filter access becomes a 64-byte HBM fetch (profiles/k_probe2_h3100_r1k.txt).
+__device__ __forceinline__ u64 p_policy_stream() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ u64 p_policy_keep() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 p_ldg_v4(const uint4* ptr, u64 pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ u32 p_ldg_u32(const u32* ptr, u64 pol) {
+  u32 v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+  return v;
+}
+
 // asynchronous copy of the 32 x 16 ASCII bases of `tile` into sm.raw (zero beyond the end)
 __device__ __forceinline__ void p_stage_issue(WarpSmem& sm, const u8* __restrict__ seq, u64 tile, u64 total, int lane) {
   u64 g = tile * PW_TILE + 16ull * lane;
   if (g + 16 <= total) {
     unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.raw[lane]);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(seq + g) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(seq + g), "l"(p_policy_stream())
+                 : "memory");
   } else {
     u32 w[4] = {0, 0, 0, 0};
     for (int i = 0; i < 16 && g + i < total; i++) w[i >> 2] |= (u32)seq[g + i] << (8 * (i & 3));
@@ -277,9 +304,11 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         bool any_valid = ((inval >> (J * g)) & gm) != gm;
         if (TWO && any_valid) {  // whole-genome tables: L2-resident presence test before the HBM block
           u32 m1 = gvs_p1_bits(hb);
-          any_valid = (__ldg(P.filt1 + gvs_p1_word(hb, P.filt1_mask)) & m1) == m1;
+          any_valid = (p_ldg_u32(P.filt1 + gvs_p1_word(hb, P.filt1_mask), p_policy_keep()) & m1) == m1;
         }
-        blk[g] = any_valid ? __ldg((const uint4*)P.filt + (hb & P.filt_mask)) : make_uint4(0, 0, 0, 0);
+        // single-level: the blocks are the L2-resident structure; two-level: 1 GiB of blocks, touched once
+        blk[g] = any_valid ? p_ldg_v4((const uint4*)P.filt + (hb & P.filt_mask), TWO ? p_policy_stream() : p_policy_keep())
+                           : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int i = 0; i < 16; i++) {
