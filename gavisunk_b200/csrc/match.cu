@@ -12,22 +12,19 @@
 //                  never reset between reads, Q4) and the position drift it causes (Q3)
 #include "table.cuh"
 
-int gvs_probe_launch(gvs_ctx* ctx, u64* n_tiles_out);  // probe.cu
+int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out);  // probe.cu
 
 #define FLAG_KEYERROR 1u
 #define FLAG_OVERFLOW 2u
 
-// tile hit runs -> global position order
-__global__ void __launch_bounds__(256) k_gather_hits(const u32* __restrict__ tile_cnt, const u64* __restrict__ tile_off,
-                                                     const u64* __restrict__ tile_dst, u64 n_tiles,
+// per-warp hit regions -> one dense array in global position order (warp order = position order)
+__global__ void __launch_bounds__(128) k_gather_hits(const u32* __restrict__ warp_cnt, const u64* __restrict__ warp_dst, u64 cap_w,
                                                      const u32* __restrict__ a0, const u32* __restrict__ a1,
                                                      const u32* __restrict__ a2, u32* b0, u32* b1, u32* b2) {
-  u64 tile = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tile >= n_tiles) return;
-  u32 c = tile_cnt[tile];
-  if (!c) return;
-  u64 s = tile_off[tile], d = tile_dst[tile];
-  for (u32 i = 0; i < c; i++) {
+  const u64 w = blockIdx.x;
+  const u32 c = warp_cnt[w];
+  const u64 s = w * cap_w, d = warp_dst[w];
+  for (u32 i = threadIdx.x; i < c; i += blockDim.x) {
     b0[d + i] = a0[s + i];
     b1[d + i] = a1[s + i];
     b2[d + i] = a2[s + i];
@@ -84,16 +81,27 @@ __global__ void __launch_bounds__(256) k_emit_rows(const u32* __restrict__ hread
 }
 
 
-static int match_once(gvs_ctx* ctx, u64* n_tiles, bool* overflow, u64* need) {
+static int match_once(gvs_ctx* ctx, u64* n_warps, u64* cap_w, bool* overflow, u64* total_hits, u64* max_per_warp) {
   u64* counters = ctx->counters.as<u64>();
   CK(cudaMemsetAsync(counters, 0, 4 * sizeof(u64), ctx->stream));
   {
     StageTimer tm(ctx, GVS_ST_PROBE);
-    CKR(gvs_probe_launch(ctx, n_tiles));
+    CKR(gvs_probe_launch(ctx, n_warps, cap_w));
   }
-  u64 h[2];
-  CKR(read_dev(ctx, counters, h, 2));
-  *need = h[0];
+  // totals of the per-warp counts (+ their exclusive scan = destination of every region)
+  const u32* wc = ctx->tile_cnt.as<u32>();
+  u64* wd = ctx->tile_dst.as<u64>();
+  {
+    auto f = [wc] __device__(u64 i) -> u64 { return (u64)wc[i]; };
+    auto g = [wd] __device__(u64 i, u64 ex, u64 v) { wd[i] = ex; };
+    CKR((device_scan<u64>(ctx, *n_warps, f, g, OpSum(), counters)));
+    auto g2 = [] __device__(u64 i, u64 ex, u64 v) {};
+    CKR((device_scan<u64>(ctx, *n_warps, f, g2, OpMax(), counters + 3)));
+  }
+  u64 h[4];
+  CKR(read_dev(ctx, counters, h, 4));
+  *total_hits = h[0];
+  *max_per_warp = h[3];
   u32 fl = (u32)h[1];
   if (fl & FLAG_KEYERROR)
     return gvs_fail(ctx, GVS_E_KEYERROR, "KeyError: a read matched a db k-mer that has no .loc row (kmerpos_annot3.nim:90)");
@@ -116,7 +124,7 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
     return 0;
   }
   if (((uintptr_t)ctx->seq & 15) != 0) return gvs_fail(ctx, GVS_E_ARG, "read buffer must be 16-byte aligned");
-  u64 n_tiles = 0;
+  u64 n_warps = 0, cap_w = 0;
   if (ctx->k >= 32) {  // Q2: k = 32 yields no hits in the reference (mask overflow in kmer.slide)
     ctx->match_ready = true;
     return 0;
@@ -129,14 +137,14 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
     CKR(gvs_reserve(ctx, ctx->hit_w, ctx->hit_cap * 4));
     CKR(gvs_reserve(ctx, ctx->hit_row, ctx->hit_cap * 4));
     bool overflow = false;
-    u64 need = 0;
-    CKR(match_once(ctx, &n_tiles, &overflow, &need));
+    u64 need = 0, max_w = 0;
+    CKR(match_once(ctx, &n_warps, &cap_w, &overflow, &need, &max_w));
     if (!overflow) {
       ctx->n_hits = need;
       break;
     }
     if (attempt >= 1) return gvs_fail(ctx, GVS_E_OVERFLOW, "hit buffer overflow after resize");
-    ctx->hit_cap = need + 4096;
+    ctx->hit_cap = (max_w + max_w / 4 + 64) * n_warps;  // every warp region must hold the densest span
   }
   u64 nh = ctx->n_hits;
   if (nh == 0) {
@@ -149,16 +157,8 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
   CKR(gvs_reserve(ctx, ctx->ohit_read, nh * 4));
   CKR(gvs_reserve(ctx, ctx->ohit_w, nh * 4));
   CKR(gvs_reserve(ctx, ctx->ohit_row, nh * 4));
-  {
-    const u32* tc = ctx->tile_cnt.as<u32>();
-    u64* td = ctx->tile_dst.as<u64>();
-    auto f = [tc] __device__(u64 i) -> u64 { return (u64)tc[i]; };
-    auto g = [td] __device__(u64 i, u64 ex, u64 v) { td[i] = ex; };
-    CKR((device_scan<u64>(ctx, n_tiles, f, g, OpSum(), (u64*)nullptr)));
-    LAUNCH(k_gather_hits, (unsigned)cdiv(n_tiles, 256), 256, 0, tc, ctx->tile_off.as<u64>(), td, n_tiles, ctx->hit_read.as<u32>(),
-           ctx->hit_w.as<u32>(), ctx->hit_row.as<u32>(), ctx->ohit_read.as<u32>(), ctx->ohit_w.as<u32>(),
-           ctx->ohit_row.as<u32>());
-  }
+  LAUNCH(k_gather_hits, (unsigned)n_warps, 128, 0, ctx->tile_cnt.as<u32>(), ctx->tile_dst.as<u64>(), cap_w, ctx->hit_read.as<u32>(),
+         ctx->hit_w.as<u32>(), ctx->hit_row.as<u32>(), ctx->ohit_read.as<u32>(), ctx->ohit_w.as<u32>(), ctx->ohit_row.as<u32>());
   // ---- suppression + position drift ----
   CKR(gvs_reserve(ctx, ctx->flags_a, nh));          // u8 flags
   CKR(gvs_reserve(ctx, ctx->flags_b, nh * 8));      // packed exclusive counts

@@ -111,10 +111,9 @@ struct Probe2Params {
   u32* hit_w;
   u32* hit_row;
   u64 hit_cap;
-  unsigned long long* cursor;
   u32* flags;
-  u32* tile_cnt;
-  u64* tile_off;
+  u32* warp_cnt;  // hits found by each warp (its hits sit at warp * cap_w in the hit arrays)
+  u64 cap_w;
 };
 
 // L2 residency: the reads stream through once (evict_first), the filter that every window group touches
@@ -201,6 +200,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
   p_stage_finish(sm, 32, lane);
   __syncwarp();
 
+  u32 wcount = 0;  // hits of this warp so far
   for (u64 tile = tile0; tile < tile_end; tile++) {
     const u64 ts = tile * PW_TILE;
     const u32 rb = (u32)((tile - tile0) & 1) * 32;  // ring base of this tile
@@ -387,21 +387,14 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         __syncwarp();
       }
     }
-    // ---- append the tile's hits ----
-    u64 obase = 0;
-    if (lane == 0) {
-      if (nh) {
-        obase = atomicAdd(P.cursor, (unsigned long long)nh);
-        if (obase + nh > P.hit_cap) atomicOr(P.flags, FLAG_OVERFLOW);
-      }
-      __stcs(P.tile_cnt + tile, nh);
-      __stcs((unsigned long long*)P.tile_off + tile, (unsigned long long)obase);
-    }
+    // ---- append the tile's hits to this warp's region (position order, no global atomics) ----
     if (nh) {
-      obase = __shfl_sync(ALL, obase, 0);
-      for (u32 idx = lane; idx < nh; idx += 32) {
+      const bool fits = (u64)wcount + nh <= P.cap_w;
+      if (!fits && lane == 0) atomicOr(P.flags, FLAG_OVERFLOW);
+      const u64 obase = warp * P.cap_w + wcount;
+      wcount += nh;
+      for (u32 idx = lane; fits && idx < nh; idx += 32) {
         u64 o = obase + idx;
-        if (o >= P.hit_cap) break;
         u32 prel = sm.q_p[idx];
         u64 p = ts + prel;
         u32 rd;
@@ -437,6 +430,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
     p_stage_finish(sm, rb, lane);
     __syncwarp();
   }
+  if (lane == 0) P.warp_cnt[warp] = wcount;
 }
 
 typedef void (*probe_fn)(const Probe2Params);
@@ -453,15 +447,11 @@ static probe_fn probe_table(int k, bool two) {
   return nullptr;
 }
 
-// launches the probe over ctx's reads; outputs in ctx->hit_*, tile_cnt, tile_off; counters[0] =
-// total hits, counters[1] = flags
-int gvs_probe_launch(gvs_ctx* ctx, u64* n_tiles_out) {
+// launches the probe over ctx's reads; warp w's hits land at w * cap_w in ctx->hit_*, its count in
+// ctx->tile_cnt[w] (zeroed here); counters[1] = flags
+int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   u64 total = ctx->total_bases;
   u64 n_tiles = cdiv(total, PW_TILE);
-  *n_tiles_out = n_tiles;
-  CKR(gvs_reserve(ctx, ctx->tile_cnt, n_tiles * 4));
-  CKR(gvs_reserve(ctx, ctx->tile_off, n_tiles * 8));
-  CKR(gvs_reserve(ctx, ctx->tile_dst, n_tiles * 8));
   probe_fn fn = probe_table(ctx->k, ctx->filt1_words != 0);
   if (!fn) return gvs_fail(ctx, GVS_E_ARG, "no probe kernel for k=%d", ctx->k);
   u64* counters = ctx->counters.as<u64>();
@@ -476,6 +466,13 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_tiles_out) {
   P.tiles_per_warp = cdiv(n_tiles, warps);
   if (P.tiles_per_warp < 4) P.tiles_per_warp = 4;
   blocks = cdiv(cdiv(n_tiles, P.tiles_per_warp), PW_WARPS);
+  warps = blocks * PW_WARPS;
+  *n_warps_out = warps;
+  CKR(gvs_reserve(ctx, ctx->tile_cnt, warps * 4));
+  CKR(gvs_reserve(ctx, ctx->tile_dst, warps * 8));
+  CK(cudaMemsetAsync(ctx->tile_cnt.p, 0, warps * 4, ctx->stream));
+  P.cap_w = ctx->hit_cap / warps;
+  *cap_w_out = P.cap_w;
   P.filt = ctx->filt.as<u32>();
   P.filt_mask = (u32)(ctx->filt_words - 1);
   P.filt1 = ctx->filt1_words ? ctx->filt1.as<u32>() : nullptr;
@@ -487,13 +484,47 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_tiles_out) {
   P.hit_w = ctx->hit_w.as<u32>();
   P.hit_row = ctx->hit_row.as<u32>();
   P.hit_cap = ctx->hit_cap;
-  P.cursor = (unsigned long long*)counters;
   P.flags = (u32*)(counters + 1);
-  P.tile_cnt = ctx->tile_cnt.as<u32>();
-  P.tile_off = ctx->tile_off.as<u64>();
-  fn<<<(unsigned)blocks, PW_WARPS * 32, 0, ctx->stream>>>(P);
+  P.warp_cnt = ctx->tile_cnt.as<u32>();
+  // L2 persistence: the structure every window group touches (the presence filter of a whole-genome
+  // database, else the blocked filter) is pinned in the persisting carve-out of L2; everything outside
+  // the window (reads, exact table, hit lists) is treated as streaming.
+  static int persist_max = -1, window_max = 0;
+  if (persist_max < 0) {
+    cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    if (persist_max < 0) persist_max = 0;
+  }
+  const void* hot = ctx->filt1_words ? ctx->filt1.p : ctx->filt.p;
+  size_t hot_bytes = ctx->filt1_words ? ctx->filt1_words * 4 : ctx->filt_words * 16;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(PW_WARPS * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  int n_attr = 0;
+  if (persist_max > 0 && window_max > 0) {
+    size_t carve = hot_bytes < (size_t)persist_max ? hot_bytes : (size_t)persist_max;
+    static size_t carve_set = 0;
+    if (carve_set != carve) {
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      carve_set = carve;
+    }
+    size_t win = hot_bytes < (size_t)window_max ? hot_bytes : (size_t)window_max;
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(hot);
+    attr[0].val.accessPolicyWindow.num_bytes = win;
+    attr[0].val.accessPolicyWindow.hitRatio = win <= carve ? 1.0f : (float)carve / (float)win;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    n_attr = 1;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fn, P);
   ctx->launches++;
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return gvs_fail(ctx, GVS_E_CUDA, "k_probe2 launch: %s", cudaGetErrorString(e));
   return 0;
 }
