@@ -17,8 +17,8 @@
 //     per base); 4 bits per key, one per 32-bit word of the block
 //   * filter-positive windows (~1 %) are compacted into a per-warp queue in position order and looked
 //     up in the exact table (32-byte bucket in HBM) 32 at a time
-//   * hits are appended to the global hit list with one atomicAdd per tile; (count, offset) per tile
-//     lets a later pass restore global position order
+//   * every warp appends its hits to its own region of the hit arrays (position order, no global
+//     atomics); a scan of the per-warp counts + one coalesced copy give the dense ordered list
 #include "table.cuh"
 
 #define PW_WARPS 8     // warps per block
@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
       constexpr int J = GVS_FJ(K);
       constexpr int L = K - J + 1;
       constexpr int NG = 16 / J;
-      uint4 blk[NG];
+      // Phase 1: block hashes of the NG groups; two-level: all presence-filter loads go out together
+      u32 hbv[NG];
+      u32 w1[NG];
 #pragma unroll
       for (int g = 0; g < NG; g++) {
         const int o = J * g + (J - 1);  // lane-relative base offset of the shared sub-mer
@@ -299,17 +301,20 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         const int j0 = CMAX - c;
         const int off = 16 * c - e;
         u64 sr = (j0 == 0) ? p_extract<L>(r0, r1, r2, off) : p_extract<L>(r1, r2, r3, off);
-        u32 hb = gvs_bhash(sf < sr ? sf : sr);
+        hbv[g] = gvs_bhash(sf < sr ? sf : sr);
         const u32 gm = (1u << J) - 1;
         bool any_valid = ((inval >> (J * g)) & gm) != gm;
-        if (TWO && any_valid) {  // whole-genome tables: L2-resident presence test before the HBM block
-          u32 m1 = gvs_p1_bits(hb);
-          any_valid = (p_ldg_u32(P.filt1 + gvs_p1_word(hb, P.filt1_mask), p_policy_keep()) & m1) == m1;
-        }
-        // single-level: the blocks are the L2-resident structure; two-level: 1 GiB of blocks, touched once
-        blk[g] = any_valid ? p_ldg_v4((const uint4*)P.filt + (hb & P.filt_mask), TWO ? p_policy_stream() : p_policy_keep())
-                           : make_uint4(0, 0, 0, 0);
+        // whole-genome tables: L2-resident presence test before the HBM block
+        w1[g] = (TWO && any_valid) ? p_ldg_u32(P.filt1 + gvs_p1_word(hbv[g], P.filt1_mask), p_policy_keep()) : (any_valid ? ~0u : 0u);
       }
+      uint4 blk[NG];
+      if (!TWO) {  // single-level: the blocks are the L2-resident structure, loads go out before the window math
+#pragma unroll
+        for (int g = 0; g < NG; g++)
+          blk[g] = w1[g] ? p_ldg_v4((const uint4*)P.filt + (hbv[g] & P.filt_mask), p_policy_keep()) : make_uint4(0, 0, 0, 0);
+      }
+      // Phase 2: the 16 window hashes (pure ALU, overlaps the loads in flight)
+      u32 hv[16];
 #pragma unroll
       for (int i = 0; i < 16; i++) {
         u64 f = p_extract<K>(f0, f1, f2, i);
@@ -318,9 +323,21 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         const int j0 = CMAX - c;
         const int off = 16 * c - e;
         u64 r = (j0 == 0) ? p_extract<K>(r0, r1, r2, off) : p_extract<K>(r1, r2, r3, off);
-        u64 canon = f < r ? f : r;
-        u32 h = gvs_fhash(canon);
+        hv[i] = gvs_fhash(f < r ? f : r);
+      }
+      if (TWO) {  // Phase 3: presence verdicts -> the (few) 16-byte blocks in HBM, touched once
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+          u32 m1 = gvs_p1_bits(hbv[g]);
+          blk[g] = ((w1[g] & m1) == m1) ? p_ldg_v4((const uint4*)P.filt + (hbv[g] & P.filt_mask), p_policy_stream())
+                                        : make_uint4(0, 0, 0, 0);
+        }
+      }
+      // Phase 4: 4 bits per window, one in each word of its group's block
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
         const uint4 b4 = blk[i / J];
+        const u32 h = hv[i];
         u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
                 __funnelshift_r(b4.w, 0u, h >> 15);
         cm |= (t & 1u) << i;
