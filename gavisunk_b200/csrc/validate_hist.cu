@@ -29,13 +29,25 @@ __global__ void __launch_bounds__(256) k_hist_max(const i32* __restrict__ hist, 
 }
 __global__ void __launch_bounds__(256) k_cnt_hist(const i32* __restrict__ hist, const u32* __restrict__ grp_contig,
                                                   const u8* __restrict__ contig_hap, u64 ng, u32 M, u32* cnt_hist) {
-  u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= ng) return;
-  u32 c = (u32)hist[g];
-  if (!c) return;
-  u8 h = contig_hap[grp_contig[g]];
-  if (h > 1) return;
-  atomicAdd(&cnt_hist[(u64)h * (M + 1) + c], 1u);
+  // almost all groups share a handful of count values: privatise the low bins per block
+  constexpr u32 LOW = 2048;
+  __shared__ u32 s_low[2 * LOW];
+  for (u32 i = threadIdx.x; i < 2 * LOW; i += blockDim.x) s_low[i] = 0;
+  __syncthreads();
+  for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (u64)gridDim.x * blockDim.x) {
+    u32 c = (u32)hist[g];
+    if (!c) continue;
+    u8 h = contig_hap[grp_contig[g]];
+    if (h > 1) continue;
+    if (c < LOW) atomicAdd(&s_low[h * LOW + c], 1u);
+    else atomicAdd(&cnt_hist[(u64)h * (M + 1) + c], 1u);
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < 2 * LOW; i += blockDim.x) {
+    u32 v = s_low[i];
+    u32 h = i / LOW, c = i % LOW;
+    if (v && c <= M) atomicAdd(&cnt_hist[(u64)h * (M + 1) + c], v);
+  }
 }
 // pandas .mode()[0]: the smallest of the most frequent values
 __global__ void __launch_bounds__(1024) k_mode(const u32* __restrict__ cnt_hist, u32 M, i64* mode) {
@@ -115,7 +127,7 @@ extern "C" int gvs_hist_mode(gvs_ctx* ctx, int64_t mode[2]) {
   if (M > (1u << 28)) return gvs_fail(ctx, GVS_E_OVERFLOW, "group hit count %u too large for the mode table", M);
   CKR(gvs_reserve(ctx, ctx->cnt_hist, 2ull * (M + 1) * 4 + 16));
   CK(cudaMemsetAsync(ctx->cnt_hist.p, 0, 2ull * (M + 1) * 4 + 16, ctx->stream));
-  LAUNCH(k_cnt_hist, (unsigned)cdiv(ng, 256), 256, 0, ctx->hist.as<i32>(), ctx->grp_contig.as<u32>(), ctx->contig_hap.as<u8>(), ng,
+  LAUNCH(k_cnt_hist, (unsigned)(cdiv(ng, 256) < (u64)ctx->n_sm * 4 ? cdiv(ng, 256) : (u64)ctx->n_sm * 4), 256, 0, ctx->hist.as<i32>(), ctx->grp_contig.as<u32>(), ctx->contig_hap.as<u8>(), ng,
          M, ctx->cnt_hist.as<u32>());
   i64* dm = (i64*)(ctx->counters.as<u64>() + 18);
   LAUNCH(k_mode, 2, 1024, 0, ctx->cnt_hist.as<u32>(), M, dm);

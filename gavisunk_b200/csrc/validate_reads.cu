@@ -142,18 +142,34 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       if (tid == 0) V.seg_cnt[s] = 0;
       continue;
     }
-    // ---- pass A: masked pairs by sign (:140-152); every unordered pair is seen twice ----
+    // ---- pass AB: masked pairs by sign (:140-152) and, for BOTH candidate orientations at once, the
+    //      incidence of every row in the oriented edge list (the (ID,pos) multiset M) with its order of
+    //      first appearance in M = [all left ends in edge order] + [all right ends]; the orientation is
+    //      only known after the whole read has been seen, so both variants are kept until then ----
     {
       u32 n0 = 0, n1 = 0;
       for (u32 r = tid; r < m; r += NT) {
         const u32 pr = w.P[r], sr = w.S[r];
+        u32 deg0 = 0, deg1 = 0, ld0 = 0, ld1 = 0, fp0 = NOV, fp1 = NOV;
         for (u32 q = 0; q < m; q++) {
           u32 pq = w.P[q], sq = w.S[q];
-          u32 ok = pair_ok(pr, sr, pq, sq) & (q > r);
-          u32 sg = pr > pq;  // sign of (i, j) = pos_i > pos_j with i = r < j = q
-          n1 += ok & sg;
-          n0 += ok & (sg ^ 1u);
+          u32 hi = q > r;
+          u32 sg = hi ? (pr > pq) : (pq > pr);  // sign of the pair ordered (min, max)
+          u32 ok = pair_ok(pr, sr, pq, sq) & (q != r);
+          u32 e1 = ok & sg, e0 = ok & (sg ^ 1u);
+          deg0 += e0;
+          deg1 += e1;
+          ld0 += e0 & hi;
+          ld1 += e1 & hi;
+          fp0 = (e0 & (hi ^ 1u) & (fp0 == NOV)) ? q : fp0;  // first edge (q, r) with r as the right end
+          fp1 = (e1 & (hi ^ 1u) & (fp1 == NOV)) ? q : fp1;
         }
+        n0 += ld0;
+        n1 += ld1;
+        w.deg[r] = deg0;
+        w.label[r] = deg1;
+        w.key[r] = ld0 ? (u64)r : ((1ull << 63) | ((u64)fp0 * m + r));
+        w.ct[r] = ld1 ? (u64)r : ((1ull << 63) | ((u64)fp1 * m + r));
       }
       for (int d = 16; d; d >>= 1) {
         n0 += __shfl_xor_sync(0xFFFFFFFFu, n0, d);
@@ -170,22 +186,12 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       continue;
     }
     const u32 orient = s_n1[grp] > s_n0[grp];  // np.unique sorted + argmax: a tie keeps 0 (:151-152)
-    // ---- pass B: incidence of every row in the oriented edge list (the (ID,pos) multiset M) and its
-    //      order of first appearance in M = [all left ends in edge order] + [all right ends] ----
     for (u32 r = tid; r < m; r += NT) {
-      const u32 pr = w.P[r], sr = w.S[r];
-      u32 deg = 0, fpart = NOV, left = 0;
-      for (u32 q = 0; q < m; q++) {
-        u32 pq = w.P[q], sq = w.S[q];
-        u32 hi = q > r;
-        u32 sg = hi ? (pr > pq) : (pq > pr);  // sign of the pair ordered (min, max)
-        u32 e = pair_ok(pr, sr, pq, sq) & (q != r) & (sg == orient);
-        deg += e;
-        left |= e & hi;
-        fpart = (e & (hi ^ 1u) & (fpart == NOV)) ? q : fpart;  // first edge (q, r) with r as the right end
+      if (orient) {
+        w.deg[r] = w.label[r];
+        w.key[r] = w.ct[r];
       }
-      w.deg[r] = deg;
-      w.key[r] = left ? (u64)r : ((1ull << 63) | ((u64)fpart * m + r));
+      w.ct[r] = NOT64;
     }
     gsync();
     // ---- multipos (:161-181): IDs seen at more than one read position keep their most frequent one ----
@@ -246,8 +252,23 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       }
       continue;
     }
+    // Shortcut for the common case: pass C already took one propagation step (label = min rep over the
+    // row's own ID and its neighbours); if every present row now carries the same label L, each of them
+    // is in or adjacent to vertex L, i.e. the graph is one component and no further round is needed.
+    if (tid == 0) { s_n0[grp] = NOV; s_n1[grp] = 0; }
+    gsync();
+    for (u32 r = tid; r < m; r += NT)
+      if (w.flags[r] & F_PRES) atomicMin(&s_n0[grp], w.label[r]);
+    gsync();
+    {
+      const u32 l0 = s_n0[grp];
+      u32 differs = 0;
+      for (u32 r = tid; r < m; r += NT) differs |= ((w.flags[r] & F_PRES) != 0) & (w.label[r] != l0);
+      if (differs) s_n1[grp] = 1;
+    }
+    gsync();
     // ---- components: min-label propagation over surviving edges and same-ID rows until stable ----
-    for (int round = 0; round < 4096; round++) {
+    for (int round = 0; s_n1[grp] && round < 4096; round++) {
       if (tid == 0) s_flag[grp] = 0;
       gsync();
       u32 changed = 0;
