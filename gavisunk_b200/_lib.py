@@ -31,6 +31,7 @@ PROTOTYPES = {
     "gvs_db_size": (C.c_int, [vp, u64p, u64p]),
     "gvs_db_export": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "gvs_reads_set": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_int]),
+    "gvs_set_copy_pipeline": (C.c_int, [vp, C.c_uint64, C.c_uint32]),
     "gvs_reads_meta": (C.c_int, [vp, vp, C.c_uint64, vp, vp, C.c_uint32]),
     "gvs_rows_set": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32]),
     "gvs_match": (C.c_int, [vp, u64p]),
@@ -43,6 +44,9 @@ PROTOTYPES = {
     "gvs_hist_mode": (C.c_int, [vp, i64p]),
     "gvs_bad_groups": (C.c_int, [vp, i64p, u64p]),
     "gvs_bad_get": (C.c_int, [vp, vp]),
+    "gvs_bad_set": (C.c_int, [vp, vp, vp, C.c_uint64, u64p]),
+    "gvs_groups_count": (C.c_int, [vp, u64p]),
+    "gvs_groups_get": (C.c_int, [vp, vp, vp, vp]),
     "gvs_validate": (C.c_int, [vp, C.c_uint32, u64p]),
     "gvs_pairs_get": (C.c_int, [vp, vp, vp, vp, vp]),
     "gvs_components_local": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),

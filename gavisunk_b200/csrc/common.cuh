@@ -19,6 +19,9 @@ typedef int32_t i32;
 typedef int64_t i64;
 
 #define GVS_NSM_DEFAULT 148
+#define GVS_TILE_BASES 512                 // window starts per probe tile (probe.cu PW_TILE)
+#define GVS_SEG_COUNT 16                   // copy/probe pipeline depth for host batches
+#define GVS_SEG_MIN_BYTES (256ull << 20)   // smaller host batches are copied in one piece
 
 // grow-only device buffer: stages re-use their scratch across calls so that the timed loop of
 // bench.py never allocates after the first (warm-up) step.
@@ -66,6 +69,14 @@ struct gvs_ctx {
   const u64* read_off = nullptr;  // device, n_reads+1
   u64 n_reads = 0, total_bases = 0;
   DevBuf own_seq, own_off;     // when copied from the host
+  // host batches are copied in segments on a second stream; the probe of segment s is launched as soon
+  // as its bytes (+ a two-tile halo) have landed, so the PCIe transfer hides the compute
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_reads_free = nullptr;  // everything that read the previous batch has finished
+  std::vector<cudaEvent_t> seg_ev;      // seg_ev[s]: bytes of segments 0..s are in HBM
+  std::vector<u64> seg_tile_end;        // tile index (512 bases) where segment s ends; empty = one launch
+  u64 seg_min_bytes = GVS_SEG_MIN_BYTES;
+  u32 seg_count = GVS_SEG_COUNT;
   DevBuf chunk_first, chunk_hap;  // device copies
   std::vector<u64> h_chunk_first;
   std::vector<u8> h_chunk_hap;

@@ -52,6 +52,12 @@ extern "C" void gvs_destroy(gvs_ctx* c) {
     cudaEventDestroy(c->ev0[i]);
     cudaEventDestroy(c->ev1[i]);
   }
+  for (cudaEvent_t e : c->seg_ev) cudaEventDestroy(e);
+  if (c->ev_reads_free) cudaEventDestroy(c->ev_reads_free);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
   delete c;
 }
 
@@ -88,6 +94,14 @@ extern "C" int gvs_stage_ms(gvs_ctx* ctx, int stage, float* ms) {
   return 0;
 }
 
+extern "C" int gvs_set_copy_pipeline(gvs_ctx* ctx, uint64_t min_bytes, uint32_t segments) {
+  if (!ctx) return GVS_E_ARG;
+  if (segments > 4096) return gvs_fail(ctx, GVS_E_ARG, "at most 4096 copy segments");
+  ctx->seg_min_bytes = min_bytes;
+  ctx->seg_count = segments;
+  return 0;
+}
+
 extern "C" uint64_t gvs_launch_count(gvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* read_off, uint64_t n_reads,
@@ -109,6 +123,8 @@ extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* r
   CKR(to_dev(ctx, ctx->chunk_hap, chunk_hap, (size_t)n_chunks));
   u64 total = 0;
   if (on_device) {
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->seg_tile_end.clear();
     CKR(read_dev(ctx, read_off + n_reads, &total));
     ctx->seq = seq;
     ctx->read_off = read_off;
@@ -117,8 +133,36 @@ extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* r
     // 64 bytes of slack: the probe kernel stages 16-byte vectors and may touch the tail
     CKR(gvs_reserve(ctx, ctx->own_seq, total + 64));
     CKR(gvs_reserve(ctx, ctx->own_off, (n_reads + 1) * sizeof(u64)));
-    if (total) CK(cudaMemcpyAsync(ctx->own_seq.p, seq, total, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->own_off.p, read_off, (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->seg_tile_end.clear();
+    const u64 n_tiles = cdiv(total, GVS_TILE_BASES);
+    u64 n_seg = (total >= ctx->seg_min_bytes && ctx->seg_count > 1) ? ctx->seg_count : 1;
+    if (n_seg > n_tiles) n_seg = n_tiles ? n_tiles : 1;
+    if (n_seg == 1) {
+      if (total) CK(cudaMemcpyAsync(ctx->own_seq.p, seq, total, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      if (!ctx->ev_reads_free) CK(cudaEventCreateWithFlags(&ctx->ev_reads_free, cudaEventDisableTiming));
+      while (ctx->seg_ev.size() < n_seg) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->seg_ev.push_back(e);
+      }
+      // the previous batch may still be read by work queued on the compute stream
+      CK(cudaEventRecord(ctx->ev_reads_free, ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_reads_free, 0));
+      u64 c0 = 0;
+      for (u64 s = 0; s < n_seg; s++) {
+        u64 t1 = (s + 1 == n_seg) ? n_tiles : (s + 1) * n_tiles / n_seg;
+        // the probe prefetches two tiles past the end of its span (the halo of the last windows)
+        u64 c1 = (s + 1 == n_seg) ? total : (t1 + 2) * GVS_TILE_BASES;
+        if (c1 > total) c1 = total;
+        if (c1 > c0) CK(cudaMemcpyAsync((u8*)ctx->own_seq.p + c0, seq + c0, c1 - c0, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->seg_ev[s], ctx->copy_stream));
+        ctx->seg_tile_end.push_back(t1);
+        c0 = c1;
+      }
+    }
     ctx->seq = ctx->own_seq.as<u8>();
     ctx->read_off = ctx->own_off.as<u64>();
   }

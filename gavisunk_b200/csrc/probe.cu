@@ -20,9 +20,11 @@
 //   * every warp appends its hits to its own region of the hit arrays (position order, no global
 //     atomics); a scan of the per-warp counts + one coalesced copy give the dense ordered list
 #include "table.cuh"
+#include <vector>
 
 #define PW_WARPS 8     // warps per block
 #define PW_TILE 512    // window starts per warp tile
+static_assert(PW_TILE == GVS_TILE_BASES, "ctx.cu sizes the copy segments in probe tiles");
 #define PW_RING 64     // packed words in the ring: two tile slots of 32 words (16 bases each)
 #define PW_MAXB 32
 
@@ -100,7 +102,8 @@ struct Probe2Params {
   u64 total;
   const u64* __restrict__ read_off;
   u64 n_reads;
-  u64 n_tiles;
+  u64 tile_begin, tile_stop;  // this launch covers tiles [tile_begin, tile_stop)
+  u64 warp_base;              // global index of this launch's first warp (hit region / count slot)
   u64 tiles_per_warp;
   const u32* __restrict__ filt;
   u32 filt_mask;
@@ -170,10 +173,11 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
   __shared__ WarpSmem sm_all[PW_WARPS];
   const int lane = threadIdx.x & 31;
   WarpSmem& sm = sm_all[threadIdx.x >> 5];
-  const u64 warp = (u64)blockIdx.x * PW_WARPS + (threadIdx.x >> 5);
-  const u64 tile0 = warp * P.tiles_per_warp;
+  const u64 lwarp = (u64)blockIdx.x * PW_WARPS + (threadIdx.x >> 5);
+  const u64 warp = P.warp_base + lwarp;
+  const u64 tile0 = P.tile_begin + lwarp * P.tiles_per_warp;
   u64 tile_end = tile0 + P.tiles_per_warp;
-  if (tile_end > P.n_tiles) tile_end = P.n_tiles;
+  if (tile_end > P.tile_stop) tile_end = P.tile_stop;
   if (tile0 >= tile_end) return;
   constexpr int CMAX = (K + 15 + 15) / 16;
   constexpr u32 ALL = 0xFFFFFFFFu;
@@ -477,13 +481,22 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   P.total = total;
   P.read_off = ctx->read_off;
   P.n_reads = ctx->n_reads;
-  P.n_tiles = n_tiles;
-  u64 blocks = (u64)ctx->n_sm * 4;
-  u64 warps = blocks * PW_WARPS;
-  P.tiles_per_warp = cdiv(n_tiles, warps);
-  if (P.tiles_per_warp < 4) P.tiles_per_warp = 4;
-  blocks = cdiv(cdiv(n_tiles, P.tiles_per_warp), PW_WARPS);
-  warps = blocks * PW_WARPS;
+  // launch plan: one launch for resident reads; for a host batch that is still arriving (ctx.cu) one
+  // launch per copy segment, each released by the segment's event
+  struct Seg { u64 t0, t1, tpw, blocks, warp_base, ev; };
+  std::vector<Seg> plan;
+  const bool piped = !ctx->seg_tile_end.empty() && ctx->seq == ctx->own_seq.as<u8>();
+  const u64 n_launch = piped ? ctx->seg_tile_end.size() : 1;
+  u64 warps = 0;
+  for (u64 s = 0, t0 = 0; s < n_launch; s++) {
+    u64 t1 = piped ? ctx->seg_tile_end[s] : n_tiles;
+    u64 tpw = cdiv(t1 - t0, (u64)ctx->n_sm * 4 * PW_WARPS);
+    if (tpw < 4) tpw = 4;
+    u64 blocks = cdiv(cdiv(t1 - t0, tpw), PW_WARPS);
+    if (blocks) plan.push_back({t0, t1, tpw, blocks, warps, s});
+    warps += blocks * PW_WARPS;
+    t0 = t1;
+  }
   *n_warps_out = warps;
   CKR(gvs_reserve(ctx, ctx->tile_cnt, warps * 4));
   CKR(gvs_reserve(ctx, ctx->tile_dst, warps * 8));
@@ -515,7 +528,6 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   const void* hot = ctx->filt1_words ? ctx->filt1.p : ctx->filt.p;
   size_t hot_bytes = ctx->filt1_words ? ctx->filt1_words * 4 : ctx->filt_words * 16;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)blocks);
   cfg.blockDim = dim3(PW_WARPS * 32);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = ctx->stream;
@@ -539,9 +551,17 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, fn, P);
-  ctx->launches++;
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) return gvs_fail(ctx, GVS_E_CUDA, "k_probe2 launch: %s", cudaGetErrorString(e));
+  for (size_t s = 0; s < plan.size(); s++) {
+    if (piped) CK(cudaStreamWaitEvent(ctx->stream, ctx->seg_ev[plan[s].ev], 0));
+    cfg.gridDim = dim3((unsigned)plan[s].blocks);
+    P.tile_begin = plan[s].t0;
+    P.tile_stop = plan[s].t1;
+    P.tiles_per_warp = plan[s].tpw;
+    P.warp_base = plan[s].warp_base;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, P);
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return gvs_fail(ctx, GVS_E_CUDA, "k_probe2 launch: %s", cudaGetErrorString(e));
+  }
   return 0;
 }

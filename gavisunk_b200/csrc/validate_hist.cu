@@ -13,6 +13,7 @@
 //       largest component (ties: the component holding the earliest vertex in graph-tool's
 //       insertion order), output in vertex order.
 #include "common.cuh"
+#include <algorithm>
 
 // ---------------------------------------------------------------------------------------------
 // histogram / bad groups
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) k_bad_flag(const i32* __restrict__ hist, 
   u8 h = contig_hap[grp_contig[g]];
   bool b = false;
   if (c > 0 && h <= 1) b = c > (h ? lim1 : lim0) || c < 2;  // badsunks_AR.py:48
+  else if (c > 0 && h <= 3) b = c > (h == 3 ? lim1 : lim0);  // contig of the other haplotype: only the upper limit (:51)
   bad[g] = b ? 1 : 0;
 }
 
@@ -176,3 +178,75 @@ extern "C" int gvs_bad_get(gvs_ctx* ctx, uint32_t* group_index) {
   return 0;
 }
 
+
+// groups named in a bad_sunks.txt (process-by-contig_lowmem_AR.py:66-72): keys = sorted (contig << 32 | group)
+__global__ void __launch_bounds__(256) k_bad_from_keys(const u32* __restrict__ grp_contig, const u32* __restrict__ grp_start, u64 ng,
+                                                       const u64* __restrict__ keys, u64 nk, u8* bad) {
+  u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  u64 key = ((u64)grp_contig[g] << 32) | grp_start[g];
+  u64 lo = 0, hi = nk;
+  while (lo < hi) {
+    u64 mid = (lo + hi) >> 1;
+    if (keys[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  bad[g] = (lo < nk && keys[lo] == key) ? 1 : 0;
+}
+
+extern "C" int gvs_bad_set(gvs_ctx* ctx, const uint32_t* contig, const uint32_t* group, uint64_t n, uint64_t* n_bad) {
+  if (!ctx || (n && (!contig || !group))) return GVS_E_ARG;
+  if (!ctx->groups_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_bad_set: no group index (database or gvs_rows_set first)");
+  CK(cudaSetDevice(ctx->device));
+  u64 ng = ctx->n_groups;
+  CKR(gvs_reserve(ctx, ctx->bad_flag, ng ? ng : 1));
+  CKR(gvs_reserve(ctx, ctx->bad_list, (ng ? ng : 1) * 4));
+  ctx->n_bad = 0;
+  if (ng) {
+    std::vector<u64> keys(n);
+    for (u64 i = 0; i < n; i++) keys[i] = ((u64)contig[i] << 32) | group[i];
+    std::sort(keys.begin(), keys.end());
+    DevBuf dk;
+    int rc = to_dev(ctx, dk, keys.data(), keys.size());
+    if (!rc) {
+      k_bad_from_keys<<<(unsigned)cdiv(ng, 256), 256, 0, ctx->stream>>>(ctx->grp_contig.as<u32>(), ctx->grp_start.as<u32>(), ng,
+                                                                        dk.as<u64>(), n, ctx->bad_flag.as<u8>());
+      ctx->launches++;
+      const u8* bf = ctx->bad_flag.as<u8>();
+      u32* bl = ctx->bad_list.as<u32>();
+      u32* tot = (u32*)(ctx->counters.as<u64>() + 20);
+      auto f = [bf] __device__(u64 g) -> u32 { return bf[g]; };
+      auto g2 = [bl] __device__(u64 g, u32 ex, u32 v) { if (v) bl[ex] = (u32)g; };
+      rc = device_scan<u32>(ctx, ng, f, g2, OpSum(), tot);
+      u32 nb = 0;
+      if (!rc) rc = read_dev(ctx, tot, &nb);
+      ctx->n_bad = nb;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    gvs_release(dk);
+    if (rc) return rc;
+  }
+  ctx->bad_ready = true;
+  if (n_bad) *n_bad = ctx->n_bad;
+  return 0;
+}
+
+extern "C" int gvs_groups_get(gvs_ctx* ctx, uint32_t* contig, uint32_t* group, int32_t* hist) {
+  if (!ctx) return GVS_E_ARG;
+  if (!ctx->groups_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_groups_get: no group index");
+  if (hist && !ctx->hist_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_groups_get: no histogram (gvs_group_hist)");
+  CK(cudaSetDevice(ctx->device));
+  u64 ng = ctx->n_groups;
+  if (ng == 0) return 0;
+  if (contig) CK(cudaMemcpyAsync(contig, ctx->grp_contig.p, ng * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (group) CK(cudaMemcpyAsync(group, ctx->grp_start.p, ng * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hist) CK(cudaMemcpyAsync(hist, ctx->hist.p, ng * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int gvs_groups_count(gvs_ctx* ctx, uint64_t* n_groups) {
+  if (!ctx || !n_groups) return GVS_E_ARG;
+  if (!ctx->groups_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_groups_count: no group index");
+  *n_groups = ctx->n_groups;
+  return 0;
+}

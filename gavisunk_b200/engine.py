@@ -213,6 +213,10 @@ class Engine:
         self._ck(self.lib.gvs_reads_set(self.ctx, _ptr(seq), _ptr(read_off), n, _ptr(chunk_first), _ptr(chunk_hap),
                                         len(chunk_hap), 0))
 
+    def set_copy_pipeline(self, min_bytes: int = 256 << 20, segments: int = 16):
+        """Host batches >= min_bytes are copied in `segments` pieces overlapped with the match."""
+        self._ck(self.lib.gvs_set_copy_pipeline(self.ctx, int(min_bytes), int(segments)))
+
     def set_reads_device(self, seq_ptr: int, off_ptr: int, n_reads: int, chunk_first, chunk_hap):
         chunk_first = _c(chunk_first, np.uint64)
         chunk_hap = _c(chunk_hap, np.uint8)

@@ -119,6 +119,11 @@ int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* read_off, ui
                   const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks,
                   int on_device);
 
+/* Host batches of at least `min_bytes` are copied in `segments` pieces on a second stream and the
+ * probe of each piece starts as soon as it has landed (PCIe transfer overlapped with the match).
+ * Defaults: 256 MiB, 16.  segments <= 1 disables the pipeline. */
+int gvs_set_copy_pipeline(gvs_ctx* ctx, uint64_t min_bytes, uint32_t segments);
+
 /* Read table without sequences (the CLI shims that start from .sunkpos / .rlen files):
  * read_len[n_reads] = column 2 of {hap}.rlen (workflow/src/rlen.nim:13-14), chunk layout as above. */
 int gvs_reads_meta(gvs_ctx* ctx, const uint32_t* read_len, uint64_t n_reads, const uint64_t* chunk_first,
@@ -147,6 +152,8 @@ int gvs_rows_get(gvs_ctx* ctx, int which, uint32_t* read_idx, uint32_t* pos, uin
 /* diag_filter_v3 (workflow/src/diag_filter_v3.nim:18-229) + diag_filter_step2
  * (workflow/src/diag_filter_step2.nim:13-66).
  *   contig_hap[n_contigs]   haplotype (0/1) whose .fai lists the contig, 255 = in neither
+ *                           (gvs_bad_groups also knows 2/3 = "contig of the other assembly, thresholded
+ *                           with haplotype 0/1's limit", badsunks_AR.py:51)
  *   contig_hash[n_contigs]  Nim `hash(name)` of the contig name (MurmurHash3_x86_32, seed 0,
  *                           0 remapped) -- decides ties through Table iteration order
  * n_best = reads that got a best contig, n_kept = rows that survive. */
@@ -178,6 +185,14 @@ int gvs_hist_mode(gvs_ctx* ctx, int64_t mode[2]);
  * caller exactly as the reference does (m + 4*sqrt(m) in float64) and passed as floor(limit). */
 int gvs_bad_groups(gvs_ctx* ctx, const int64_t limit_floor[2], uint64_t* n_bad);
 int gvs_bad_get(gvs_ctx* ctx, uint32_t* group_index /* n_bad entries */);
+/* Bad groups read from a bad_sunks.txt instead of computed here (process-by-contig_lowmem_AR.py:66-72,
+ * `ID2 not in @badsunkin`): n (contig, group) pairs in host memory; pairs that name no known group are
+ * ignored like the reference's string set does.  *n_bad = groups flagged. */
+int gvs_bad_set(gvs_ctx* ctx, const uint32_t* contig, const uint32_t* group, uint64_t n, uint64_t* n_bad);
+/* The group table behind every group_index: (contig, group start) and, when hist != NULL, the row
+ * count of gvs_group_hist (badsunks_AR.py:24-27 `counts`).  Host buffers of gvs_groups_count entries. */
+int gvs_groups_count(gvs_ctx* ctx, uint64_t* n_groups);
+int gvs_groups_get(gvs_ctx* ctx, uint32_t* contig, uint32_t* group, int32_t* hist);
 
 /* process-by-contig_lowmem_AR.py:50-207 per-read part: validated (group, read) pairs = rows of
  * inter_outs/{contig}_{hap}.tsv.  min_read_len is the reference's hard-coded 10000 (:106). */

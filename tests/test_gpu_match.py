@@ -33,3 +33,18 @@ def test_match_random_batched_chunks(name):
     got = run_match_chunks(eng, names, [ch["reads"] for ch in case["chunks"]])
     for g, ch in zip(got, case["chunks"]):
         assert g == ch["sunkpos"]
+
+
+@pytest.mark.parametrize("name", ["rand_k20", "rand_k31", "rand_k20_many", "kat_bytes"])
+@pytest.mark.parametrize("segments", [2, 7, 64])
+def test_match_copy_pipeline(name, segments):
+    """host batch copied in segments on the copy stream, one probe launch per segment
+    (gvs_set_copy_pipeline): rows identical to the reference ELF output whatever the split"""
+    case = load_golden(name)
+    eng, names = engine_from_case(case)
+    eng.set_copy_pipeline(0, segments)
+    chunks = [ch["reads"] for ch in case["chunks"]] if "chunks" in case else [case["reads"]]
+    want = [ch["sunkpos"] for ch in case["chunks"]] if "chunks" in case else [case["out"]]
+    for _ in range(2):  # second round re-uses the segment events and overwrites the resident batch
+        got = run_match_chunks(eng, names, chunks)
+        assert got == want
