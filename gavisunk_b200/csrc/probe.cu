@@ -4,21 +4,25 @@
 //
 // Warp-synchronous design (no block barriers; a warp that takes the rare exact-probe path never
 // stalls its neighbours):
-//   * each warp owns a contiguous span of 512-window tiles and walks it with a private cursor into
-//     read_off (no per-tile binary search)
+//   * a warp walks a span of consecutive 512-window tiles with a private cursor into read_off (no
+//     per-tile binary search)
 //   * per tile ONE coalesced 16-byte cp.async per lane brings the ASCII bases into shared memory two
 //     tiles ahead of the compute (the copy of tile T+2 is in flight while tile T is processed); the
 //     bases are packed to 2 bits twice -- forward (big-endian) and reverse complement -- into a
 //     two-tile ring, so the 32-base halo of a tile is simply the head of the next ring slot and both
 //     strands of every window are constant-shift funnel extractions (no rolling state)
-//   * canonical = min(fwd, rc); J = 4 consecutive windows share the (K-3)-mer that starts at the last
-//     of them, and every SUNK was inserted into the filter block of each of its 4 sub-mers, so ONE
-//     16-byte block of the L2-resident blocked Bloom filter serves 4 windows (0.25 scattered sectors
-//     per base); 4 bits per key, one per 32-bit word of the block
+//   * J = 4 consecutive windows share the (K-3)-mer that starts at the last of them, and every SUNK was
+//     entered into the filters under each of its 4 sub-mers.  Per group of 4 windows ONE word of the
+//     L2-resident presence filter is tested; the groups that pass (a few % / ~20 % for a whole genome)
+//     are compacted across the warp and only their windows are hashed (canonical = min(fwd, rc)) and
+//     tested against the group's 16-byte block of the blocked Bloom filter (4 bits per key, one per
+//     word) -- one window per lane, so the ALU work per base follows the pass rate, not the read length
 //   * filter-positive windows (~1 %) are compacted into a per-warp queue in position order and looked
 //     up in the exact table (32-byte bucket in HBM) 32 at a time
-//   * every warp appends its hits to its own region of the hit arrays (position order, no global
-//     atomics); a scan of the per-warp counts + one coalesced copy give the dense ordered list
+//   * work is handed out in spans of a few hundred tiles through one atomic counter (no tail: a warp
+//     that drew hit-poor reads simply takes more spans); every span appends its hits to its own region
+//     of the hit arrays (position order, no per-hit atomics); a scan of the per-span counts + one
+//     coalesced copy give the dense ordered list
 #include "table.cuh"
 #include <vector>
 
@@ -69,8 +73,10 @@ struct WarpSmem {
   u32 shrt[20];
   u32 bpos[PW_MAXB];
   u32 bidx[PW_MAXB];
-  u32 q_row[PW_TILE];
-  u16 q_p[PW_TILE];
+  u32 cand[PW_TILE / 32];  // filter-positive windows of the tile (bit p)
+  u16 inv[32];             // per lane: invalid windows among its 16
+  u32 q_row[PW_TILE];      // group queue: block hash of the passing group; later: row of a hit
+  u16 q_p[PW_TILE];        // group queue: group index inside the tile; later: window of a candidate / hit
 };
 
 // forward / reverse-complement k-mer of window p (0..511) of the tile whose ring base is `rb`
@@ -103,11 +109,13 @@ struct Probe2Params {
   const u64* __restrict__ read_off;
   u64 n_reads;
   u64 tile_begin, tile_stop;  // this launch covers tiles [tile_begin, tile_stop)
-  u64 warp_base;              // global index of this launch's first warp (hit region / count slot)
-  u64 tiles_per_warp;
+  u64 span_base;              // global index of this launch's first span (hit region / count slot)
+  u32 span_tiles, n_spans;    // spans of span_tiles tiles, handed out through *span_ctr
+  u32* span_ctr;
+  u32 blk_stream;             // blocked filter too large for L2: fetch its blocks with evict_first
   const u32* __restrict__ filt;
   u32 filt_mask;
-  const u32* __restrict__ filt1;  // presence filter (TWO-level variant)
+  const u32* __restrict__ filt1;  // presence filter of the sub-mers
   u32 filt1_mask;
   TabView tab;
   u32* hit_read;
@@ -115,7 +123,7 @@ struct Probe2Params {
   u32* hit_row;
   u64 hit_cap;
   u32* flags;
-  u32* warp_cnt;  // hits found by each warp (its hits sit at warp * cap_w in the hit arrays)
+  u32* warp_cnt;  // hits found in each span (they sit at span * cap_w in the hit arrays)
   u64 cap_w;
 };
 
@@ -168,188 +176,205 @@ __device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, int lane) {
   sm.rc[(rb + lane) & 63] = p_rc16(w);
 }
 
-template <int K, bool TWO>
+template <int K>
 __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params P) {
   __shared__ WarpSmem sm_all[PW_WARPS];
   const int lane = threadIdx.x & 31;
   WarpSmem& sm = sm_all[threadIdx.x >> 5];
-  const u64 lwarp = (u64)blockIdx.x * PW_WARPS + (threadIdx.x >> 5);
-  const u64 warp = P.warp_base + lwarp;
-  const u64 tile0 = P.tile_begin + lwarp * P.tiles_per_warp;
-  u64 tile_end = tile0 + P.tiles_per_warp;
-  if (tile_end > P.tile_stop) tile_end = P.tile_stop;
-  if (tile0 >= tile_end) return;
   constexpr int CMAX = (K + 15 + 15) / 16;
   constexpr u32 ALL = 0xFFFFFFFFu;
+  // Filter groups: J consecutive windows share the (K-J+1)-mer that starts at the last of them, and
+  // every SUNK was inserted under each of its J sub-mers (table.cu)
+  constexpr int J = GVS_FJ(K);
+  constexpr int L = K - J + 1;
+  constexpr int NG = 16 / J;
+  const u64 pol_keep = p_policy_keep();
+  const u64 pol_blk = P.blk_stream ? p_policy_stream() : pol_keep;
 
-  // cursor: first boundary index j >= 1 with read_off[j] > tile start; prev_off = start of the read
-  // that contains the tile start
-  u64 cur;
-  {
-    u64 ts0 = tile0 * PW_TILE;
-    u64 lo = 1, hi = P.n_reads;
-    while (lo < hi) {
-      u64 mid = (lo + hi) >> 1;
-      if (__ldg(P.read_off + mid) > ts0) hi = mid; else lo = mid + 1;
-    }
-    cur = lo;
-  }
-  u64 next_off = __ldg(P.read_off + cur);
-  u64 prev_off = __ldg(P.read_off + cur - 1);
+  for (;;) {
+    // ---- next span of tiles ----
+    u32 span = 0;
+    if (lane == 0) span = atomicAdd(P.span_ctr, 1u);
+    span = __shfl_sync(ALL, span, 0);
+    if (span >= P.n_spans) break;
+    const u64 tile0 = P.tile_begin + (u64)span * P.span_tiles;
+    u64 tile_end = tile0 + P.span_tiles;
+    if (tile_end > P.tile_stop) tile_end = P.tile_stop;
+    const u64 region = P.span_base + span;
 
-  // prologue: tiles T0 and T0+1 into ring slots 0 and 1
-  p_stage_issue(sm, P.seq, tile0, P.total, lane);
-  p_stage_finish(sm, 0, lane);
-  p_stage_issue(sm, P.seq, tile0 + 1, P.total, lane);
-  p_stage_finish(sm, 32, lane);
-  __syncwarp();
-
-  u32 wcount = 0;  // hits of this warp so far
-  for (u64 tile = tile0; tile < tile_end; tile++) {
-    const u64 ts = tile * PW_TILE;
-    const u32 rb = (u32)((tile - tile0) & 1) * 32;  // ring base of this tile
-    // prefetch tile T+2 (lands in sm.raw while this tile is processed)
-    p_stage_issue(sm, P.seq, tile + 2, P.total, lane);
-
-    // ---- read boundaries in (ts, ts + 512 + K - 2] ----
-    const u64 limit = ts + PW_TILE + (K > 1 ? K - 1 : 1);
-    const u64 cur0 = cur;
-    u32 nb = 0;
-    const bool has_bound = next_off < limit;
-    // the read that starts exactly at ts (its boundary belongs to the previous tile) may be (K-1) long
-    const bool start_short = K >= 2 && prev_off == ts && next_off - prev_off == (u64)(K - 1);
-    if (has_bound) {
-      if (lane < 20) { sm.bound[lane] = 0; sm.shrt[lane] = 0; }
-      __syncwarp();
-      u64 j = cur + lane;
-      for (;;) {
-        u64 o = (j <= P.n_reads) ? __ldg(P.read_off + j) : ~0ull;
-        bool inr = o < limit;
-        bool intile = inr && (o - ts) < PW_TILE;
-        u32 bal_tile = __ballot_sync(ALL, intile);
-        if (inr) {
-          u32 rel = (u32)(o - ts);
-          atomicOr(&sm.bound[rel >> 5], 1u << (rel & 31));
-          if (intile) {
-            u32 slot = nb + __popc(bal_tile & ((1u << lane) - 1));
-            if (slot < PW_MAXB) { sm.bpos[slot] = rel; sm.bidx[slot] = (u32)j; }
-            if (K >= 2 && j < P.n_reads && __ldg(P.read_off + j + 1) - o == (u64)(K - 1))
-              atomicOr(&sm.shrt[rel >> 5], 1u << (rel & 31));
-          }
-        }
-        nb += __popc(bal_tile);
-        u32 bal_adv = __ballot_sync(ALL, o <= ts + PW_TILE);
-        cur += __popc(bal_adv);
-        u32 bal_in = __ballot_sync(ALL, inr);
-        if (bal_in != ALL) break;
-        j += 32;
-      }
-      next_off = (cur <= P.n_reads) ? __ldg(P.read_off + cur) : ~0ull;
-      prev_off = __ldg(P.read_off + cur - 1);
-      __syncwarp();
-    }
-
-    // ---- per lane: 16 windows, both strands by constant-shift extraction ----
-    u32 cm = 0;  // candidate (filter-positive) windows of this lane
+    // cursor: first boundary index j >= 1 with read_off[j] > tile start; prev_off = start of the read
+    // that contains the tile start
+    u64 cur;
     {
-      const u32 wb = rb + lane;
-      const u32 f0 = sm.fw[wb & 63], f1 = sm.fw[(wb + 1) & 63], f2 = sm.fw[(wb + 2) & 63];
-      // rc words in DEscending ring order: r_j = rc of forward word (lane + CMAX - 1 - j)
-      const u32 r0 = sm.rc[(wb + CMAX - 1) & 63], r1 = sm.rc[(wb + CMAX - 2) & 63], r2 = sm.rc[(wb + CMAX - 3) & 63],
-                r3 = sm.rc[(wb + CMAX - 4) & 63];
-      // validity: no boundary inside (p, p+K-1], p < total
-      u32 inval = 0, S16 = 0;
+      u64 ts0 = tile0 * PW_TILE;
+      u64 lo = 1, hi = P.n_reads;
+      while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if (__ldg(P.read_off + mid) > ts0) hi = mid; else lo = mid + 1;
+      }
+      cur = lo;
+    }
+    u64 next_off = __ldg(P.read_off + cur);
+    u64 prev_off = __ldg(P.read_off + cur - 1);
+
+    // prologue: tiles T0 and T0+1 into ring slots 0 and 1
+    __syncwarp();
+    p_stage_issue(sm, P.seq, tile0, P.total, lane);
+    p_stage_finish(sm, 0, lane);
+    p_stage_issue(sm, P.seq, tile0 + 1, P.total, lane);
+    p_stage_finish(sm, 32, lane);
+    __syncwarp();
+
+    u32 wcount = 0;  // hits of this span so far
+    for (u64 tile = tile0; tile < tile_end; tile++) {
+      const u64 ts = tile * PW_TILE;
+      const u32 rb = (u32)((tile - tile0) & 1) * 32;  // ring base of this tile
+      // prefetch tile T+2 (lands in sm.raw while this tile is processed)
+      p_stage_issue(sm, P.seq, tile + 2, P.total, lane);
+
+      // ---- read boundaries in (ts, ts + 512 + K - 2] ----
+      const u64 limit = ts + PW_TILE + (K > 1 ? K - 1 : 1);
+      const u64 cur0 = cur;
+      u32 nb = 0;
+      const bool has_bound = next_off < limit;
+      // the read that starts exactly at ts (its boundary belongs to the previous tile) may be (K-1) long
+      const bool start_short = K >= 2 && prev_off == ts && next_off - prev_off == (u64)(K - 1);
       if (has_bound) {
-        int idx = lane >> 1, sh = (lane & 1) * 16;
-        u64 B = ((u64)sm.bound[idx] | ((u64)sm.bound[idx + 1] << 32)) >> sh;
-        if (sh) B |= (u64)sm.bound[idx + 2] << 48;
-        u64 x = 0;
-        if (K >= 2) {
-          x = B >> 1;
-          int c = 1;
-#pragma unroll
-          for (int it = 0; it < 6; it++) {
-            if (c < K - 1) {
-              int step = (K - 1 - c) < c ? (K - 1 - c) : c;
-              x |= x >> step;
-              c += step;
+        if (lane < 20) { sm.bound[lane] = 0; sm.shrt[lane] = 0; }
+        __syncwarp();
+        u64 j = cur + lane;
+        for (;;) {
+          u64 o = (j <= P.n_reads) ? __ldg(P.read_off + j) : ~0ull;
+          bool inr = o < limit;
+          bool intile = inr && (o - ts) < PW_TILE;
+          u32 bal_tile = __ballot_sync(ALL, intile);
+          if (inr) {
+            u32 rel = (u32)(o - ts);
+            atomicOr(&sm.bound[rel >> 5], 1u << (rel & 31));
+            if (intile) {
+              u32 slot = nb + __popc(bal_tile & ((1u << lane) - 1));
+              if (slot < PW_MAXB) { sm.bpos[slot] = rel; sm.bidx[slot] = (u32)j; }
+              if (K >= 2 && j < P.n_reads && __ldg(P.read_off + j + 1) - o == (u64)(K - 1))
+                atomicOr(&sm.shrt[rel >> 5], 1u << (rel & 31));
             }
           }
+          nb += __popc(bal_tile);
+          u32 bal_adv = __ballot_sync(ALL, o <= ts + PW_TILE);
+          cur += __popc(bal_adv);
+          u32 bal_in = __ballot_sync(ALL, inr);
+          if (bal_in != ALL) break;
+          j += 32;
         }
-        inval = (u32)x & 0xFFFFu;
-        S16 = (sm.shrt[idx] >> sh) & 0xFFFFu;
+        next_off = (cur <= P.n_reads) ? __ldg(P.read_off + cur) : ~0ull;
+        prev_off = __ldg(P.read_off + cur - 1);
+        __syncwarp();
       }
-      if (start_short && lane == 0) S16 |= 1u;
-      {
-        u64 p0 = ts + 16ull * lane;
-        if (p0 + 16 > P.total) {
-          u32 nv = p0 < P.total ? (u32)(P.total - p0) : 0u;
-          inval |= 0xFFFFu & ~((1u << nv) - 1);
-        }
-      }
-      // Filter blocks: J consecutive windows share the (K-J+1)-mer that starts at the last of them, and
-      // every SUNK was inserted into the block of each of its J sub-mers (table.cu), so ONE 16-byte
-      // block load serves J windows.
-      constexpr int J = GVS_FJ(K);
-      constexpr int L = K - J + 1;
-      constexpr int NG = 16 / J;
-      // Phase 1: block hashes of the NG groups; two-level: all presence-filter loads go out together
+
+      // ---- per lane: its 16 windows in NG groups; presence test of every group's shared sub-mer ----
+      u32 cm = 0;  // candidate (filter-positive) windows of this lane
+      u32 S16 = 0;
+      u32 pass = 0;  // groups whose sub-mer is (probably) a sub-mer of some SUNK
       u32 hbv[NG];
-      u32 w1[NG];
+      {
+        const u32 wb = rb + lane;
+        const u32 f0 = sm.fw[wb & 63], f1 = sm.fw[(wb + 1) & 63], f2 = sm.fw[(wb + 2) & 63];
+        // rc words in DEscending ring order: r_j = rc of forward word (lane + CMAX - 1 - j)
+        const u32 r0 = sm.rc[(wb + CMAX - 1) & 63], r1 = sm.rc[(wb + CMAX - 2) & 63], r2 = sm.rc[(wb + CMAX - 3) & 63],
+                  r3 = sm.rc[(wb + CMAX - 4) & 63];
+        // validity: no boundary inside (p, p+K-1], p < total
+        u32 inval = 0;
+        if (has_bound) {
+          int idx = lane >> 1, sh = (lane & 1) * 16;
+          u64 B = ((u64)sm.bound[idx] | ((u64)sm.bound[idx + 1] << 32)) >> sh;
+          if (sh) B |= (u64)sm.bound[idx + 2] << 48;
+          u64 x = 0;
+          if (K >= 2) {
+            x = B >> 1;
+            int c = 1;
 #pragma unroll
-      for (int g = 0; g < NG; g++) {
-        const int o = J * g + (J - 1);  // lane-relative base offset of the shared sub-mer
-        u64 sf = p_extract<L>(f0, f1, f2, o);
-        const int e = o + L;            // = J*g + K, inside [K, K+15] like the windows' own ends
-        const int c = (e + 15) / 16;
-        const int j0 = CMAX - c;
-        const int off = 16 * c - e;
-        u64 sr = (j0 == 0) ? p_extract<L>(r0, r1, r2, off) : p_extract<L>(r1, r2, r3, off);
-        hbv[g] = gvs_bhash(sf < sr ? sf : sr);
-        const u32 gm = (1u << J) - 1;
-        bool any_valid = ((inval >> (J * g)) & gm) != gm;
-        // whole-genome tables: L2-resident presence test before the HBM block
-        w1[g] = (TWO && any_valid) ? p_ldg_u32(P.filt1 + gvs_p1_word(hbv[g], P.filt1_mask), p_policy_keep()) : (any_valid ? ~0u : 0u);
-      }
-      uint4 blk[NG];
-      if (!TWO) {  // single-level: the blocks are the L2-resident structure, loads go out before the window math
-#pragma unroll
-        for (int g = 0; g < NG; g++)
-          blk[g] = w1[g] ? p_ldg_v4((const uint4*)P.filt + (hbv[g] & P.filt_mask), p_policy_keep()) : make_uint4(0, 0, 0, 0);
-      }
-      // Phase 2: the 16 window hashes (pure ALU, overlaps the loads in flight)
-      u32 hv[16];
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        u64 f = p_extract<K>(f0, f1, f2, i);
-        const int e = i + K;
-        const int c = (e + 15) / 16;
-        const int j0 = CMAX - c;
-        const int off = 16 * c - e;
-        u64 r = (j0 == 0) ? p_extract<K>(r0, r1, r2, off) : p_extract<K>(r1, r2, r3, off);
-        hv[i] = gvs_fhash(f < r ? f : r);
-      }
-      if (TWO) {  // Phase 3: presence verdicts -> the (few) 16-byte blocks in HBM, touched once
+            for (int it = 0; it < 6; it++) {
+              if (c < K - 1) {
+                int step = (K - 1 - c) < c ? (K - 1 - c) : c;
+                x |= x >> step;
+                c += step;
+              }
+            }
+          }
+          inval = (u32)x & 0xFFFFu;
+          S16 = (sm.shrt[idx] >> sh) & 0xFFFFu;
+        }
+        if (start_short && lane == 0) S16 |= 1u;
+        {
+          u64 p0 = ts + 16ull * lane;
+          if (p0 + 16 > P.total) {
+            u32 nv = p0 < P.total ? (u32)(P.total - p0) : 0u;
+            inval |= 0xFFFFu & ~((1u << nv) - 1);
+          }
+        }
+        sm.inv[lane] = (u16)inval;
+        if (lane < PW_TILE / 32) sm.cand[lane] = 0;
+        u32 w1[NG];
 #pragma unroll
         for (int g = 0; g < NG; g++) {
-          u32 m1 = gvs_p1_bits(hbv[g]);
-          blk[g] = ((w1[g] & m1) == m1) ? p_ldg_v4((const uint4*)P.filt + (hbv[g] & P.filt_mask), p_policy_stream())
-                                        : make_uint4(0, 0, 0, 0);
+          const int o = J * g + (J - 1);  // lane-relative base offset of the shared sub-mer
+          u64 sf = p_extract<L>(f0, f1, f2, o);
+          const int e = o + L;            // = J*g + K, inside [K, K+15] like the windows' own ends
+          const int c = (e + 15) / 16;
+          const int j0 = CMAX - c;
+          const int off = 16 * c - e;
+          u64 sr = (j0 == 0) ? p_extract<L>(r0, r1, r2, off) : p_extract<L>(r1, r2, r3, off);
+          hbv[g] = gvs_bhash(sf < sr ? sf : sr);
+          const u32 gm = (1u << J) - 1;
+          const bool any_valid = ((inval >> (J * g)) & gm) != gm;
+          w1[g] = any_valid ? p_ldg_u32(P.filt1 + gvs_p1_word(hbv[g], P.filt1_mask), pol_keep) : 0u;
+        }
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+          const u32 m1 = gvs_p1_bits(hbv[g]);
+          pass |= ((w1[g] & m1) == m1 ? 1u : 0u) << g;
         }
       }
-      // Phase 4: 4 bits per window, one in each word of its group's block
+      // ---- passing groups -> warp queue (position order); their windows are tested one per lane ----
+      if (__any_sync(ALL, pass != 0)) {
+        const u32 np_lane = __popc(pass);
+        u32 incl = np_lane;
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const uint4 b4 = blk[i / J];
-        const u32 h = hv[i];
-        u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
-                __funnelshift_r(b4.w, 0u, h >> 15);
-        cm |= (t & 1u) << i;
+        for (int d = 1; d < 32; d <<= 1) {
+          u32 o = __shfl_up_sync(ALL, incl, d);
+          if (lane >= d) incl += o;
+        }
+        const u32 n_grp = __shfl_sync(ALL, incl, 31);
+        u32 qo = incl - np_lane;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+          if ((pass >> g) & 1u) {
+            sm.q_p[qo] = (u16)(lane * NG + g);
+            sm.q_row[qo] = hbv[g];
+            qo++;
+          }
+        }
+        __syncwarp();
+        const u32 n_ent = n_grp * J;
+        for (u32 base = 0; base < n_ent; base += 32) {
+          const u32 e = base + lane;
+          if (e < n_ent) {
+            const u32 q = e / J, w = e % J;
+            const u32 p = (u32)sm.q_p[q] * J + w;  // window inside the tile
+            const u32 hb = sm.q_row[q];
+            const uint4 b4 = p_ldg_v4((const uint4*)P.filt + (hb & P.filt_mask), pol_blk);
+            const bool valid = !((sm.inv[p >> 4] >> (p & 15)) & 1u);
+            const u32 h = gvs_fhash(p_canon_at<K>(sm, rb, p, false));
+            const u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
+                          __funnelshift_r(b4.w, 0u, h >> 15);
+            if (valid && (t & 1u)) atomicOr(&sm.cand[p >> 5], 1u << (p & 31));
+          }
+        }
+        __syncwarp();
+        cm = (sm.cand[lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu;
       }
-      cm &= ~inval;
       if (S16) {  // bogus windows of (K-1)-long reads: last base read as A, always "valid"
-        for (u32 s = S16; s; s &= s - 1) {
-          int i = __ffs(s) - 1;
+        for (u32 s16 = S16; s16; s16 &= s16 - 1) {
+          int i = __ffs(s16) - 1;
           u32 p = 16u * lane + i;
           u64 canon = p_canon_at<K>(sm, rb, p, true);
           // its own first sub-mer (real bases only) selects the block
@@ -363,104 +388,101 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         }
       }
       cm |= (S16 << 16);  // remember which candidates are forced-A windows
-    }
-    // ---- queue candidates in position order ----
-    u32 nh = 0;
-    if (__any_sync(ALL, (cm & 0xFFFFu) != 0)) {
-      u32 ncand_lane = __popc(cm & 0xFFFFu);
-      u32 incl = ncand_lane;
+      // ---- queue candidates in position order ----
+      u32 nh = 0;
+      if (__any_sync(ALL, (cm & 0xFFFFu) != 0)) {
+        u32 ncand_lane = __popc(cm & 0xFFFFu);
+        u32 incl = ncand_lane;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        u32 o = __shfl_up_sync(ALL, incl, d);
-        if (lane >= d) incl += o;
-      }
-      const u32 ncand = __shfl_sync(ALL, incl, 31);
-      u32 qo = incl - ncand_lane;
-      for (u32 s = cm & 0xFFFFu; s; s &= s - 1) {
-        int i = __ffs(s) - 1;
-        sm.q_p[qo++] = (u16)((16u * lane + i) | (((cm >> (16 + i)) & 1) << 15));
-      }
-      __syncwarp();
-      // ---- exact lookups, 32 candidates per round ----
-      for (u32 base = 0; base < ncand; base += 32) {
-        u32 row = GVS_NOHIT;
-        u32 pp = 0;
-        if (base + lane < ncand) {
-          u32 e = sm.q_p[base + lane];
-          pp = e & 0x7FFFu;
-          u64 canon = p_canon_at<K>(sm, rb, pp, (e >> 15) != 0);
-          row = tab_lookup(P.tab, canon, gvs_mix(canon));
-          if (row == GVS_ROW_MISSING) {
-            atomicOr(P.flags, FLAG_KEYERROR);
-            row = GVS_NOHIT;
-          } else if (row >= GVS_NOHIT) {
-            row = GVS_NOHIT;
-          }
+        for (int d = 1; d < 32; d <<= 1) {
+          u32 o = __shfl_up_sync(ALL, incl, d);
+          if (lane >= d) incl += o;
         }
-        u32 bal = __ballot_sync(ALL, row != GVS_NOHIT);
-        __syncwarp();
-        if (row != GVS_NOHIT) {
-          u32 d = nh + __popc(bal & ((1u << lane) - 1));
-          sm.q_p[d] = (u16)pp;
-          sm.q_row[d] = row;
+        const u32 ncand = __shfl_sync(ALL, incl, 31);
+        u32 qo = incl - ncand_lane;
+        for (u32 s = cm & 0xFFFFu; s; s &= s - 1) {
+          int i = __ffs(s) - 1;
+          sm.q_p[qo++] = (u16)((16u * lane + i) | (((cm >> (16 + i)) & 1) << 15));
         }
-        nh += __popc(bal);
         __syncwarp();
-      }
-    }
-    // ---- append the tile's hits to this warp's region (position order, no global atomics) ----
-    if (nh) {
-      const bool fits = (u64)wcount + nh <= P.cap_w;
-      if (!fits && lane == 0) atomicOr(P.flags, FLAG_OVERFLOW);
-      const u64 obase = warp * P.cap_w + wcount;
-      wcount += nh;
-      for (u32 idx = lane; fits && idx < nh; idx += 32) {
-        u64 o = obase + idx;
-        u32 prel = sm.q_p[idx];
-        u64 p = ts + prel;
-        u32 rd;
-        if (!has_bound || nb <= PW_MAXB) {
-          rd = (u32)(cur0 - 1);
-          if (has_bound) {
-            u32 bestpos = 0;
-            bool any = false;
-            for (u32 q = 0; q < nb; q++) {
-              u32 bp = sm.bpos[q], bj = sm.bidx[q];
-              if (bp <= prel && (!any || bp > bestpos || (bp == bestpos && bj > rd))) {
-                any = true;
-                bestpos = bp;
-                rd = bj;
-              }
+        // ---- exact lookups, 32 candidates per round ----
+        for (u32 base = 0; base < ncand; base += 32) {
+          u32 row = GVS_NOHIT;
+          u32 pp = 0;
+          if (base + lane < ncand) {
+            u32 e = sm.q_p[base + lane];
+            pp = e & 0x7FFFu;
+            u64 canon = p_canon_at<K>(sm, rb, pp, (e >> 15) != 0);
+            row = tab_lookup(P.tab, canon, gvs_mix(canon));
+            if (row == GVS_ROW_MISSING) {
+              atomicOr(P.flags, FLAG_KEYERROR);
+              row = GVS_NOHIT;
+            } else if (row >= GVS_NOHIT) {
+              row = GVS_NOHIT;
             }
           }
-        } else {
-          u64 l = 1, h2 = P.n_reads;
-          while (l < h2) {
-            u64 mid = (l + h2) >> 1;
-            if (__ldg(P.read_off + mid) > p) h2 = mid; else l = mid + 1;
+          u32 bal = __ballot_sync(ALL, row != GVS_NOHIT);
+          __syncwarp();
+          if (row != GVS_NOHIT) {
+            u32 d = nh + __popc(bal & ((1u << lane) - 1));
+            sm.q_p[d] = (u16)pp;
+            sm.q_row[d] = row;
           }
-          rd = (u32)(l - 1);
+          nh += __popc(bal);
+          __syncwarp();
         }
-        P.hit_read[o] = rd;
-        P.hit_w[o] = (u32)(p - __ldg(P.read_off + rd));
-        P.hit_row[o] = sm.q_row[idx];
       }
+      // ---- append the tile's hits to this span's region (position order, no global atomics) ----
+      if (nh) {
+        const bool fits = (u64)wcount + nh <= P.cap_w;
+        if (!fits && lane == 0) atomicOr(P.flags, FLAG_OVERFLOW);
+        const u64 obase = region * P.cap_w + wcount;
+        wcount += nh;
+        for (u32 idx = lane; fits && idx < nh; idx += 32) {
+          u64 o = obase + idx;
+          u32 prel = sm.q_p[idx];
+          u64 p = ts + prel;
+          u32 rd;
+          if (!has_bound || nb <= PW_MAXB) {
+            rd = (u32)(cur0 - 1);
+            if (has_bound) {
+              u32 bestpos = 0;
+              bool any = false;
+              for (u32 q = 0; q < nb; q++) {
+                u32 bp = sm.bpos[q], bj = sm.bidx[q];
+                if (bp <= prel && (!any || bp > bestpos || (bp == bestpos && bj > rd))) {
+                  any = true;
+                  bestpos = bp;
+                  rd = bj;
+                }
+              }
+            }
+          } else {
+            u64 l = 1, h2 = P.n_reads;
+            while (l < h2) {
+              u64 mid = (l + h2) >> 1;
+              if (__ldg(P.read_off + mid) > p) h2 = mid; else l = mid + 1;
+            }
+            rd = (u32)(l - 1);
+          }
+          P.hit_read[o] = rd;
+          P.hit_w[o] = (u32)(p - __ldg(P.read_off + rd));
+          P.hit_row[o] = sm.q_row[idx];
+        }
+      }
+      // ---- tile T is done: its ring slot receives tile T+2 ----
+      __syncwarp();
+      p_stage_finish(sm, rb, lane);
+      __syncwarp();
     }
-    // ---- tile T is done: its ring slot receives tile T+2 ----
-    __syncwarp();
-    p_stage_finish(sm, rb, lane);
-    __syncwarp();
+    if (lane == 0) P.warp_cnt[region] = wcount;
   }
-  if (lane == 0) P.warp_cnt[warp] = wcount;
 }
 
 typedef void (*probe_fn)(const Probe2Params);
-template <int K>
-static probe_fn probe_entry(bool two) { return two ? k_probe2<K, true> : k_probe2<K, false>; }
-
-static probe_fn probe_table(int k, bool two) {
+static probe_fn probe_table(int k) {
   switch (k) {
-#define PK(n) case n: return probe_entry<n>(two);
+#define PK(n) case n: return k_probe2<n>;
     PK(1) PK(2) PK(3) PK(4) PK(5) PK(6) PK(7) PK(8) PK(9) PK(10) PK(11) PK(12) PK(13) PK(14) PK(15) PK(16)
     PK(17) PK(18) PK(19) PK(20) PK(21) PK(22) PK(23) PK(24) PK(25) PK(26) PK(27) PK(28) PK(29) PK(30) PK(31)
 #undef PK
@@ -468,12 +490,12 @@ static probe_fn probe_table(int k, bool two) {
   return nullptr;
 }
 
-// launches the probe over ctx's reads; warp w's hits land at w * cap_w in ctx->hit_*, its count in
-// ctx->tile_cnt[w] (zeroed here); counters[1] = flags
+// launches the probe over ctx's reads; span s's hits land at s * cap_w in ctx->hit_*, its count in
+// ctx->tile_cnt[s] (zeroed here); counters[1] = flags
 int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   u64 total = ctx->total_bases;
   u64 n_tiles = cdiv(total, PW_TILE);
-  probe_fn fn = probe_table(ctx->k, ctx->filt1_words != 0);
+  probe_fn fn = probe_table(ctx->k);
   if (!fn) return gvs_fail(ctx, GVS_E_ARG, "no probe kernel for k=%d", ctx->k);
   u64* counters = ctx->counters.as<u64>();
   Probe2Params P;
@@ -482,31 +504,42 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   P.read_off = ctx->read_off;
   P.n_reads = ctx->n_reads;
   // launch plan: one launch for resident reads; for a host batch that is still arriving (ctx.cu) one
-  // launch per copy segment, each released by the segment's event
-  struct Seg { u64 t0, t1, tpw, blocks, warp_base, ev; };
+  // launch per copy segment, each released by the segment's event.  Inside a launch the tiles are cut
+  // into spans (~32 per resident warp) that the warps draw from an atomic counter.
+  struct Seg { u64 t0, t1, span_base, ev; u32 span_tiles, n_spans, blocks; };
   std::vector<Seg> plan;
   const bool piped = !ctx->seg_tile_end.empty() && ctx->seq == ctx->own_seq.as<u8>();
   const u64 n_launch = piped ? ctx->seg_tile_end.size() : 1;
-  u64 warps = 0;
+  const u64 resident_warps = (u64)ctx->n_sm * 4 * PW_WARPS;
+  u64 spans = 0;
   for (u64 s = 0, t0 = 0; s < n_launch; s++) {
     u64 t1 = piped ? ctx->seg_tile_end[s] : n_tiles;
-    u64 tpw = cdiv(t1 - t0, (u64)ctx->n_sm * 4 * PW_WARPS);
-    if (tpw < 4) tpw = 4;
-    u64 blocks = cdiv(cdiv(t1 - t0, tpw), PW_WARPS);
-    if (blocks) plan.push_back({t0, t1, tpw, blocks, warps, s});
-    warps += blocks * PW_WARPS;
+    if (t1 > t0) {
+      u64 st = cdiv(t1 - t0, resident_warps * 32);
+      if (st < 8) st = 8;
+      if (st > 1024) st = 1024;
+      u64 ns = cdiv(t1 - t0, st);
+      u64 blocks = cdiv(ns, PW_WARPS);
+      if (blocks > (u64)ctx->n_sm * 4) blocks = (u64)ctx->n_sm * 4;
+      plan.push_back({t0, t1, spans, s, (u32)st, (u32)ns, (u32)blocks});
+      spans += ns;
+    }
     t0 = t1;
   }
-  *n_warps_out = warps;
-  CKR(gvs_reserve(ctx, ctx->tile_cnt, warps * 4));
-  CKR(gvs_reserve(ctx, ctx->tile_dst, warps * 8));
-  CK(cudaMemsetAsync(ctx->tile_cnt.p, 0, warps * 4, ctx->stream));
-  P.cap_w = ctx->hit_cap / warps;
+  if (spans >= 0xFFFFFFF0ull) return gvs_fail(ctx, GVS_E_OVERFLOW, "too many probe spans");
+  *n_warps_out = spans;
+  CKR(gvs_reserve(ctx, ctx->tile_cnt, spans * 4));
+  CKR(gvs_reserve(ctx, ctx->tile_dst, spans * 8));
+  CKR(gvs_reserve(ctx, ctx->tile_off, (plan.size() + 1) * 4));  // one span counter per launch
+  CK(cudaMemsetAsync(ctx->tile_cnt.p, 0, spans * 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->tile_off.p, 0, (plan.size() + 1) * 4, ctx->stream));
+  P.cap_w = ctx->hit_cap / spans;
   *cap_w_out = P.cap_w;
   P.filt = ctx->filt.as<u32>();
   P.filt_mask = (u32)(ctx->filt_words - 1);
-  P.filt1 = ctx->filt1_words ? ctx->filt1.as<u32>() : nullptr;
-  P.filt1_mask = (u32)(ctx->filt1_words ? ctx->filt1_words - 1 : 0);
+  P.filt1 = ctx->filt1.as<u32>();
+  P.filt1_mask = (u32)(ctx->filt1_words - 1);
+  P.blk_stream = ctx->filt_words * 16 > (32ull << 20) ? 1u : 0u;
   P.tab.keys = ctx->tab_keys.as<u64>();
   P.tab.rows = ctx->tab_rows.as<u32>();
   P.tab.slots = ctx->tab_slots;
@@ -516,17 +549,17 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   P.hit_cap = ctx->hit_cap;
   P.flags = (u32*)(counters + 1);
   P.warp_cnt = ctx->tile_cnt.as<u32>();
-  // L2 persistence: the structure every window group touches (the presence filter of a whole-genome
-  // database, else the blocked filter) is pinned in the persisting carve-out of L2; everything outside
-  // the window (reads, exact table, hit lists) is treated as streaming.
+  // L2 persistence: the structure every window group touches (the presence filter) is pinned in the
+  // persisting carve-out of L2; everything outside the window (reads, exact table, hit lists) is
+  // treated as streaming.
   static int persist_max = -1, window_max = 0;
   if (persist_max < 0) {
     cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
     cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
     if (persist_max < 0) persist_max = 0;
   }
-  const void* hot = ctx->filt1_words ? ctx->filt1.p : ctx->filt.p;
-  size_t hot_bytes = ctx->filt1_words ? ctx->filt1_words * 4 : ctx->filt_words * 16;
+  const void* hot = ctx->filt1.p;
+  size_t hot_bytes = ctx->filt1_words * 4;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(PW_WARPS * 32);
   cfg.dynamicSmemBytes = 0;
@@ -553,11 +586,13 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   cfg.numAttrs = n_attr;
   for (size_t s = 0; s < plan.size(); s++) {
     if (piped) CK(cudaStreamWaitEvent(ctx->stream, ctx->seg_ev[plan[s].ev], 0));
-    cfg.gridDim = dim3((unsigned)plan[s].blocks);
+    cfg.gridDim = dim3(plan[s].blocks);
     P.tile_begin = plan[s].t0;
     P.tile_stop = plan[s].t1;
-    P.tiles_per_warp = plan[s].tpw;
-    P.warp_base = plan[s].warp_base;
+    P.span_tiles = plan[s].span_tiles;
+    P.n_spans = plan[s].n_spans;
+    P.span_base = plan[s].span_base;
+    P.span_ctr = ctx->tile_off.as<u32>() + s;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fn, P);
     ctx->launches++;
     if (e == cudaSuccess) e = cudaGetLastError();

@@ -48,7 +48,7 @@ __global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slot
       u64 rc = gvs_revcomp(sub, L);
       u32 hb = gvs_bhash(sub < rc ? sub : rc);
       u64 blk = hb & (filt_blocks - 1);
-      if (filt1) atomicOr(&filt1[gvs_p1_word(hb, filt1_mask)], gvs_p1_bits(hb));
+      atomicOr(&filt1[gvs_p1_word(hb, filt1_mask)], gvs_p1_bits(hb));
       atomicOr(&filt[4 * blk + 0], 1u << (h & 31));
       atomicOr(&filt[4 * blk + 1], 1u << ((h >> 5) & 31));
       atomicOr(&filt[4 * blk + 2], 1u << ((h >> 10) & 31));
@@ -113,11 +113,14 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
   if (fw > (1ull << 27)) fw = 1ull << 27;
   ctx->filt_words = fw;  // number of blocks
   CKR(gvs_reserve(ctx, ctx->filt, fw * 16));
-  // blocked filter beyond L2 reach (> 48 MiB): put a 64 MiB presence filter of the sub-mers in front
-  ctx->filt1_words = (fw * 16 > (48ull << 20)) ? (1ull << 24) : 0;
-  if (ctx->filt1_words) {
-    CKR(gvs_reserve(ctx, ctx->filt1, ctx->filt1_words * 4));
-    LAUNCH(k_fill_u32, grid_for(ctx, ctx->filt1_words, 256), 256, 0, ctx->filt1.as<u32>(), ctx->filt1_words, 0u);
+  // presence filter of the sub-mers in front of it: ~16 bits per distinct sub-mer, at most 64 MiB (L2)
+  {
+    u64 w1 = next_pow2((n_loc ? n_loc : 1) * 5 / 8);
+    if (w1 < (1ull << 10)) w1 = 1ull << 10;
+    if (w1 > (1ull << 24)) w1 = 1ull << 24;
+    ctx->filt1_words = w1;
+    CKR(gvs_reserve(ctx, ctx->filt1, w1 * 4));
+    LAUNCH(k_fill_u32, grid_for(ctx, w1, 256), 256, 0, ctx->filt1.as<u32>(), w1, 0u);
   }
   u64* keys = ctx->tab_keys.as<u64>();
   u32* rows = ctx->tab_rows.as<u32>();
@@ -131,7 +134,7 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
     LAUNCH(k_tab_mark_db, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
   }
   LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u32>(), fw, ctx->k,
-         ctx->filt1_words ? ctx->filt1.as<u32>() : (u32*)nullptr, (u32)(ctx->filt1_words ? ctx->filt1_words - 1 : 0));
+         ctx->filt1.as<u32>(), (u32)(ctx->filt1_words - 1));
   return 0;
 }
 
