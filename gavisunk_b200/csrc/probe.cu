@@ -45,10 +45,30 @@ __device__ __forceinline__ u32 p_codes4(u32 x) {
   u32 low = __vcmpeq4(x & 0xFCFCFCFCu, 0u);
   return (f & letter) | (x & low & 0x03030303u);
 }
-// 4 code bytes (first base in byte 0) -> 8 bits big-endian (first base in bits 7:6)
-__device__ __forceinline__ u32 p_be8(u32 c) { return (c * 0x40100401u) >> 24; }
+// Fast path for the overwhelmingly common tile that holds nothing but A/C/G/T (any case): the code of a
+// letter is ((x >> 1) ^ (x >> 2)) & 3; `bad` collects a non-zero value when a byte is something else
+// (the codes are turned back into letters with one PRMT and compared with the upper-cased input).
+__device__ __forceinline__ u32 p_codes4_fast(u32 x, u32& bad) {
+  u32 f = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+  u32 t = f | (f >> 4);                      // byte 0 = f1:f0, byte 2 = f3:f2 (nibbles)
+  u32 sel = __byte_perm(t, 0u, 0x4420);      // low 16 bits = f3:f2:f1:f0
+  u32 letters = __byte_perm(0x54474341u, 0u, sel);  // "ACGT"[f] per byte
+  bad |= letters ^ (x & 0xDFDFDFDFu);
+  return f;
+}
+// 4 code bytes (first base in byte 0) -> 8 bits big-endian (first base in bits 7:6), left in the TOP byte
+__device__ __forceinline__ u32 p_be8_top(u32 c) { return c * 0x40100401u; }
+__device__ __forceinline__ u32 p_gather_top(u32 px, u32 py, u32 pz, u32 pw) {
+  u32 t1 = __byte_perm(py, px, 0x0073);  // low 16 bits = top(px):top(py)
+  u32 t2 = __byte_perm(pw, pz, 0x0073);
+  return __byte_perm(t2, t1, 0x5410);
+}
 __device__ __forceinline__ u32 p_pack16_be(uint4 v) {
-  return (p_be8(p_codes4(v.x)) << 24) | (p_be8(p_codes4(v.y)) << 16) | (p_be8(p_codes4(v.z)) << 8) | p_be8(p_codes4(v.w));
+  return p_gather_top(p_be8_top(p_codes4(v.x)), p_be8_top(p_codes4(v.y)), p_be8_top(p_codes4(v.z)), p_be8_top(p_codes4(v.w)));
+}
+__device__ __forceinline__ u32 p_pack16_be_fast(uint4 v, u32& bad) {
+  return p_gather_top(p_be8_top(p_codes4_fast(v.x, bad)), p_be8_top(p_codes4_fast(v.y, bad)),
+                      p_be8_top(p_codes4_fast(v.z, bad)), p_be8_top(p_codes4_fast(v.w, bad)));
 }
 // reverse complement of 16 packed bases
 __device__ __forceinline__ u32 p_rc16(u32 w) {
@@ -171,7 +191,9 @@ __device__ __forceinline__ void p_stage_issue(WarpSmem& sm, const u8* __restrict
 __device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, int lane) {
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   uint4 v = sm.raw[lane];
-  u32 w = p_pack16_be(v);
+  u32 bad = 0;
+  u32 w = p_pack16_be_fast(v, bad);
+  if (__any_sync(0xFFFFFFFFu, bad != 0)) w = p_pack16_be(v);  // N runs, U, control bytes: the exact byte map
   sm.fw[(rb + lane) & 63] = w;
   sm.rc[(rb + lane) & 63] = p_rc16(w);
 }
@@ -355,18 +377,32 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         }
         __syncwarp();
         const u32 n_ent = n_grp * J;
-        for (u32 base = 0; base < n_ent; base += 32) {
-          const u32 e = base + lane;
-          if (e < n_ent) {
-            const u32 q = e / J, w = e % J;
-            const u32 p = (u32)sm.q_p[q] * J + w;  // window inside the tile
-            const u32 hb = sm.q_row[q];
-            const uint4 b4 = p_ldg_v4((const uint4*)P.filt + (hb & P.filt_mask), pol_blk);
-            const bool valid = !((sm.inv[p >> 4] >> (p & 15)) & 1u);
-            const u32 h = gvs_fhash(p_canon_at<K>(sm, rb, p, false));
-            const u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
-                          __funnelshift_r(b4.w, 0u, h >> 15);
-            if (valid && (t & 1u)) atomicOr(&sm.cand[p >> 5], 1u << (p & 31));
+        constexpr int RB = 4;  // rounds whose block loads are issued back to back before any window math
+        for (u32 base = 0; base < n_ent; base += 32 * RB) {
+          uint4 b4[RB];
+          u32 pw[RB];
+#pragma unroll
+          for (int r = 0; r < RB; r++) {
+            const u32 e = base + 32 * r + lane;
+            pw[r] = 0xFFFFFFFFu;
+            b4[r] = make_uint4(0, 0, 0, 0);
+            if (e < n_ent) {
+              const u32 q = e / J, w = e % J;
+              pw[r] = (u32)sm.q_p[q] * J + w;  // window inside the tile
+              b4[r] = p_ldg_v4((const uint4*)P.filt + (sm.q_row[q] & P.filt_mask), pol_blk);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < RB; r++) {
+            if (base + 32 * r >= n_ent) break;  // warp-uniform
+            const u32 p = pw[r];
+            if (p != 0xFFFFFFFFu) {
+              const bool valid = !((sm.inv[p >> 4] >> (p & 15)) & 1u);
+              const u32 h = gvs_fhash(p_canon_at<K>(sm, rb, p, false));
+              const u32 t = __funnelshift_r(b4[r].x, 0u, h) & __funnelshift_r(b4[r].y, 0u, h >> 5) &
+                            __funnelshift_r(b4[r].z, 0u, h >> 10) & __funnelshift_r(b4[r].w, 0u, h >> 15);
+              if (valid && (t & 1u)) atomicOr(&sm.cand[p >> 5], 1u << (p & 31));
+            }
           }
         }
         __syncwarp();
