@@ -53,9 +53,12 @@ PROTOTYPES = {
     "gvs_components_merge": (C.c_int, [vp, vp]),
     "gvs_intervals": (C.c_int, [vp, u64p]),
     "gvs_intervals_get": (C.c_int, [vp, vp, vp, vp]),
+    "gvs_intervals_set": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint32]),
     "gvs_gaps": (C.c_int, [vp, vp, u64p, u64p]),
     "gvs_gaps_get": (C.c_int, [vp, vp, vp, vp, vp]),
     "gvs_covprob_table": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_double, C.c_double, vp]),
+    "gvs_covprob_gaps": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, vp]),
+    "gvs_slop": (C.c_int, [vp, vp, vp, vp, C.c_uint64, vp, C.c_uint32, C.c_int64]),
     "gvs_synth_assembly": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_double, C.c_double, C.c_uint64]),
     "gvs_synth_reads_plan": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_double, C.c_double,
                                        C.c_uint32, C.c_uint32, C.c_uint64, vp, u64p]),

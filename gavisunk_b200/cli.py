@@ -4,10 +4,20 @@
   python -m gavisunk_b200.cli rlen <reads> <out.rlen>
   python -m gavisunk_b200.cli diag_filter_v3 <sunkpos> <asm.fai>            (stdout)
   python -m gavisunk_b200.cli diag_filter_step2 <sunkpos[.gz]> <diag[.gz]>  (stdout)
+  python -m gavisunk_b200.cli badsunks_AR <fai1> <fai2> <sunkpos1> <sunkpos2> <out>
+  python -m gavisunk_b200.cli process_by_contig <locs> <sunkpos> <rlen> <badsunks> <out.tsv> <out.bed> [--minlen N] [--opt_filt]
+  python -m gavisunk_b200.cli get_gaps <fai1> <fai2> <sample> <indir/> <outdir/>
+  python -m gavisunk_b200.cli slop_gaps <gaps.bed> <asm.fai> <out.bed>
+  python -m gavisunk_b200.cli covprob --bed B --locs L --rlen R --fai F --sunk-len K --tsv OUT
+  python -m gavisunk_b200.cli split_locs --ont-pos P --kmer-loc L --flag results/S/breaks/hapN_splits_pos.done --hap hapN
   python -m gavisunk_b200.cli fused --sample S --k K --hap1-asm .. --hap2-asm .. --hap1-reads f.. --hap2-reads f.. --outdir D
 
 The first four replace workflow/scripts/{kmerpos_annot3,rlen,diag_filter_v3,diag_filter_step2}
-(workflow/rules/tagONT.smk:36,73,92,110) one to one; `fused` replaces the rules from jellyfish_count
+(workflow/rules/tagONT.smk:36,73,92,110) one to one; the next six replace badsunks_AR.py,
+process-by-contig_lowmem_AR.py, get_gaps.py, `bedtools slop`, covprob.py and split_locs.py with the
+argv of their rules (tagONT.smk:150,189,230,249; the two `script:` rules take their snakemake.input /
+.output / .config values as options, and `covprob_script(snakemake)` / `split_locs_script(snakemake)`
+accept the snakemake object itself); `fused` replaces the rules from jellyfish_count
 to get_gaps and writes the same files under results/{sample}/.  Text parsing / formatting is host
 plumbing; all per-base and per-row work runs in libgavisunk_b200.so.  Errors exit non-zero with a
 message on stderr and never leave a partial output file behind.
@@ -114,6 +124,269 @@ def cmd_diag_filter_step2(argv):
     eng.set_rows(0, *cols)
     eng.filter_best(table)
     sys.stdout.write(_fmt_rows(eng.rows(1), rnames, cnames))
+
+
+
+# ------------------------------------------------------------------------------------------------
+# per-rule shims of the Python stages
+# ------------------------------------------------------------------------------------------------
+def _index_names(names: Sequence[str], known: Dict[str, int] = None):
+    idx = dict(known or {})
+    out = np.zeros(len(names), np.uint32)
+    for i, n in enumerate(names):
+        j = idx.get(n)
+        if j is None:
+            j = idx[n] = len(idx)
+        out[i] = j
+    return out, idx
+
+
+def _engine_with_rows(rows, contig_order: Sequence[str] = ()):
+    """kept-row engine from parsed sunkpos rows: reads = distinct names in sorted order (pandas groupby
+    order), each read's rows contiguous in file order."""
+    rnames = sorted({r[0] for r in rows})
+    ridx = {n: i for i, n in enumerate(rnames)}
+    rows = sorted(rows, key=lambda r: ridx[r[0]])  # stable: file order inside a read
+    cidx = {n: i for i, n in enumerate(contig_order)}
+    ccol, cidx = _index_names([r[2] for r in rows], cidx)
+    cnames = [None] * len(cidx)
+    for n, i in cidx.items():
+        cnames[i] = n
+    eng = Engine(20)
+    eng.contig_names = cnames
+    cols = (np.asarray([ridx[r[0]] for r in rows], np.uint32), np.asarray([r[1] for r in rows], np.uint32), ccol,
+            np.asarray([r[3] for r in rows], np.uint32), np.asarray([r[4] for r in rows], np.uint32))
+    return eng, rows, rnames, cnames, cols
+
+
+def bad_sunks_of_hap(sunkpos_p: str, fai_p: str, hap: int):
+    """badsunks_AR.py:20-52 (hap1) / :56-93 (hap2) -> set of 'contig:ID'"""
+    rows = gio.read_sunkpos(sunkpos_p)
+    fai = {n for n, _ in gio.read_fai(fai_p)}
+    eng, rows, rnames, cnames, cols = _engine_with_rows(rows)
+    if not any(c in fai for c in cnames):
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0 (mode of no correct-haplotype counts, badsunks_AR.py:43)")
+    eng.set_reads_meta(np.zeros(len(rnames), np.uint32), [0, len(rnames)], [hap])
+    eng.set_rows(1, *cols)
+    # contigs of this haplotype's .fai are "correct"; the others only get the upper limit (:48-51)
+    eng.set_contigs([hap if c in fai else 2 + hap for c in cnames])
+    eng.group_hist()
+    eng.bad_groups()
+    sys.stdout.write(f"mean coverage {eng.modes[hap]}\n")
+    g = eng.groups()
+    return {f"{cnames[g['contig'][i]]}:{g['group'][i]}" for i in eng.bad_list().tolist()}
+
+
+def cmd_badsunks(argv):
+    fai1, fai2, sp1, sp2, out_p = argv
+    bad = bad_sunks_of_hap(sp1, fai1, 0) | bad_sunks_of_hap(sp2, fai2, 1)
+    sys.stdout.write(f"{len(bad)}\n")
+    _atomic_write(out_p, "".join(b + "\n" for b in sorted(bad)))  # the reference writes set order (SURVEY Q18)
+
+
+def process_by_contig(locs_p, sunkpos_p, rlen_p, badsunks_p, out_tsv, out_bed):
+    """process-by-contig_lowmem_AR.py:30-260 for one breaks/{contig}_{hap}.sunkpos"""
+    rlen = {}
+    with gio.open_maybe_gz(rlen_p) as f:
+        for l in f.read().decode().splitlines():
+            p = l.split("\t")
+            if len(p) >= 2:
+                rlen.setdefault(p[0], int(p[1]))
+    open(locs_p).close()  # the reference reads it (:54-57) but none of its outputs depend on it
+    rows = gio.read_sunkpos(sunkpos_p)
+    if not rows:
+        raise ValueError("No columns to parse from file (empty sunkpos, process-by-contig_lowmem_AR.py:60)")
+    contig = rows[0][2]  # sunkposcat['chrom'].unique()[0] (:62)
+    with open(badsunks_p) as f:
+        badset = set(f.read().splitlines())
+    rows = list(dict.fromkeys(rows))  # drop_duplicates (:104) keeps the first of identical rows
+    eng, rows, rnames, cnames, cols = _engine_with_rows(rows)
+    eng.set_reads_meta(np.asarray([min(rlen.get(n, 0), 0xFFFFFFFF) for n in rnames], np.uint32))
+    eng.set_rows(1, *cols)
+    eng.set_contigs([0] * len(cnames))
+    bc, bg = [], []
+    cidx = {n: i for i, n in enumerate(cnames)}
+    for b in badset:
+        c, _, g = b.partition(":")  # ID2 = chrom + ":" + ID (:68)
+        if c in cidx and g.isdigit() and int(g) <= 0xFFFFFFFF:
+            bc.append(cidx[c])
+            bg.append(int(g))
+    eng.bad_set(bc, bg)
+    eng.validate(10000)  # the reference overwrites --minlen with 10000 (:106, SURVEY Q13)
+    if eng.n_pairs == 0:  # :92-94, :202-204: contig name only, no bed (the rule touches it)
+        _atomic_write(out_tsv, contig + "\n")
+        return None
+    pairs = eng.pairs()
+    _atomic_write(out_tsv, "".join(f"{g}\t{rnames[r]}\n" for g, r in zip(pairs["group"].tolist(), pairs["read"].tolist())))
+    eng.components_local()
+    iv = eng.intervals()
+    _atomic_write(out_bed, "".join(f"{contig}\t{s}\t{e}\n" for s, e in sorted(zip(iv["start"].tolist(), iv["end"].tolist()))))
+    return iv
+
+
+def cmd_process_by_contig(argv):
+    ap = argparse.ArgumentParser(prog="gavisunk_b200.cli process_by_contig")
+    for a in ("SUNKs", "sunkpos", "rlen", "badsunks", "outputfile", "outputbed"):
+        ap.add_argument(a)
+    ap.add_argument("--minlen", default=10000, type=int)
+    ap.add_argument("--opt_filt", action="store_true")
+    a = ap.parse_args(argv)
+    process_by_contig(a.SUNKs, a.sunkpos, a.rlen, a.badsunks, a.outputfile, a.outputbed)
+
+
+def cmd_get_gaps(argv):
+    """get_gaps.py: paths are string-concatenated, so indir / outdir need their trailing slash (:30,70)"""
+    fai1, fai2, sample, indir, outdir = argv
+    fais = [gio.read_fai(fai1), gio.read_fai(fai2)]
+    names, lens, hap_of = [], [], []
+    for hap in range(2):
+        for n, l in fais[hap]:
+            names.append(n)
+            lens.append(l)
+            hap_of.append(hap)
+    ic, is_, ie = [], [], []
+    for ci, n in enumerate(names):
+        bp = indir + n.replace("#", "_") + f"_hap{hap_of[ci] + 1}.bed"
+        if not os.path.exists(bp):
+            sys.stdout.write(f"No bed for {n}\n")
+            continue
+        with open(bp) as f:
+            for l in f:
+                p = l.rstrip("\n").split("\t")
+                if len(p) >= 3:
+                    ic.append(ci)
+                    is_.append(int(p[1]))
+                    ie.append(int(p[2]))
+    eng = Engine(20)
+    eng.contig_names = names
+    eng.set_intervals(ic, is_, ie, len(names))
+    gaps, nodata = eng.gaps(np.asarray(lens, np.uint32))
+    for hap in range(2):
+        g = [(names[c], s, e) for c, s, e in zip(gaps["contig"].tolist(), gaps["start"].tolist(), gaps["end"].tolist()) if hap_of[c] == hap]
+        nd = [(names[c], 0, lens[c]) for c in nodata.tolist() if hap_of[c] == hap]
+        sys.stdout.write(f"hap{hap + 1}\nbreaks:  {len(g)} {sum(e + 1 - s for _, s, e in g)}\nno data:  {len(nd)} {sum(l for _, _, l in nd)}\n")
+        _atomic_write(outdir + f"hap{hap + 1}.nodata.bed", "".join(f"{a}\t{s}\t{e}\n" for a, s, e in nd))
+        _atomic_write(outdir + f"hap{hap + 1}.gaps.bed", "".join(f"{a}\t{s}\t{e}\n" for a, s, e in g))
+
+
+def _read_bed3(path):
+    out = []
+    with open(path) as f:
+        for l in f:
+            p = l.rstrip("\n").split("\t")
+            if len(p) >= 3:
+                out.append((p[0], int(p[1]), int(p[2])))
+    return out
+
+
+def cmd_slop_gaps(argv):
+    """bedtools slop -i gaps -g fai -b 200000 (tagONT.smk:249)"""
+    bed_p, fai_p, out_p = argv
+    fai = gio.read_fai(fai_p)
+    cidx = {n: i for i, (n, _) in enumerate(fai)}
+    rows = _read_bed3(bed_p)
+    for c, _, _ in rows:
+        if c not in cidx:
+            raise KeyError(f"chromosome {c} is not in the genome file")
+    eng = Engine(20)
+    s, e = eng.slop([cidx[c] for c, _, _ in rows], [r[1] for r in rows], [r[2] for r in rows], [l for _, l in fai], 200000)
+    _atomic_write(out_p, "".join(f"{c}\t{a}\t{b}\n" for (c, _, _), a, b in zip(rows, s.tolist(), e.tolist())))
+
+
+def _natural_key(s: str):
+    import re
+    return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", s)]
+
+
+def covprob(bed_p, locs_p, rlen_p, fai_p, sunk_len: int, tsv_p):
+    """covprob.py:14-134"""
+    from .engine import covprob_bins, covprob_pn
+    genome_kbp = sum(l for _, l in gio.read_fai(fai_p)) / 1000
+    gaps = _read_bed3(bed_p)
+    contig, start, kmer, group = gio.read_loc(locs_p)
+    seen_k, seen_g, gc, gi = set(), set(), [], []
+    cidx: Dict[str, int] = {}
+    for c, km, g in zip(contig, kmer, group):  # drop_duplicates(kmer) then drop_duplicates(ID2) (:36-38)
+        if km in seen_k:
+            continue
+        seen_k.add(km)
+        if (c, g) in seen_g:
+            continue
+        seen_g.add((c, g))
+        gc.append(cidx.setdefault(c, len(cidx)))
+        gi.append(g)
+    lens = []
+    with gio.open_maybe_gz(rlen_p) as f:
+        for l in f.read().decode().splitlines():
+            p = l.split("\t")
+            if len(p) >= 2:
+                lens.append((p[0], int(p[1])))
+    kbp, cnt = covprob_bins(lens)
+    eng = Engine(int(sunk_len) if 1 <= int(sunk_len) <= 32 else 20)
+    table = eng.covprob_table(kbp, cnt, genome_kbp, covprob_pn(int(sunk_len)))
+    # breaks.df: pyranges groups the rows by chromosome (natural order of the names), file order inside
+    order = sorted(range(len(gaps)), key=lambda i: (_natural_key(gaps[i][0]), i))
+    g_sorted = [gaps[i] for i in order]
+    unknown = len(cidx)
+    mg, pr = eng.covprob_gaps(gc, gi, [cidx.get(c, unknown) for c, _, _ in g_sorted], [s for _, s, _ in g_sorted],
+                              [e for _, _, e in g_sorted], table)
+    out = ["index\tChromosome\tStart\tEnd\ttype\tmax_gap\tcovprob\n"]
+    for i, (c, s, e), m, p in zip(order, g_sorted, mg.tolist(), pr.tolist()):
+        out.append(f"{i}\t{c}\t{s}\t{e}\tgap\t{m}\t{p!r}\n")
+    _atomic_write(tsv_p, "".join(out))
+    return table
+
+
+def covprob_script(snakemake):
+    """drop-in body for `script: ../scripts/covprob.py` (tagONT.smk:211-231)"""
+    covprob(snakemake.input.bed, snakemake.input.locs, snakemake.input.rlen, snakemake.input.fai,
+            int(snakemake.config["SUNK_len"]), snakemake.output.tsv)
+
+
+def cmd_covprob(argv):
+    ap = argparse.ArgumentParser(prog="gavisunk_b200.cli covprob")
+    for a in ("bed", "locs", "rlen", "fai", "tsv"):
+        ap.add_argument("--" + a, required=True)
+    ap.add_argument("--sunk-len", type=int, required=True)
+    a = ap.parse_args(argv)
+    covprob(a.bed, a.locs, a.rlen, a.fai, a.sunk_len, a.tsv)
+
+
+def split_locs(ont_pos_p, kmer_loc_p, flag_p, hap: str):
+    """split_locs.py:5-22: byte-level partition by contig, no arithmetic (host only)"""
+    dirname = os.path.dirname(flag_p)
+    os.makedirs(dirname or ".", exist_ok=True)
+    by_c: Dict[str, List[str]] = defaultdict(list)
+    with gio.open_maybe_gz(ont_pos_p) as f:
+        for l in f.read().decode().splitlines():
+            p = l.split("\t")
+            if len(p) >= 5:
+                by_c[p[2]].append(l + "\n")
+    loc_c: Dict[str, List[str]] = defaultdict(list)
+    with open(kmer_loc_p) as f:
+        for l in f:
+            c = l.split("\t", 1)[0]
+            if c in by_c:
+                loc_c[c].append(l if l.endswith("\n") else l + "\n")
+    for c, lines in by_c.items():
+        _atomic_write(f"{dirname}/{c.replace('#', '_')}_{hap}.sunkpos", "".join(lines))
+    for c, lines in loc_c.items():
+        _atomic_write(f"{dirname}/{c.replace('#', '_')}_{hap}.loc", "".join(lines))
+
+
+def split_locs_script(snakemake):
+    split_locs(snakemake.input.ONT_pos, snakemake.input.kmer_loc, snakemake.output.flag, snakemake.wildcards.hap)
+
+
+def cmd_split_locs(argv):
+    ap = argparse.ArgumentParser(prog="gavisunk_b200.cli split_locs")
+    ap.add_argument("--ont-pos", required=True)
+    ap.add_argument("--kmer-loc", required=True)
+    ap.add_argument("--flag", required=True)
+    ap.add_argument("--hap", required=True)
+    a = ap.parse_args(argv)
+    split_locs(a.ont_pos, a.kmer_loc, a.flag, a.hap)
+    open(a.flag, "a").close()  # touch() of the checkpoint rule (tagONT.smk:158)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -243,7 +516,9 @@ def cmd_fused(argv):
 
 
 COMMANDS = {"kmerpos_annot3": (cmd_kmerpos_annot3, 4), "rlen": (cmd_rlen, 2), "diag_filter_v3": (cmd_diag_filter_v3, 2),
-            "diag_filter_step2": (cmd_diag_filter_step2, 2), "fused": (cmd_fused, None)}
+            "diag_filter_step2": (cmd_diag_filter_step2, 2), "badsunks_AR": (cmd_badsunks, 5),
+            "process_by_contig": (cmd_process_by_contig, None), "get_gaps": (cmd_get_gaps, 5), "slop_gaps": (cmd_slop_gaps, 3),
+            "covprob": (cmd_covprob, None), "split_locs": (cmd_split_locs, None), "fused": (cmd_fused, None)}
 
 
 def main(argv=None):

@@ -9,6 +9,7 @@
 // group index (hook larger root under smaller: the root is the component's first group).
 // Multi-GPU: every rank builds its forest; forests are merged by unioning g with peer_parent[g].
 #include "common.cuh"
+#include <algorithm>
 
 __device__ __forceinline__ u32 guf_find(u32* par, u32 x) {
   u32 p = par[x];
@@ -257,6 +258,33 @@ extern "C" int gvs_gaps_get(gvs_ctx* ctx, uint32_t* contig, uint32_t* start, uin
   return 0;
 }
 
+// intervals read from bed_files/*.bed instead of computed here (input of get_gaps.py:30): sorted by
+// (contig, start) on the way in, like pyranges does before merging
+extern "C" int gvs_intervals_set(gvs_ctx* ctx, const uint32_t* contig, const uint32_t* start, const uint32_t* end, uint64_t n,
+                                 uint32_t n_contigs) {
+  if (!ctx || (n && (!contig || !start || !end))) return GVS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<u64> order(n);
+  for (u64 i = 0; i < n; i++) {
+    if (contig[i] >= n_contigs) return gvs_fail(ctx, GVS_E_ARG, "gvs_intervals_set: contig id %u out of range", contig[i]);
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](u64 a, u64 b) {
+    return contig[a] != contig[b] ? contig[a] < contig[b] : start[a] < start[b];
+  });
+  std::vector<u32> c(n), s(n), e(n);
+  for (u64 i = 0; i < n; i++) { c[i] = contig[order[i]]; s[i] = start[order[i]]; e[i] = end[order[i]]; }
+  ctx->n_contigs = n_contigs;
+  CKR(to_dev(ctx, ctx->iv_contig, c.data(), n));
+  CKR(to_dev(ctx, ctx->iv_start, s.data(), n));
+  CKR(to_dev(ctx, ctx->iv_end, e.data(), n));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->n_iv = n;
+  ctx->iv_ready = true;
+  ctx->gaps_ready = false;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // covprob table (covprob.py:56-60,86-100), float64
 // ---------------------------------------------------------------------------------------------
@@ -294,5 +322,129 @@ extern "C" int gvs_covprob_table(gvs_ctx* ctx, const int64_t* kbp, const int64_t
     rc = gvs_fail(ctx, GVS_E_CUDA, "covprob D2H failed");
   cudaStreamSynchronize(ctx->stream);
   gvs_release(dk); gvs_release(dc); gvs_release(dt);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// covprob per-gap lookup (covprob.py:35-40,109-131) and slop_gaps (tagONT.smk:249)
+// ---------------------------------------------------------------------------------------------
+// groups = first row of every (contig, group) of kmer.loc in FILE order, which is (contig, start) order
+// (defineSUNKs.smk:101-126 sorts it).  dist[i] = max(id[i] - id[i-1], 0) with dist[0] = id[0]; the diff
+// runs across contig boundaries exactly like pandas' Series.diff on the concatenated file (:39-40).
+__global__ void __launch_bounds__(128) k_covprob_gaps(const u32* __restrict__ g_contig, const u32* __restrict__ g_id, u64 ng,
+                                                      const u32* __restrict__ gap_contig, const i64* __restrict__ gap_start,
+                                                      const i64* __restrict__ gap_end, u64 n_gaps,
+                                                      const double* __restrict__ table, i64* max_gap, double* prob, u32* err) {
+  u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_gaps) return;
+  const u32 c = gap_contig[t];
+  const i64 lo_id = gap_start[t] - 2, hi_id = gap_end[t] + 2;  // ID > xmin-2 and ID < xmax+2 (:115)
+  // first group with (contig, id) > (c, lo_id)
+  u64 lo = 0, hi = ng;
+  while (lo < hi) {
+    u64 mid = (lo + hi) >> 1;
+    u32 mc = g_contig[mid];
+    bool le = mc < c || (mc == c && (i64)g_id[mid] <= lo_id);
+    if (le) lo = mid + 1; else hi = mid;
+  }
+  i64 best = -1;
+  for (u64 i = lo; i < ng && g_contig[i] == c && (i64)g_id[i] < hi_id; i++) {
+    i64 d = i == 0 ? (i64)g_id[0] : (i64)g_id[i] - (i64)g_id[i - 1];
+    if (d < 0) d = 0;
+    if (d > best) best = d;
+  }
+  max_gap[t] = best;
+  if (best < 0) {  // no group in range: the reference dies on int(nan)
+    atomicOr(err, 1u);
+    prob[t] = 0.0;
+    return;
+  }
+  i64 kb = best / 1000;  // int(x/1000) (:130)
+  if (kb >= 3500) {      // KeyError in covprobsdict
+    atomicOr(err, 2u);
+    prob[t] = 0.0;
+    return;
+  }
+  prob[t] = table[kb];
+}
+__global__ void __launch_bounds__(256) k_groups_sorted(const u32* __restrict__ g_contig, const u32* __restrict__ g_id, u64 ng, u32* err) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 >= ng) return;
+  u32 a = g_contig[i], b = g_contig[i + 1];
+  if (a > b || (a == b && g_id[i] >= g_id[i + 1])) atomicOr(err, 4u);
+}
+
+extern "C" int gvs_covprob_gaps(gvs_ctx* ctx, const uint32_t* grp_contig, const uint32_t* grp_id, uint64_t n_groups,
+                                const uint32_t* gap_contig, const int64_t* gap_start, const int64_t* gap_end, uint64_t n_gaps,
+                                const double* table3500, int64_t* max_gap, double* covprob) {
+  if (!ctx || !table3500 || (n_groups && (!grp_contig || !grp_id)) || (n_gaps && (!gap_contig || !gap_start || !gap_end || !max_gap || !covprob)))
+    return GVS_E_ARG;
+  if (n_gaps == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  DevBuf gc, gi, pc, ps, pe, tb, mg, pr;
+  u32* err = (u32*)(ctx->counters.as<u64>() + 24);
+  int rc = to_dev(ctx, gc, grp_contig, n_groups);
+  if (!rc) rc = to_dev(ctx, gi, grp_id, n_groups);
+  if (!rc) rc = to_dev(ctx, pc, gap_contig, n_gaps);
+  if (!rc) rc = to_dev(ctx, ps, gap_start, n_gaps);
+  if (!rc) rc = to_dev(ctx, pe, gap_end, n_gaps);
+  if (!rc) rc = to_dev(ctx, tb, table3500, 3500);
+  if (!rc) rc = gvs_reserve(ctx, mg, n_gaps * 8);
+  if (!rc) rc = gvs_reserve(ctx, pr, n_gaps * 8);
+  u32 herr = 0;
+  if (!rc) {
+    cudaMemsetAsync(err, 0, 4, ctx->stream);
+    if (n_groups > 1) {
+      k_groups_sorted<<<(unsigned)cdiv(n_groups, 256), 256, 0, ctx->stream>>>(gc.as<u32>(), gi.as<u32>(), n_groups, err);
+      ctx->launches++;
+    }
+    k_covprob_gaps<<<(unsigned)cdiv(n_gaps, 128), 128, 0, ctx->stream>>>(gc.as<u32>(), gi.as<u32>(), n_groups, pc.as<u32>(), ps.as<i64>(),
+                                                                         pe.as<i64>(), n_gaps, tb.as<double>(), mg.as<i64>(), pr.as<double>(), err);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = gvs_fail(ctx, GVS_E_CUDA, "k_covprob_gaps launch failed");
+  }
+  if (!rc) rc = read_dev(ctx, err, &herr);
+  if (!rc && cudaMemcpyAsync(max_gap, mg.p, n_gaps * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = gvs_fail(ctx, GVS_E_CUDA, "D2H failed");
+  if (!rc && cudaMemcpyAsync(covprob, pr.p, n_gaps * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = gvs_fail(ctx, GVS_E_CUDA, "D2H failed");
+  cudaStreamSynchronize(ctx->stream);
+  gvs_release(gc); gvs_release(gi); gvs_release(pc); gvs_release(ps); gvs_release(pe); gvs_release(tb); gvs_release(mg); gvs_release(pr);
+  if (rc) return rc;
+  if (herr & 4u) return gvs_fail(ctx, GVS_E_ARG, "gvs_covprob_gaps: group rows are not in (contig, start) order (kmer.loc must be sorted)");
+  if (herr & 1u) return gvs_fail(ctx, GVS_E_KEYERROR, "ValueError: a gap has no SUNK group within [start-2, end+2] (covprob.py:118)");
+  if (herr & 2u) return gvs_fail(ctx, GVS_E_KEYERROR, "KeyError: max_gap >= 3500 kbp has no covprob entry (covprob.py:130)");
+  return 0;
+}
+
+// bedtools slop -b B clipped to [0, contig length] (tagONT.smk:249)
+__global__ void __launch_bounds__(256) k_slop(const u32* __restrict__ contig, const u32* __restrict__ contig_len, u64 n, i64 b, i64* start,
+                                              i64* end) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  i64 L = contig_len[contig[i]];
+  i64 s = start[i] - b, e = end[i] + b;
+  start[i] = s < 0 ? 0 : (s > L ? L : s);
+  end[i] = e > L ? L : (e < 0 ? 0 : e);
+}
+extern "C" int gvs_slop(gvs_ctx* ctx, const uint32_t* contig, int64_t* start, int64_t* end, uint64_t n, const uint32_t* contig_len,
+                        uint32_t n_contigs, int64_t b) {
+  if (!ctx || (n && (!contig || !start || !end || !contig_len))) return GVS_E_ARG;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  for (u64 i = 0; i < n; i++)
+    if (contig[i] >= n_contigs) return gvs_fail(ctx, GVS_E_ARG, "gvs_slop: contig id %u out of range", contig[i]);
+  DevBuf dc, dl, ds, de;
+  int rc = to_dev(ctx, dc, contig, n);
+  if (!rc) rc = to_dev(ctx, dl, contig_len, (size_t)n_contigs);
+  if (!rc) rc = to_dev(ctx, ds, start, n);
+  if (!rc) rc = to_dev(ctx, de, end, n);
+  if (!rc) {
+    k_slop<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(dc.as<u32>(), dl.as<u32>(), n, b, ds.as<i64>(), de.as<i64>());
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = gvs_fail(ctx, GVS_E_CUDA, "k_slop launch failed");
+  }
+  if (!rc && cudaMemcpyAsync(start, ds.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = gvs_fail(ctx, GVS_E_CUDA, "D2H failed");
+  if (!rc && cudaMemcpyAsync(end, de.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = gvs_fail(ctx, GVS_E_CUDA, "D2H failed");
+  cudaStreamSynchronize(ctx->stream);
+  gvs_release(dc); gvs_release(dl); gvs_release(ds); gvs_release(de);
   return rc;
 }

@@ -344,6 +344,26 @@ class Engine:
         self._ck(self.lib.gvs_bad_get(self.ctx, _ptr(out)))
         return out
 
+    def bad_set(self, contig, group) -> int:
+        """bad groups from a bad_sunks.txt (process-by-contig_lowmem_AR.py:66-72): (contig id, group) pairs."""
+        c = _c(contig, np.uint32)
+        g = _c(group, np.uint32)
+        n = C.c_uint64()
+        self._ck(self.lib.gvs_bad_set(self.ctx, _ptr(c), _ptr(g), len(c), C.byref(n)))
+        self.n_bad = int(n.value)
+        return self.n_bad
+
+    def groups(self, with_hist: bool = False) -> Dict[str, np.ndarray]:
+        """group table behind every group index: (contig, group start[, row count of group_hist])"""
+        n = C.c_uint64()
+        self._ck(self.lib.gvs_groups_count(self.ctx, C.byref(n)))
+        n = int(n.value)
+        out = dict(contig=np.zeros(n, np.uint32), group=np.zeros(n, np.uint32))
+        if with_hist:
+            out["count"] = np.zeros(n, np.int32)
+        self._ck(self.lib.gvs_groups_get(self.ctx, _ptr(out["contig"]), _ptr(out["group"]), _ptr(out.get("count"))))
+        return out
+
     def validate(self, min_read_len: int = 10000) -> int:
         """process-by-contig_lowmem_AR.py:50-207 (per-read part)."""
         n = C.c_uint64()
@@ -375,6 +395,11 @@ class Engine:
         self._ck(self.lib.gvs_intervals_get(self.ctx, _ptr(out["contig"]), _ptr(out["start"]), _ptr(out["end"])))
         return out
 
+    def set_intervals(self, contig, start, end, n_contigs: int):
+        """rows of bed_files/*.bed as the input of gaps() (get_gaps.py:30)."""
+        c, s, e = _c(contig, np.uint32), _c(start, np.uint32), _c(end, np.uint32)
+        self._ck(self.lib.gvs_intervals_set(self.ctx, _ptr(c), _ptr(s), _ptr(e), len(c), int(n_contigs)))
+
     def gaps(self, contig_len: Sequence[int]):
         """get_gaps.py:17-123."""
         cl = _c(contig_len, np.uint32)
@@ -393,6 +418,26 @@ class Engine:
         self._ck(self.lib.gvs_covprob_table(self.ctx, _ptr(kbp), _ptr(cnt), len(kbp), float(genome_kbp), float(pn),
                                             _ptr(out)))
         return out
+
+
+    def covprob_gaps(self, grp_contig, grp_id, gap_contig, gap_start, gap_end, table):
+        """covprob.py:109-131: per gap (max_gap, covprob)."""
+        gc, gi = _c(grp_contig, np.uint32), _c(grp_id, np.uint32)
+        pc, ps, pe = _c(gap_contig, np.uint32), _c(gap_start, np.int64), _c(gap_end, np.int64)
+        tb = _c(table, np.float64)
+        assert len(tb) == 3500
+        mg, pr = np.zeros(len(pc), np.int64), np.zeros(len(pc), np.float64)
+        self._ck(self.lib.gvs_covprob_gaps(self.ctx, _ptr(gc), _ptr(gi), len(gc), _ptr(pc), _ptr(ps), _ptr(pe), len(pc),
+                                           _ptr(tb), _ptr(mg), _ptr(pr)))
+        return mg, pr
+
+    def slop(self, contig, start, end, contig_len, b: int = 200000):
+        """slop_gaps (workflow/rules/tagONT.smk:249)."""
+        c = _c(contig, np.uint32)
+        s, e = np.array(start, dtype=np.int64), np.array(end, dtype=np.int64)
+        cl = _c(contig_len, np.uint32)
+        self._ck(self.lib.gvs_slop(self.ctx, _ptr(c), _ptr(s), _ptr(e), len(c), _ptr(cl), len(cl), int(b)))
+        return s, e
 
 
 # ----------------------------------------------------------------------------------------------

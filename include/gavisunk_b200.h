@@ -211,6 +211,11 @@ int gvs_components_merge(gvs_ctx* ctx, const uint32_t* peer_parent_dev);
 int gvs_intervals(gvs_ctx* ctx, uint64_t* n_intervals);
 int gvs_intervals_get(gvs_ctx* ctx, uint32_t* contig, uint32_t* start, uint32_t* end);
 
+/* Intervals parsed from bed_files/{contig}_{hap}.bed instead of produced by gvs_intervals (the input
+ * of get_gaps.py:30); any order, host memory. */
+int gvs_intervals_set(gvs_ctx* ctx, const uint32_t* contig, const uint32_t* start, const uint32_t* end,
+                      uint64_t n, uint32_t n_contigs);
+
 /* get_gaps.py:17-123: per contig merge intervals, gaps (prev_end, next_start-1); contigs without
  * intervals are "nodata".  contig_len[n_contigs]. */
 int gvs_gaps(gvs_ctx* ctx, const uint32_t* contig_len, uint64_t* n_gaps, uint64_t* n_nodata);
@@ -223,6 +228,20 @@ int gvs_gaps_get(gvs_ctx* ctx, uint32_t* contig, uint32_t* start, uint32_t* end,
  * root solve), genome_kbp = sum(fai.len)/1000. */
 int gvs_covprob_table(gvs_ctx* ctx, const int64_t* kbp, const int64_t* cnt, uint32_t n_bins,
                       double genome_kbp, double pn, double* table3500);
+
+/* covprob.py:35-40,109-131: per gap the largest inter-group distance `dist` among the SUNK groups with
+ * chrom == contig and start-2 < ID < end+2, and covprob = table[int(max_gap/1000)].  grp_contig/grp_id =
+ * the first row of every (contig, group) of kmer.loc in file order, which must be (contig, start)
+ * order as defineSUNKs.smk:101-126 writes it (dist is the file-order diff, across contig boundaries,
+ * clamped at 0, first row = its own ID).  Errors mirror the reference: GVS_E_KEYERROR when a gap has
+ * no group in range or max_gap >= 3500 kbp.  All pointers are host memory. */
+int gvs_covprob_gaps(gvs_ctx* ctx, const uint32_t* grp_contig, const uint32_t* grp_id, uint64_t n_groups,
+                     const uint32_t* gap_contig, const int64_t* gap_start, const int64_t* gap_end,
+                     uint64_t n_gaps, const double* table3500, int64_t* max_gap, double* covprob);
+/* slop_gaps (workflow/rules/tagONT.smk:249, `bedtools slop -b 200000`): start/end are widened by b in
+ * place and clipped to [0, contig_len[contig]]. */
+int gvs_slop(gvs_ctx* ctx, const uint32_t* contig, int64_t* start, int64_t* end, uint64_t n,
+             const uint32_t* contig_len, uint32_t n_contigs, int64_t b);
 
 /* ------------------------------------------------------------------------------------------ */
 /* synthetic workloads (bench.py / tests only)                                   */

@@ -98,9 +98,10 @@ def _oracle_pipeline(contigs_h, reads_h, k):
     return out
 
 
-@pytest.mark.gpu
-def test_fused_rule_files(tmp_path):
-    import torch
+@pytest.fixture(scope="module")
+def fused_case(tmp_path_factory):
+    """one small diploid sample run through `cli fused` + the oracle's composition of every stage"""
+    tmp_path = tmp_path_factory.mktemp("fused")
     from gavisunk_b200.engine import Engine
     from gavisunk_b200 import workload as W
     k = 20
@@ -122,16 +123,25 @@ def test_fused_rule_files(tmp_path):
         fp = tmp_path / f"hap{hap + 1}_{ci}.fa"
         fp.write_bytes(b"".join(b">" + n.encode() + b"\n" + s + b"\n" for n, s in chunk))
         files_h[hap].append(str(fp))
-    asm_files = []
+    asm_files, fai_files = [], []
     for hap in range(2):
         fp = tmp_path / f"hap{hap + 1}.fa"
         fp.write_bytes(b"".join(b">" + n.encode() + b"\n" + s + b"\n" for n, s in contigs_h[hap]))
         asm_files.append(str(fp))
+        fai = tmp_path / f"hap{hap + 1}.fa.fai"
+        fai.write_text("".join(f"{n}\t{len(s)}\t0\t60\t61\n" for n, s in contigs_h[hap]))
+        fai_files.append(str(fai))
     outdir = tmp_path / "results"
     rc = cli.main(["fused", "--k", str(k), "--hap1-asm", asm_files[0], "--hap2-asm", asm_files[1], "--hap1-reads", *files_h[0],
                    "--hap2-reads", *files_h[1], "--outdir", str(outdir)])
     assert rc == 0
     exp = _oracle_pipeline(contigs_h, reads_h, k)
+    return dict(outdir=str(outdir), exp=exp, contigs_h=contigs_h, fai=fai_files, k=k, tmp=tmp_path)
+
+
+@pytest.mark.gpu
+def test_fused_rule_files(fused_case):
+    outdir, exp = fused_case["outdir"], fused_case["exp"]
     rd = lambda *p: open(os.path.join(outdir, *p)).read()
     assert rd("mrsfast", "kmer.loc") == exp["kmer.loc"]
     assert sorted(rd("db", "jellyfish.db").split()) == sorted(l.split("\t")[2] for l in exp["kmer.loc"].splitlines())
@@ -149,3 +159,82 @@ def test_fused_rule_files(tmp_path):
             assert rd("inter_outs", f"{ctg}_hap{hap}.tsv") == val, ctg
             n_inter += val.count("\n")
     assert n_inter > 100
+
+
+@pytest.mark.gpu
+def test_rule_shims_chain(fused_case):
+    """the per-rule shims (badsunks_AR, split_locs, process_by_contig, get_gaps, slop_gaps, covprob) chained
+    through files exactly as workflow/rules/tagONT.smk:132-250 chains the reference scripts"""
+    outdir, exp, fai, k = fused_case["outdir"], fused_case["exp"], fused_case["fai"], fused_case["k"]
+    work = fused_case["tmp"] / "rules"
+    for sub in ("sunkpos", "breaks", "inter_outs", "bed_files", "final_out"):
+        os.makedirs(work / sub, exist_ok=True)
+    src = lambda *p: os.path.join(outdir, *p)
+    # rule bad_sunks
+    assert cli.main(["badsunks_AR", fai[0], fai[1], src("sunkpos", "hap1.sunkpos"), src("sunkpos", "hap2.sunkpos"),
+                     str(work / "sunkpos" / "bad_sunks.txt")]) == 0
+    assert set((work / "sunkpos" / "bad_sunks.txt").read_text().split()) == exp["bad"]
+    # checkpoint split_sunkpos + rule process_by_contig
+    rlen_all = work / "sunkpos" / "all.rlen"
+    n_bed = 0
+    for hap in (1, 2):
+        flag = work / "breaks" / f"hap{hap}_splits_pos.done"
+        assert cli.main(["split_locs", "--ont-pos", src("sunkpos", f"hap{hap}.sunkpos"), "--kmer-loc", src("mrsfast", "kmer.loc"),
+                         "--flag", str(flag), "--hap", f"hap{hap}"]) == 0
+        assert flag.exists()
+        for fn in sorted(os.listdir(work / "breaks")):
+            if not fn.endswith(f"_hap{hap}.sunkpos"):
+                continue
+            ctg = fn[:-len(f"_hap{hap}.sunkpos")]
+            assert open(work / "breaks" / fn).read() == open(src("breaks", fn)).read()
+            assert open(work / "breaks" / f"{ctg}_hap{hap}.loc").read() == open(src("breaks", f"{ctg}_hap{hap}.loc")).read()
+            tsv, bed = work / "inter_outs" / f"{ctg}_hap{hap}.tsv", work / "bed_files" / f"{ctg}_hap{hap}.bed"
+            assert cli.main(["process_by_contig", str(work / "breaks" / f"{ctg}_hap{hap}.loc"), str(work / "breaks" / fn),
+                             src("sunkpos", f"hap{hap}.rlen"), str(work / "sunkpos" / "bad_sunks.txt"), str(tsv), str(bed)]) == 0
+            assert tsv.read_text() == exp[f"inter:{ctg}"], ctg
+            if bed.exists():
+                n_bed += 1
+                want = sorted(l for l in exp[f"hap{hap}.valid.bed"] if l.split("\t")[0] == ctg)
+                assert sorted(bed.read_text().splitlines(True)) == want
+                assert bed.read_text() == open(src("bed_files", f"{ctg}_hap{hap}.bed")).read()
+            else:
+                bed.write_text("")  # `touch {output.bed}` (tagONT.smk:190)
+    assert n_bed >= 2
+    # rule get_gaps (paths are concatenated: trailing slashes) + slop_gaps
+    assert cli.main(["get_gaps", fai[0], fai[1], "sample", str(work / "bed_files") + "/", str(work / "final_out") + "/"]) == 0
+    for hap in (1, 2):
+        for f in ("gaps.bed", "nodata.bed"):
+            assert (work / "final_out" / f"hap{hap}.{f}").read_text() == exp[f"hap{hap}.{f}"], f
+        assert cli.main(["slop_gaps", str(work / "final_out" / f"hap{hap}.gaps.bed"), fai[hap - 1],
+                         str(work / "final_out" / f"hap{hap}.gaps.slop.bed")]) == 0
+        assert (work / "final_out" / f"hap{hap}.gaps.slop.bed").read_text() == exp[f"hap{hap}.gaps.slop.bed"]
+    # rule cov_prob (covprob.py): table + per-gap lookup against the oracle, 1e-6 relative
+    n_gap_rows = 0
+    for hap in (1, 2):
+        gaps_p = work / "final_out" / f"hap{hap}.gaps.bed"
+        tsv = work / "final_out" / f"hap{hap}.gaps.covprob.tsv"
+        gaps = [(l.split("\t")[0], int(l.split("\t")[1]), int(l.split("\t")[2])) for l in gaps_p.read_text().splitlines()]
+        rc = cli.main(["covprob", "--bed", str(gaps_p), "--locs", src("mrsfast", "kmer.loc"), "--rlen", src("sunkpos", f"hap{hap}.rlen"),
+                       "--fai", fai[hap - 1], "--sunk-len", str(k), "--tsv", str(tsv)])
+        contig, start, kmer, group = gio.read_loc(src("mrsfast", "kmer.loc"))
+        loc_rows = list(zip(contig, start, kmer, group))
+        rl = [(l.split("\t")[0], int(l.split("\t")[1])) for l in open(src("sunkpos", f"hap{hap}.rlen")).read().splitlines()]
+        table = O.covprob_table(rl, sum(l for _, l in gio.read_fai(fai[hap - 1])) / 1000, k)
+        try:
+            want = O.covprob_gaps(gaps, loc_rows, table)
+        except ValueError:
+            assert rc == 1  # a gap without a SUNK group in range kills the reference as well
+            continue
+        assert rc == 0
+        lines = tsv.read_text().splitlines()
+        assert lines[0] == "index\tChromosome\tStart\tEnd\ttype\tmax_gap\tcovprob"
+        got = {}
+        for l in lines[1:]:
+            i, c, s, e, t, mg, p = l.split("\t")
+            assert t == "gap"
+            got[int(i)] = (c, int(s), int(e), int(mg), float(p))
+        assert len(got) == len(want)
+        for i, (c, s, e, mg, p) in enumerate(want):
+            assert got[i][:4] == (c, s, e, mg)
+            assert got[i][4] == pytest.approx(p, rel=1e-6, abs=1e-15)  # tolerance of BASELINE.json's north_star
+            n_gap_rows += 1
