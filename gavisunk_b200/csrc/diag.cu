@@ -107,38 +107,120 @@ __global__ void __launch_bounds__(256) k_cand_gather(const u32* __restrict__ can
   }
 }
 
-// one thread group (NT threads) per candidate; NT = 32 (a warp, 4 per block) or 1024 (a block)
-template <int NT>
-__global__ void __launch_bounds__(NT == 32 ? 128 : NT) k_cand_vote(const u32* __restrict__ cand_row,
-                                                                    const u32* __restrict__ cand_voff, u32 n_cand,
-                                                                    const u32* __restrict__ row_cnt,
-                                                                    const u32* __restrict__ v_pos,
-                                                                    const u32* __restrict__ v_start,
-                                                                    const u32* __restrict__ v_group, u32 small_max,
-                                                                    u32* cand_good, u8* cand_dir) {
-  constexpr int GROUPS = NT == 32 ? 4 : 1;
-  __shared__ i64 s_alo[GROUPS], s_ahi[GROUPS];
-  __shared__ u32 s_good[GROUPS];
-  const int grp = NT == 32 ? (threadIdx.x >> 5) : 0;
-  const int tid = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
-  u32 ci = NT == 32 ? blockIdx.x * GROUPS + grp : blockIdx.x;
-  bool active = ci < n_cand;
-  u32 cnt = 0, o = 0;
-  if (active) {
-    cnt = row_cnt[cand_row[ci]];
-    o = cand_voff[ci];
-    if (NT == 32 ? cnt > small_max : cnt <= small_max) active = false;
+// warp per candidate (<= VOTE_WARP_MAX rows): the diagonals of both orientations are staged in shared
+// memory once, ranks / medians / band membership / distinct groups are computed for both in one sweep
+#define VOTE_WARP_MAX 256
+#define VOTE_WARPS 4
+__global__ void __launch_bounds__(VOTE_WARPS * 32) k_cand_vote_warp(const u32* __restrict__ cand_row, const u32* __restrict__ cand_voff,
+                                                                    u32 n_cand, const u32* __restrict__ row_cnt,
+                                                                    const u32* __restrict__ v_pos, const u32* __restrict__ v_start,
+                                                                    const u32* __restrict__ v_group, u32* cand_good, u8* cand_dir,
+                                                                    u32* big_list, u32* n_big) {
+  __shared__ i64 s_n0[VOTE_WARPS][VOTE_WARP_MAX], s_n1[VOTE_WARPS][VOTE_WARP_MAX];
+  __shared__ u32 s_g[VOTE_WARPS][VOTE_WARP_MAX];
+  __shared__ u8 s_f[VOTE_WARPS][VOTE_WARP_MAX];
+  __shared__ i64 s_med[VOTE_WARPS][4];
+  const int grp = threadIdx.x >> 5, tid = threadIdx.x & 31;
+  const u32 ci = blockIdx.x * VOTE_WARPS + grp;
+  if (ci >= n_cand) return;
+  const u32 cnt = row_cnt[cand_row[ci]];
+  if (cnt > VOTE_WARP_MAX) {  // k_cand_vote<1024> takes it
+    if (tid == 0) big_list[atomicAdd(n_big, 1u)] = ci;
+    return;
   }
-  if (NT != 32 && !active) return;  // whole block
-  auto gsync = [&]() {
-    if (NT == 32) __syncwarp(); else __syncthreads();
-  };
-  u32 good2[2] = {0, 0};
-  for (int orient = 0; orient < 2; orient++) {  // 0: reverse (pos + start), 1: forward (start - pos)
-    if (tid == 0) { s_alo[grp] = 0; s_ahi[grp] = 0; s_good[grp] = 0; }
-    gsync();
-    if (active) {
-      u32 lo = (cnt - 1) >> 1;
+  const u32 o = cand_voff[ci];
+  i64 *n0 = s_n0[grp], *n1 = s_n1[grp];
+  u32* sg = s_g[grp];
+  u8* sf = s_f[grp];
+  for (u32 i = tid; i < cnt; i += 32) {
+    i64 st = v_start[o + i], ps = v_pos[o + i];
+    n0[i] = st + ps;  // reverse strand: pos + start is constant along the diagonal (nim:84-86)
+    n1[i] = st - ps;  // forward strand (nim:111-113)
+    sg[i] = v_group[o + i];
+  }
+  if (tid < 4) s_med[grp][tid] = 0;
+  __syncwarp();
+  const u32 lo = (cnt - 1) >> 1;
+  for (u32 i = tid; i < cnt; i += 32) {
+    const i64 a0 = n0[i], a1 = n1[i];
+    u32 r0 = 0, r1 = 0;
+    for (u32 j = 0; j < cnt; j++) {
+      const i64 b0 = n0[j], b1 = n1[j];
+      const bool before = j < i;
+      r0 += (b0 < a0) || (b0 == a0 && before);
+      r1 += (b1 < a1) || (b1 == a1 && before);
+    }
+    if (r0 == lo) s_med[grp][0] = a0;
+    if (r0 == lo + 1) s_med[grp][1] = a0;
+    if (r1 == lo) s_med[grp][2] = a1;
+    if (r1 == lo + 1) s_med[grp][3] = a1;
+  }
+  __syncwarp();
+  i64 med[2];
+#pragma unroll
+  for (int orient = 0; orient < 2; orient++) {
+    // arraymancer percentile(n, 50): linear interpolation in float64, then int() truncation toward
+    // zero (diag_filter_v3.nim:86,113; Q8)
+    i64 alo = s_med[grp][2 * orient], m = alo;
+    if (!(cnt & 1)) {
+      i64 d = s_med[grp][2 * orient + 1] - alo;  // >= 0
+      m = alo + (d >> 1);
+      if ((d & 1) && m < 0) m += 1;  // x.5 below zero truncates up
+    }
+    med[orient] = m;
+  }
+  for (u32 i = tid; i < cnt; i += 32) {
+    i64 d0 = n0[i] - med[0], d1 = n1[i] - med[1];
+    if (d0 < 0) d0 = -d0;
+    if (d1 < 0) d1 = -d1;
+    sf[i] = (u8)((d0 < BANDWIDTH ? 1 : 0) | (d1 < BANDWIDTH ? 2 : 0));
+  }
+  __syncwarp();
+  u32 good0 = 0, good1 = 0;
+  for (u32 i = tid; i < cnt; i += 32) {
+    const u32 f = sf[i];
+    if (!f) continue;
+    const u32 gi = sg[i];
+    u32 seen = 0;  // orientations in which an earlier in-band row already carries this group
+    for (u32 j = 0; j < i; j++)
+      if (sg[j] == gi) seen |= sf[j];
+    good0 += (f & ~seen) & 1u;
+    good1 += ((f & ~seen) >> 1) & 1u;
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    good0 += __shfl_xor_sync(0xFFFFFFFFu, good0, d);
+    good1 += __shfl_xor_sync(0xFFFFFFFFu, good1, d);
+  }
+  if (tid == 0) {
+    // reverse is tried first; forward replaces it only on a strictly larger count (nim:98-138)
+    const bool fwd = good1 > good0;
+    cand_good[ci] = fwd ? good1 : good0;
+    cand_dir[ci] = fwd ? 1 : 0;
+  }
+}
+
+// one thread group (NT threads) per candidate; NT = 32 (a warp, 4 per block) or 1024 (a block)
+// one block per LARGE candidate (> VOTE_WARP_MAX rows), taken from the list the warp kernel left behind
+template <int NT>
+__global__ void __launch_bounds__(NT) k_cand_vote(const u32* __restrict__ cand_row, const u32* __restrict__ cand_voff,
+                                                  const u32* __restrict__ big_list, const u32* __restrict__ n_big,
+                                                  const u32* __restrict__ row_cnt, const u32* __restrict__ v_pos,
+                                                  const u32* __restrict__ v_start, const u32* __restrict__ v_group,
+                                                  u32* cand_good, u8* cand_dir) {
+  __shared__ i64 s_alo, s_ahi;
+  __shared__ u32 s_good;
+  const int tid = threadIdx.x;
+  const u32 nbig = *n_big;
+  for (u32 q = blockIdx.x; q < nbig; q += gridDim.x) {
+    const u32 ci = big_list[q];
+    const u32 cnt = row_cnt[cand_row[ci]];
+    const u32 o = cand_voff[ci];
+    u32 good2[2] = {0, 0};
+    for (int orient = 0; orient < 2; orient++) {  // 0: reverse (pos + start), 1: forward (start - pos)
+      if (tid == 0) { s_alo = 0; s_ahi = 0; s_good = 0; }
+      __syncthreads();
+      const u32 lo = (cnt - 1) >> 1;
       for (u32 i = tid; i < cnt; i += NT) {
         i64 ni = orient == 0 ? (i64)v_start[o + i] + (i64)v_pos[o + i] : (i64)v_start[o + i] - (i64)v_pos[o + i];
         u32 rank = 0;
@@ -146,17 +228,15 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) k_cand_vote(const u32* __
           i64 nj = orient == 0 ? (i64)v_start[o + j] + (i64)v_pos[o + j] : (i64)v_start[o + j] - (i64)v_pos[o + j];
           rank += (nj < ni) || (nj == ni && j < i);
         }
-        if (rank == lo) s_alo[grp] = ni;
-        if (rank == lo + 1) s_ahi[grp] = ni;
+        if (rank == lo) s_alo = ni;
+        if (rank == lo + 1) s_ahi = ni;
       }
-    }
-    gsync();
-    if (active) {
+      __syncthreads();
       // arraymancer percentile(n, 50): linear interpolation in float64, then int() truncation
       // toward zero (diag_filter_v3.nim:86,113; Q8)
-      i64 alo = s_alo[grp], med = alo;
+      i64 alo = s_alo, med = alo;
       if (!(cnt & 1)) {
-        i64 d = s_ahi[grp] - alo;  // >= 0
+        i64 d = s_ahi - alo;  // >= 0
         med = alo + (d >> 1);
         if ((d & 1) && med < 0) med += 1;  // x.5 below zero truncates up
       }
@@ -174,18 +254,18 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) k_cand_vote(const u32* __
           if (dj < 0) dj = -dj;
           dup = dj < BANDWIDTH;
         }
-        if (!dup) atomicAdd(&s_good[grp], 1u);
+        if (!dup) atomicAdd(&s_good, 1u);
       }
+      __syncthreads();
+      good2[orient] = s_good;
+      __syncthreads();
     }
-    gsync();
-    good2[orient] = s_good[grp];
-    gsync();
-  }
-  if (active && tid == 0) {
-    // reverse is tried first; forward replaces it only on a strictly larger count (nim:98-138)
-    bool fwd = good2[1] > good2[0];
-    cand_good[ci] = fwd ? good2[1] : good2[0];
-    cand_dir[ci] = fwd ? 1 : 0;
+    if (tid == 0) {
+      // reverse is tried first; forward replaces it only on a strictly larger count (nim:98-138)
+      bool fwd = good2[1] > good2[0];
+      cand_good[ci] = fwd ? good2[1] : good2[0];
+      cand_dir[ci] = fwd ? 1 : 0;
+    }
   }
 }
 
@@ -388,14 +468,16 @@ static int diag_impl(gvs_ctx* ctx, u64* n_best_out, u64* n_kept_out) {
   CKR(read_dev(ctx, tot, &packed));
   u32 n_cand = (u32)(packed >> 32);
   CK(cudaMemcpyAsync(D.cidx + n, &n_cand, 4, cudaMemcpyHostToDevice, ctx->stream));
-  const u32 SMALL_MAX = 768;
   if (n_cand) {
     LAUNCH(k_cand_gather, (unsigned)cdiv((u64)n_cand * 32, 256), 256, 0, D.cand_row, D.cand_voff, n_cand, contig, pos, start,
            group, row_seg, seg_start, D.v_pos, D.v_start, D.v_group);
-    LAUNCH(k_cand_vote<32>, (unsigned)cdiv(n_cand, 4), 128, 0, D.cand_row, D.cand_voff, n_cand, D.row_cnt, D.v_pos,
-           D.v_start, D.v_group, SMALL_MAX, D.cand_good, D.cand_dir);
-    LAUNCH(k_cand_vote<1024>, n_cand, 1024, 0, D.cand_row, D.cand_voff, n_cand, D.row_cnt, D.v_pos, D.v_start, D.v_group,
-           SMALL_MAX, D.cand_good, D.cand_dir);
+    u32* n_big = (u32*)(ctx->counters.as<u64>() + 30);
+    CK(cudaMemsetAsync(n_big, 0, 4, ctx->stream));
+    u32* big_list = D.keep_excl;  // free until the keep scan below
+    LAUNCH(k_cand_vote_warp, (unsigned)cdiv(n_cand, VOTE_WARPS), VOTE_WARPS * 32, 0, D.cand_row, D.cand_voff, n_cand, D.row_cnt,
+           D.v_pos, D.v_start, D.v_group, D.cand_good, D.cand_dir, big_list, n_big);
+    LAUNCH(k_cand_vote<1024>, (unsigned)ctx->n_sm * 2, 1024, 0, D.cand_row, D.cand_voff, big_list, n_big, D.row_cnt, D.v_pos,
+           D.v_start, D.v_group, D.cand_good, D.cand_dir);
   }
   LAUNCH(k_seg_best, (unsigned)cdiv(n_seg, 256), 256, 0, (u32)n_seg, seg_start, D.cidx, D.cand_row, D.row_cnt, contig,
          D.cand_good, D.cand_dir, D.seg_best, D.seg_good, D.seg_dir, D.seg_tie);
