@@ -64,15 +64,16 @@ def cmd_kmerpos_annot3(argv):
     k = _k_from_db(db_lines)
     eng = Engine(k if 1 <= k <= 32 else 20)
     eng.load_loc_text(db_lines, list(zip(contig, start, [km.encode() for km in kmer], group)))
-    names, seq, off = gio.pack_reads(gio.read_fastx(reads_p))
-    eng.set_reads(seq, off)
+    reads = gio.NativeReads([reads_p])  # multi-threaded gz/parse into page-locked memory (csrc/fastx.cu)
+    eng.set_reads(reads.seq, reads.read_off)
     eng.match()
-    _atomic_write(out_p, _fmt_rows(eng.rows(0), names, eng.contig_names))
+    _atomic_write(out_p, _fmt_rows(eng.rows(0), reads.names, eng.contig_names))
 
 
 def cmd_rlen(argv):
     reads_p, out_p = argv
-    _atomic_write(out_p, "".join(f"{n}\t{len(s)}\n" for n, s in gio.read_fastx(reads_p)))
+    reads = gio.NativeReads([reads_p], pin=False)
+    _atomic_write(out_p, "".join(f"{n}\t{l}\n" for n, l in zip(reads.names, reads.lengths().tolist())))
 
 
 def _rows_from_sunkpos(path):
@@ -412,20 +413,11 @@ def run_fused(k: int, hap_asm: Sequence[str], hap_reads: Sequence[Sequence[str]]
     eng = Engine(k, device=device)
     eng.build_db(contigs)
     names = eng.contig_names
-    rnames, parts, lens, chunk_first, chunk_hap = [], [], [], [0], []
-    for hap in range(2):
-        for fp in hap_reads[hap]:
-            for n, s in gio.read_fastx(fp):
-                rnames.append(n)
-                parts.append(s)
-                lens.append(len(s))
-            chunk_first.append(len(rnames))
-            chunk_hap.append(hap)
-    off = np.zeros(len(lens) + 1, dtype=np.uint64)
-    if lens:
-        off[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64))
-    seq = np.frombuffer(b"".join(parts), dtype=np.uint8)
-    eng.set_reads(seq, off, chunk_first, chunk_hap)
+    files = list(hap_reads[0]) + list(hap_reads[1])
+    chunk_hap = [0] * len(hap_reads[0]) + [1] * len(hap_reads[1])
+    reads = gio.NativeReads(files)  # one chunk per file, in scatter order
+    rnames, lens, chunk_first = reads.names, reads.lengths().tolist(), reads.chunk_first.tolist()
+    eng.set_reads(reads.seq, reads.read_off, chunk_first, chunk_hap)
     iv = eng.run_all(contig_hap)
     gaps, nodata = eng.gaps(np.asarray([len(s) for _, s in contigs], dtype=np.uint32))
     # ---- files ----

@@ -76,6 +76,53 @@ def read_fastx(path_or_bytes) -> List[Tuple[str, bytes]]:
         return list(iter_fastx(f))
 
 
+class NativeReads:
+    """Reads of one or more FASTA/FASTQ(.gz) files parsed by libgavisunk_b200.so (gvs_fastx_read): one
+    chunk per file, sequences back to back in one (page-locked when possible) host buffer.  The numpy
+    arrays are views of library memory: keep this object alive while they are in use."""
+
+    def __init__(self, paths, threads: int = 0, pin: bool = True):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        self._lib = lib
+        self._fx = _lib.FastxStruct()
+        paths = [os.fspath(p) for p in paths]
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        err = C.create_string_buffer(512)
+        rc = lib.gvs_fastx_read(arr, len(paths), threads or min(len(paths), os.cpu_count() or 1), 1 if pin else 0,
+                                C.byref(self._fx), err, 512)
+        if rc != 0:
+            self._fx = None
+            raise IOError(err.value.decode("utf-8", "replace"))
+        fx = self._fx
+        n, tot = int(fx.n_reads), int(fx.total_bases)
+        as_np = lambda ptr, ctype, cnt: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(cnt,)) if cnt else np.zeros(0, ctype)
+        self.seq = as_np(fx.seq, C.c_uint8, tot)
+        self.read_off = as_np(fx.read_off, C.c_uint64, n + 1)
+        self.chunk_first = as_np(fx.chunk_first, C.c_uint64, int(fx.n_files) + 1).copy()
+        name_off = as_np(fx.name_off, C.c_uint64, n + 1)
+        raw = C.string_at(fx.names, int(name_off[-1])) if n else b""
+        no = name_off.tolist()
+        self.names = [raw[no[i]:no[i + 1]].decode("latin-1") for i in range(n)]
+        self.n_reads, self.total_bases, self.pinned = n, tot, bool(fx.pinned)
+
+    def lengths(self) -> np.ndarray:
+        return np.diff(self.read_off).astype(np.uint64)
+
+    def close(self):
+        if getattr(self, "_fx", None) is not None:
+            self.seq = self.read_off = None
+            self._lib.gvs_fastx_free(self._fx)
+            self._fx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def pack_reads(reads: Iterable[Tuple[str, bytes]]):
     """-> (names, seq uint8[total], off uint64[n+1])"""
     names, parts, lens = [], [], []

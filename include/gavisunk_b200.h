@@ -103,6 +103,26 @@ int gvs_db_export(gvs_ctx* ctx, uint64_t* kmer, uint32_t* contig, uint32_t* star
 
 /* ------------------------------------------------------------------------------------------ */
 /* reads                                                                                       */
+/* Host ingest of FASTA/FASTQ(.gz) read files (the `readfq` loop of workflow/src/kmerpos_annot3.nim:85 and
+ * workflow/src/rlen.nim:13-14; chunk files of workflow/rules/tagONT.smk:17): every file is one chunk, files
+ * are decompressed and parsed on `threads` host threads and laid out back to back in one host buffer
+ * (page-locked when pin != 0 and a CUDA device exists, so that gvs_reads_set can overlap the copy with
+ * the probe).  All arrays are owned by the library until gvs_fastx_free.  No context needed. */
+typedef struct gvs_fastx {
+  void* impl;
+  const uint8_t* seq;          /* total_bases ASCII bytes (+ 64 zero bytes of slack)               */
+  const uint64_t* read_off;    /* n_reads + 1                                                     */
+  const char* names;           /* read names back to back (no terminators)                        */
+  const uint64_t* name_off;    /* n_reads + 1 offsets into names                                  */
+  const uint64_t* chunk_first; /* n_files + 1 read indices: file i = reads [chunk_first[i], [i+1]) */
+  uint64_t n_reads, total_bases;
+  uint32_t n_files;
+  int pinned;
+} gvs_fastx;
+int gvs_fastx_read(const char* const* paths, uint32_t n_files, int threads, int pin, gvs_fastx* out,
+                   char* err, uint64_t err_len);
+void gvs_fastx_free(gvs_fastx* fx);
+
 /* ------------------------------------------------------------------------------------------ */
 /* A batch = the reads of one or more chunk files (temp/{sample}/reads/{hap}_{i-of-N}.fq.gz,
  * workflow/rules/tagONT.smk:17), concatenated in file order.
