@@ -71,7 +71,7 @@ struct ValParams {
 template <int NT, int GROUPS, bool GLOBAL>
 __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
   extern __shared__ __align__(16) u8 smem[];
-  __shared__ u32 s_n0[GROUPS], s_n1[GROUPS], s_m[GROUPS], s_kept[GROUPS], s_bestroot[GROUPS], s_flag[GROUPS];
+  __shared__ u32 s_n0[GROUPS], s_n1[GROUPS], s_m[GROUPS], s_kept[GROUPS], s_bestroot[GROUPS], s_flag[GROUPS], s_dup[GROUPS];
   __shared__ unsigned long long s_best[GROUPS];
   const int grp = threadIdx.x / NT;
   const int tid = threadIdx.x % NT;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     const u32 mrows = b - a;
     if (mrows <= V.m_lo || mrows > V.m_hi) continue;  // another launch owns this read (group-uniform)
     gsync();
-    if (tid == 0) { s_m[grp] = 0; s_n0[grp] = 0; s_n1[grp] = 0; s_kept[grp] = 0; s_best[grp] = 0; s_bestroot[grp] = NOV; s_flag[grp] = 0; }
+    if (tid == 0) { s_m[grp] = 0; s_n0[grp] = 0; s_n1[grp] = 0; s_kept[grp] = 0; s_best[grp] = 0; s_bestroot[grp] = NOV; s_flag[grp] = 0; s_dup[grp] = 0; }
     gsync();
     // read length filter (hard-coded 10000 in the reference, :106-108; Q13)
     const u32 rd = V.read[a];
@@ -114,20 +114,25 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     }
     // ---- sort by (start, pos): sort_values(['rname','start']) is stable and rows of a read come in
     //      increasing pos (:100) ----
-    for (u32 i = tid; i < m; i += NT) {
-      const u32 si = w.uS[i], pi = w.uP[i];
-      u32 rank = 0;
-      for (u32 j = 0; j < m; j++) {
-        u32 sj = w.uS[j], pj = w.uP[j];
-        rank += (sj < si) | ((sj == si) & (pj < pi));
+    {
+      u32 dupl = 0;  // some group ID sits on more than one row of this read (rare: the general path below)
+      for (u32 i = tid; i < m; i += NT) {
+        const u32 si = w.uS[i], pi = w.uP[i], idi = w.uID[i];
+        u32 rank = 0;
+        for (u32 j = 0; j < m; j++) {
+          u32 sj = w.uS[j], pj = w.uP[j];
+          rank += (sj < si) | ((sj == si) & (pj < pi));
+          dupl |= (w.uID[j] == idi) & (j != i);
+        }
+        w.P[rank] = pi;
+        w.S[rank] = si;
+        w.ID[rank] = idi;
+        w.G[rank] = w.uG[i];
+        w.csize[i] = 0;
+        w.tv[i] = NOT64;
+        w.ct[i] = NOT64;
       }
-      w.P[rank] = pi;
-      w.S[rank] = si;
-      w.ID[rank] = w.uID[i];
-      w.G[rank] = w.uG[i];
-      w.csize[i] = 0;
-      w.tv[i] = NOT64;
-      w.ct[i] = NOT64;
+      if (dupl) s_dup[grp] = 1;
     }
     gsync();
     // at least two distinct groups (:91-97)
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       u32 n0 = 0, n1 = 0;
       for (u32 r = tid; r < m; r += NT) {
         const u32 pr = w.P[r], sr = w.S[r];
-        u32 deg0 = 0, deg1 = 0, ld0 = 0, ld1 = 0, fp0 = NOV, fp1 = NOV;
+        u32 deg0 = 0, deg1 = 0, ld0 = 0, ld1 = 0, fp0 = NOV, fp1 = NOV, fh0 = NOV, fh1 = NOV;
         for (u32 q = 0; q < m; q++) {
           u32 pq = w.P[q], sq = w.S[q];
           u32 hi = q > r;
@@ -163,7 +168,11 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
           ld1 += e1 & hi;
           fp0 = (e0 & (hi ^ 1u) & (fp0 == NOV)) ? q : fp0;  // first edge (q, r) with r as the right end
           fp1 = (e1 & (hi ^ 1u) & (fp1 == NOV)) ? q : fp1;
+          fh0 = (e0 & hi & (fh0 == NOV)) ? q : fh0;  // first edge (r, q) with r as the left end
+          fh1 = (e1 & hi & (fh1 == NOV)) ? q : fh1;
         }
+        // the unsorted copies are dead after the sort: they keep the first partners of both orientations
+        w.uP[r] = fp0; w.uS[r] = fh0; w.uID[r] = fp1; w.uG[r] = fh1;
         n0 += ld0;
         n1 += ld1;
         w.deg[r] = deg0;
@@ -186,63 +195,87 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       continue;
     }
     const u32 orient = s_n1[grp] > s_n0[grp];  // np.unique sorted + argmax: a tie keeps 0 (:151-152)
-    for (u32 r = tid; r < m; r += NT) {
-      if (orient) {
-        w.deg[r] = w.label[r];
-        w.key[r] = w.ct[r];
-      }
-      w.ct[r] = NOT64;
-    }
-    gsync();
-    // ---- multipos (:161-181): IDs seen at more than one read position keep their most frequent one ----
-    for (u32 r = tid; r < m; r += NT) {
-      const u32 id = w.ID[r], dr = w.deg[r];
-      const u64 kr = w.key[r];
-      u32 first = r, multi = 0, good = dr > 0;
-      for (u32 q = 0; q < m; q++) {
-        u32 same = (w.ID[q] == id);
-        u32 dq = w.deg[q];
-        first = (same & (q < first)) ? q : first;
-        u32 other = same & (q != r) & (dq > 0);
-        multi |= other;
-        u32 beats = other & ((dq > dr) | ((dq == dr) & (w.key[q] < kr)));
-        good &= beats ^ 1u;
-      }
-      w.rep[r] = first;
-      w.flags[r] = ((multi & (dr > 0)) ? F_MULTI : 0u) | (good ? F_GOOD : 0u);
-    }
-    gsync();
-    // ---- pass C: surviving edges (:189-192): presence, first appearance, first label ----
-    // edge (lo, hi) is dropped iff the LEFT row's ID is multi-positioned, lo is not that ID's good row and
-    // hi is not that ID's good row either (left end only: Q14)
-    {
-      u32 nk = 0;
+    if (!s_dup[grp]) {
+      // Every ID sits on exactly one row: the multipos clean-up (:161-181) cannot drop anything, a vertex is
+      // a row, and what pass C would derive follows from the first partners found in pass AB -- presence
+      // = degree > 0, first appearance in the edge list = the earlier of (r, first right partner) as a
+      // source and (first left partner, r) as a target, first label = smallest neighbour or itself.
       for (u32 r = tid; r < m; r += NT) {
-        const u32 pr = w.P[r], sr = w.S[r], idr = w.ID[r], fr = w.flags[r];
+        const u32 deg = orient ? w.label[r] : w.deg[r];
+        const u32 fp = orient ? w.uID[r] : w.uP[r], fh = orient ? w.uG[r] : w.uS[r];
+        const u32 present = deg > 0;
         u64 tmin = NOT64;
-        u32 lab = NOV;
-        for (u32 q = 0; q < m; q++) {
-          u32 pq = w.P[q], sq = w.S[q], idq = w.ID[q], fq = w.flags[q];
-          u32 hi = q > r;
-          u32 sg = hi ? (pr > pq) : (pq > pr);
-          u32 e = pair_ok(pr, sr, pq, sq) & (q != r) & (sg == orient);
-          u32 fl = hi ? fr : fq, fh = hi ? fq : fr;  // flags of the left / right row of the pair
-          u32 drop = ((fl & F_MULTI) != 0) & ((fl & F_GOOD) == 0) & (((fh & F_GOOD) == 0) | (idq != idr));
-          u32 kept = e & (drop ^ 1u);
-          u32 lo_row = hi ? r : q, hi_row = hi ? q : r;
-          u64 et = 2 * ((u64)lo_row * m + hi_row) + (hi ^ 1u);  // source before target
-          tmin = (kept && et < tmin) ? et : tmin;
-          nk += kept & hi;
-          u32 rq = w.rep[q];
-          lab = (kept && rq < lab) ? rq : lab;
+        if (fh != NOV) tmin = 2 * ((u64)r * m + fh);
+        if (fp != NOV) {
+          u64 et = 2 * ((u64)fp * m + r) + 1;
+          tmin = et < tmin ? et : tmin;
         }
-        u32 present = tmin != NOT64;
-        u32 rr = w.rep[r];
-        w.flags[r] = fr | (present ? F_PRES : 0u);
-        w.label[r] = present ? (rr < lab ? rr : lab) : NOV;
-        if (present) atomicMin((unsigned long long*)&w.tv[rr], (unsigned long long)tmin);
+        w.rep[r] = r;
+        w.flags[r] = present ? F_PRES : 0u;
+        w.label[r] = present ? (fp != NOV ? fp : r) : NOV;
+        w.tv[r] = present ? tmin : NOT64;
+        w.ct[r] = NOT64;
       }
-      if (nk) atomicAdd(&s_kept[grp], nk);
+      if (tid == 0) s_kept[grp] = orient ? s_n1[grp] : s_n0[grp];
+    } else {
+      for (u32 r = tid; r < m; r += NT) {
+        if (orient) {
+          w.deg[r] = w.label[r];
+          w.key[r] = w.ct[r];
+        }
+        w.ct[r] = NOT64;
+      }
+      gsync();
+      // ---- multipos (:161-181): IDs seen at more than one read position keep their most frequent one ----
+      for (u32 r = tid; r < m; r += NT) {
+        const u32 id = w.ID[r], dr = w.deg[r];
+        const u64 kr = w.key[r];
+        u32 first = r, multi = 0, good = dr > 0;
+        for (u32 q = 0; q < m; q++) {
+          u32 same = (w.ID[q] == id);
+          u32 dq = w.deg[q];
+          first = (same & (q < first)) ? q : first;
+          u32 other = same & (q != r) & (dq > 0);
+          multi |= other;
+          u32 beats = other & ((dq > dr) | ((dq == dr) & (w.key[q] < kr)));
+          good &= beats ^ 1u;
+        }
+        w.rep[r] = first;
+        w.flags[r] = ((multi & (dr > 0)) ? F_MULTI : 0u) | (good ? F_GOOD : 0u);
+      }
+      gsync();
+      // ---- pass C: surviving edges (:189-192): presence, first appearance, first label ----
+      // edge (lo, hi) is dropped iff the LEFT row's ID is multi-positioned, lo is not that ID's good row and
+      // hi is not that ID's good row either (left end only: Q14)
+      {
+        u32 nk = 0;
+        for (u32 r = tid; r < m; r += NT) {
+          const u32 pr = w.P[r], sr = w.S[r], idr = w.ID[r], fr = w.flags[r];
+          u64 tmin = NOT64;
+          u32 lab = NOV;
+          for (u32 q = 0; q < m; q++) {
+            u32 pq = w.P[q], sq = w.S[q], idq = w.ID[q], fq = w.flags[q];
+            u32 hi = q > r;
+            u32 sg = hi ? (pr > pq) : (pq > pr);
+            u32 e = pair_ok(pr, sr, pq, sq) & (q != r) & (sg == orient);
+            u32 fl = hi ? fr : fq, fh = hi ? fq : fr;  // flags of the left / right row of the pair
+            u32 drop = ((fl & F_MULTI) != 0) & ((fl & F_GOOD) == 0) & (((fh & F_GOOD) == 0) | (idq != idr));
+            u32 kept = e & (drop ^ 1u);
+            u32 lo_row = hi ? r : q, hi_row = hi ? q : r;
+            u64 et = 2 * ((u64)lo_row * m + hi_row) + (hi ^ 1u);  // source before target
+            tmin = (kept && et < tmin) ? et : tmin;
+            nk += kept & hi;
+            u32 rq = w.rep[q];
+            lab = (kept && rq < lab) ? rq : lab;
+          }
+          u32 present = tmin != NOT64;
+          u32 rr = w.rep[r];
+          w.flags[r] = fr | (present ? F_PRES : 0u);
+          w.label[r] = present ? (rr < lab ? rr : lab) : NOV;
+          if (present) atomicMin((unsigned long long*)&w.tv[rr], (unsigned long long)tmin);
+        }
+        if (nk) atomicAdd(&s_kept[grp], nk);
+      }
     }
     gsync();
     if (s_kept[grp] == 0) {  // graph-tool would raise on the empty graph; counted, read skipped (A.6 step 5)
