@@ -53,7 +53,10 @@ def test_sizes_are_config3(full):
 
 
 def test_properties_of_the_reference_algorithm(full):
-    eng, wl, res = full
+    check_properties(*full)
+
+
+def check_properties(eng, wl, res):
     rows, kept, best, pairs = res["rows"], res["kept"], res["best"], res["pairs"]
     rd, pos, ctg, st, grp = (rows[c].astype(np.int64) for c in ("read", "pos", "contig", "start", "group"))
     lens = np.diff(res["off"])
@@ -79,7 +82,7 @@ def test_properties_of_the_reference_algorithm(full):
     assert np.array_equal(wl.contig_hap[best["contig"]], hap_of_read)
     assert best["ngood"].min() >= 2
     # validated pairs: only reads >= 10 kb (:106), never a bad group (:70-72), every pair is a kept row of that read,
-    # at least two IDs per read (an edge has two ends), IDs distinct inside a read (graph vertices)
+    # IDs distinct inside a read (graph vertices)
     pr, pg, pgi = pairs["read"].astype(np.int64), pairs["group"].astype(np.int64), pairs["gidx"].astype(np.int64)
     assert lens[pr].min() >= 10000
     assert not np.isin(pgi, res["bad"]).any()
@@ -87,7 +90,12 @@ def test_properties_of_the_reference_algorithm(full):
     key_pair = pr << 32 | pg
     assert np.isin(key_pair, key_kept).all()
     assert len(np.unique(key_pair)) == len(key_pair)
-    assert np.unique(pr, return_counts=True)[1].min() >= 2
+    # an edge has two ends: a read reports >= 2 IDs, or a single ID that sits on >= 2 of its rows (a self-loop
+    # of the ID graph: the same group hit at two consistent positions)
+    ur, cnt = np.unique(pr, return_counts=True)
+    single = key_pair[np.isin(pr, ur[cnt == 1])]
+    kk, kc = np.unique(kept["read"].astype(np.int64) << 32 | kept["group"].astype(np.int64), return_counts=True)
+    assert np.all(kc[np.searchsorted(kk, single)] >= 2)
     # intervals: >= 3 groups means start < end; sorted by (contig, start) (:248-260)
     iv = res["iv"]
     assert np.all(iv["start"] < iv["end"])
