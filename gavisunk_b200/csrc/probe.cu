@@ -351,10 +351,8 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           w1[g] = any_valid ? p_ldg_u32(P.filt1 + gvs_p1_word(hbv[g], P.filt1_mask), pol_keep) : 0u;
         }
 #pragma unroll
-        for (int g = 0; g < NG; g++) {
-          const u32 m1 = gvs_p1_bits(hbv[g]);
-          pass |= ((w1[g] & m1) == m1 ? 1u : 0u) << g;
-        }
+        for (int g = 0; g < NG; g++)  // both bits of gvs_p1_bits(hb) set in the word (the funnel shift wraps mod 32)
+          pass |= (__funnelshift_r(w1[g], 0u, hbv[g]) & __funnelshift_r(w1[g], 0u, hbv[g] >> 5) & 1u) << g;
       }
       // ---- passing groups -> warp queue (position order); their windows are tested one per lane ----
       if (__any_sync(ALL, pass != 0)) {

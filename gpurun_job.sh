@@ -1,1 +1,6 @@
-(time python -m pytest tests/test_gpu_fullsize_h.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -30)
+python -m pytest tests/test_gpu_match.py tests/test_gpu_db.py -m gpu -x -q 2>&1 | tail -3
+for wl in h3100 s150; do
+python bench.py --workload $wl --steps 5 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/bench_${wl}_y.json 2> gpurun_out/bench_${wl}_y.err; echo rc=$?; tail -3 gpurun_out/bench_${wl}_y.err
+python -c "
+import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['config']['stage_ms'], d['roofline']['frac'], d['config']['results_per_step']['rows'])" gpurun_out/bench_${wl}_y.json
+done
