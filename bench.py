@@ -165,6 +165,8 @@ def main_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from gavisunk_b200.parallel import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local) if world > 1 else dict(numa_node=None)  # pinned read buffers on the GPU's own socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine(args.k, device=local, stream=torch.cuda.current_stream().cuda_stream)
@@ -272,7 +274,7 @@ def main_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = dict(value=total_bases * args.e2e_steps / (float(t.item()) * 1e-3) / 1e9, unit=UNIT,
                    h2d_bytes_per_step=int(wl.total_bases + 8 * (wl.n_reads + 1)), d2h_bytes_per_step=int(d2h),
-                   steps=args.e2e_steps, ms_per_step=float(t.item()) / args.e2e_steps)
+                   steps=args.e2e_steps, ms_per_step=float(t.item()) / args.e2e_steps, host_numa_node=numa.get("numa_node"))
         del h_reads, h_off
 
     cpu_baseline = None

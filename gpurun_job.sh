@@ -1,6 +1,7 @@
-python -m pytest tests/test_gpu_match.py tests/test_gpu_db.py -m gpu -x -q 2>&1 | tail -3
-for wl in h3100 s150; do
-python bench.py --workload $wl --steps 5 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/bench_${wl}_y.json 2> gpurun_out/bench_${wl}_y.err; echo rc=$?; tail -3 gpurun_out/bench_${wl}_y.err
+nvidia-smi topo -m 2>&1 | head -16
+lscpu | grep -i -E "numa|socket|^CPU\(s\)" | head
+for n in 4; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n bench.py --gpus $n --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_h3100_n${n}_numa.json 2> gpurun_out/bench_h3100_n${n}_numa.err; echo rc=$?; tail -5 gpurun_out/bench_h3100_n${n}_numa.err | cut -c1-300
 python -c "
-import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['config']['stage_ms'], d['roofline']['frac'], d['config']['results_per_step']['rows'])" gpurun_out/bench_${wl}_y.json
+import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e'])" gpurun_out/bench_h3100_n${n}_numa.json
 done

@@ -106,3 +106,11 @@ def test_exchanges_world2_gloo():
         assert npeers == 1
         assert h == exp_hist
         assert roots == exp_roots  # replicated result: min index of the component on every rank
+
+
+def test_parse_cpulist_and_numa_binding_is_best_effort():
+    from gavisunk_b200.parallel import parse_cpulist, bind_to_gpu_numa
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("") == []
+    info = bind_to_gpu_numa(0)  # no GPU here: must not raise, must not change anything
+    assert info["device"] == 0 and info["cpus"] is None
