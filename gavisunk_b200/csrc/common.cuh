@@ -55,7 +55,7 @@ struct gvs_ctx {
   u32 n_contigs = 0;
   DevBuf loc_kmer, loc_contig, loc_start, loc_group, loc_gidx;  // per .loc row
   DevBuf grp_contig, grp_start;                                  // per group (index = gidx)
-  DevBuf tab_keys, tab_rows;                                     // open-addressed probe table
+  DevBuf tab_keys, tab_rows, tab_gidx;                           // open-addressed probe table (+ group index of the row)
   u64 tab_slots = 0;                                             // power of two, buckets of 4
   DevBuf filt;                                                   // 32-bit-word blocked Bloom filter
   u64 filt_words = 0;                                            // number of 16-byte blocks, power of two
@@ -89,8 +89,11 @@ struct gvs_ctx {
 
   // ---- match ----
   DevBuf tile_first, tile_cnt, tile_off, tile_dst;
-  DevBuf hit_read, hit_w, hit_row;     // unordered (per-tile allocated)
-  DevBuf ohit_read, ohit_w, ohit_row;  // ordered
+  // hit records: the first hit of a run of consecutive hits on ONE group inside one read (and one probe
+  // tile), with the number of hits that follow it in the run -- kmerpos_annot3 prints only the first
+  // (nim:92) and the others merely shift later positions (Q3)
+  DevBuf hit_read, hit_w, hit_row, hit_gidx, hit_nf;       // per probe span
+  DevBuf ohit_read, ohit_w, ohit_row, ohit_gidx, ohit_nf;  // dense, position order
   u64 hit_cap = 0, n_hits = 0;
   DevBuf counters;                     // small block of device counters / flags
   DevBuf scan_tmp, scan_tmp2, flags_a, flags_b, flags_c;
@@ -411,6 +414,7 @@ static int to_dev(gvs_ctx* ctx, DevBuf& b, const T* h, size_t n) {
 
 // stage entry points implemented in the other translation units
 int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db);  // table.cu
+int gvs_tab_attach_gidx(gvs_ctx* ctx);                                 // table.cu (after loc_gidx exists)
 int gvs_group_index_rows(gvs_ctx* ctx, const u32* contig, const u32* group, u64 n, u32* gidx_out);  // table.cu
 int gvs_build_segments(gvs_ctx* ctx, const u32* read, u64 n, DevBuf& seg_start, DevBuf& row_seg, u64* n_seg_out);  // diag.cu
 int gvs_reserve_rows(gvs_ctx* ctx, Rows& r, u64 n);

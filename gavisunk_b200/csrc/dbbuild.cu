@@ -347,6 +347,7 @@ static int db_build_device(gvs_ctx* ctx, const u8* seq, const u64* contig_off, u
   gvs_release(keys);
   gvs_release(vals);
   CKR(gvs_tab_build_impl(ctx, nullptr, 0));
+  CKR(gvs_tab_attach_gidx(ctx));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

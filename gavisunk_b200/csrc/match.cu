@@ -17,10 +17,11 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out);  // probe.
 #define FLAG_KEYERROR 1u
 #define FLAG_OVERFLOW 2u
 
-// per-warp hit regions -> one dense array in global position order (warp order = position order)
+// per-span record regions -> dense arrays in global position order (span order = position order)
 __global__ void __launch_bounds__(128) k_gather_hits(const u32* __restrict__ warp_cnt, const u64* __restrict__ warp_dst, u64 cap_w,
                                                      const u32* __restrict__ a0, const u32* __restrict__ a1,
-                                                     const u32* __restrict__ a2, u32* b0, u32* b1, u32* b2) {
+                                                     const u32* __restrict__ a2, const u32* __restrict__ a3,
+                                                     const u8* __restrict__ a4, u32* b0, u32* b1, u32* b2, u32* b3, u8* b4) {
   const u64 w = blockIdx.x;
   const u32 c = warp_cnt[w];
   const u64 s = w * cap_w, d = warp_dst[w];
@@ -28,6 +29,8 @@ __global__ void __launch_bounds__(128) k_gather_hits(const u32* __restrict__ war
     b0[d + i] = a0[s + i];
     b1[d + i] = a1[s + i];
     b2[d + i] = a2[s + i];
+    b3[d + i] = a3[s + i];
+    b4[d + i] = a4[s + i];
   }
 }
 
@@ -40,9 +43,8 @@ __device__ __forceinline__ u32 chunk_of(const u64* __restrict__ chunk_first, u32
   return lo;
 }
 
-// flags: bit0 = emitted (curLoc != prevLoc, nim:92), bit1 = first hit of its read
-__global__ void __launch_bounds__(256) k_emit_flags(const u32* __restrict__ hread, const u32* __restrict__ hrow,
-                                                    const u32* __restrict__ loc_gidx, u64 n,
+// flags: bit0 = emitted (curLoc != prevLoc, nim:92), bit1 = first record of its read
+__global__ void __launch_bounds__(256) k_emit_flags(const u32* __restrict__ hread, const u32* __restrict__ hgidx, u64 n,
                                                     const u64* __restrict__ chunk_first, u32 n_chunks, u8* flags) {
   u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -52,24 +54,25 @@ __global__ void __launch_bounds__(256) k_emit_flags(const u32* __restrict__ hrea
     u32 rp = hread[j - 1];
     head = rp != rd;
     bool same_chunk = !head || chunk_of(chunk_first, n_chunks, rp) == chunk_of(chunk_first, n_chunks, rd);
-    if (same_chunk) emit = loc_gidx[hrow[j]] != loc_gidx[hrow[j - 1]];
+    if (same_chunk) emit = hgidx[j] != hgidx[j - 1];
   }
   flags[j] = (emit ? 1 : 0) | (head ? 2 : 0);
 }
 
 __global__ void __launch_bounds__(256) k_emit_rows(const u32* __restrict__ hread, const u32* __restrict__ hw,
-                                                   const u32* __restrict__ hrow, const u8* __restrict__ flags,
+                                                   const u32* __restrict__ hrow, const u32* __restrict__ hgidx,
+                                                   const u8* __restrict__ flags,
                                                    const u64* __restrict__ packed_excl, const u32* __restrict__ seg_base,
                                                    u64 n, const u32* __restrict__ loc_contig,
                                                    const u32* __restrict__ loc_start, const u32* __restrict__ loc_group,
-                                                   const u32* __restrict__ loc_gidx, u32* r_read, u32* r_pos,
+                                                   u32* r_read, u32* r_pos,
                                                    u32* r_contig, u32* r_start, u32* r_group, u32* r_gidx) {
   u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   if (!(flags[j] & 1)) return;
   u64 pe = packed_excl[j];
   u32 out = (u32)(pe >> 32);        // emitted rows before j
-  u32 supp = (u32)pe;               // suppressed hits before j (whole batch)
+  u32 supp = (u32)pe;               // suppressed hits before record j (whole batch)
   u32 base = seg_base[j] - 1;       // suppressed hits before the first hit of j's read
   u32 row = hrow[j];
   r_read[out] = hread[j];
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(256) k_emit_rows(const u32* __restrict__ hread
   r_contig[out] = loc_contig[row];
   r_start[out] = loc_start[row];
   r_group[out] = loc_group[row];
-  r_gidx[out] = loc_gidx[row];
+  r_gidx[out] = hgidx[j];
 }
 
 
@@ -136,6 +139,8 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
     CKR(gvs_reserve(ctx, ctx->hit_read, ctx->hit_cap * 4));
     CKR(gvs_reserve(ctx, ctx->hit_w, ctx->hit_cap * 4));
     CKR(gvs_reserve(ctx, ctx->hit_row, ctx->hit_cap * 4));
+    CKR(gvs_reserve(ctx, ctx->hit_gidx, ctx->hit_cap * 4));
+    CKR(gvs_reserve(ctx, ctx->hit_nf, ctx->hit_cap));
     bool overflow = false;
     u64 need = 0, max_w = 0;
     CKR(match_once(ctx, &n_warps, &cap_w, &overflow, &need, &max_w));
@@ -157,8 +162,11 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
   CKR(gvs_reserve(ctx, ctx->ohit_read, nh * 4));
   CKR(gvs_reserve(ctx, ctx->ohit_w, nh * 4));
   CKR(gvs_reserve(ctx, ctx->ohit_row, nh * 4));
+  CKR(gvs_reserve(ctx, ctx->ohit_gidx, nh * 4));
+  CKR(gvs_reserve(ctx, ctx->ohit_nf, nh));
   LAUNCH(k_gather_hits, (unsigned)n_warps, 128, 0, ctx->tile_cnt.as<u32>(), ctx->tile_dst.as<u64>(), cap_w, ctx->hit_read.as<u32>(),
-         ctx->hit_w.as<u32>(), ctx->hit_row.as<u32>(), ctx->ohit_read.as<u32>(), ctx->ohit_w.as<u32>(), ctx->ohit_row.as<u32>());
+         ctx->hit_w.as<u32>(), ctx->hit_row.as<u32>(), ctx->hit_gidx.as<u32>(), ctx->hit_nf.as<u8>(), ctx->ohit_read.as<u32>(),
+         ctx->ohit_w.as<u32>(), ctx->ohit_row.as<u32>(), ctx->ohit_gidx.as<u32>(), ctx->ohit_nf.as<u8>());
   // ---- suppression + position drift ----
   CKR(gvs_reserve(ctx, ctx->flags_a, nh));          // u8 flags
   CKR(gvs_reserve(ctx, ctx->flags_b, nh * 8));      // packed exclusive counts
@@ -166,11 +174,14 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
   u8* fl = ctx->flags_a.as<u8>();
   u64* pex = ctx->flags_b.as<u64>();
   u32* sb = ctx->flags_c.as<u32>();
-  LAUNCH(k_emit_flags, (unsigned)cdiv(nh, 256), 256, 0, ctx->ohit_read.as<u32>(), ctx->ohit_row.as<u32>(),
-         ctx->loc_gidx.as<u32>(), nh, ctx->chunk_first.as<u64>(), ctx->n_chunks, fl);
+  const u8* nf = ctx->ohit_nf.as<u8>();
+  LAUNCH(k_emit_flags, (unsigned)cdiv(nh, 256), 256, 0, ctx->ohit_read.as<u32>(), ctx->ohit_gidx.as<u32>(), nh,
+         ctx->chunk_first.as<u64>(), ctx->n_chunks, fl);
   u64* tot = ctx->counters.as<u64>() + 2;
   {
-    auto f = [fl] __device__(u64 i) -> u64 { return (fl[i] & 1) ? (1ull << 32) : 1ull; };
+    // high word: rows emitted; low word: suppressed hits = the record's followers (+ the record's own
+    // first hit when it continues the previous record's group)
+    auto f = [fl, nf] __device__(u64 i) -> u64 { return ((fl[i] & 1) ? (1ull << 32) : 1ull) + nf[i]; };
     auto g = [pex] __device__(u64 i, u64 ex, u64 v) { pex[i] = ex; };
     CKR((device_scan<u64>(ctx, nh, f, g, OpSum(), tot)));
   }
@@ -186,8 +197,8 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
   u64 n_rows = packed_total >> 32;
   CKR(gvs_reserve_rows(ctx, ctx->rows, n_rows));
   LAUNCH(k_emit_rows, (unsigned)cdiv(nh, 256), 256, 0, ctx->ohit_read.as<u32>(), ctx->ohit_w.as<u32>(),
-         ctx->ohit_row.as<u32>(), fl, pex, sb, nh, ctx->loc_contig.as<u32>(), ctx->loc_start.as<u32>(),
-         ctx->loc_group.as<u32>(), ctx->loc_gidx.as<u32>(), ctx->rows.read.as<u32>(), ctx->rows.pos.as<u32>(),
+         ctx->ohit_row.as<u32>(), ctx->ohit_gidx.as<u32>(), fl, pex, sb, nh, ctx->loc_contig.as<u32>(), ctx->loc_start.as<u32>(),
+         ctx->loc_group.as<u32>(), ctx->rows.read.as<u32>(), ctx->rows.pos.as<u32>(),
          ctx->rows.contig.as<u32>(), ctx->rows.start.as<u32>(), ctx->rows.group.as<u32>(), ctx->rows.gidx.as<u32>());
   ctx->rows.n = n_rows;
   ctx->match_ready = true;

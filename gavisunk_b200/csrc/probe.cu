@@ -20,9 +20,10 @@
 //   * filter-positive windows (~1 %) are compacted into a per-warp queue in position order and looked
 //     up in the exact table (32-byte bucket in HBM) 32 at a time
 //   * work is handed out in spans of a few hundred tiles through one atomic counter (no tail: a warp
-//     that drew hit-poor reads simply takes more spans); every span appends its hits to its own region
-//     of the hit arrays (position order, no per-hit atomics); a scan of the per-span counts + one
-//     coalesced copy give the dense ordered list
+//     that drew hit-poor reads simply takes more spans); runs of hits on one SUNK group collapse into one
+//     record (first hit + follower count: ~6 hits per group crossing at 94 % read identity); every span
+//     appends its records to its own region (position order, no per-hit atomics); a scan of the per-span
+//     counts + one coalesced copy give the dense ordered list
 #include "table.cuh"
 #include <vector>
 
@@ -95,8 +96,8 @@ struct WarpSmem {
   u32 bidx[PW_MAXB];
   u32 cand[PW_TILE / 32];  // filter-positive windows of the tile (bit p)
   u16 inv[32];             // per lane: invalid windows among its 16
-  u32 q_row[PW_TILE];      // group queue: block hash of the passing group; later: row of a hit
-  u16 q_p[PW_TILE];        // group queue: group index inside the tile; later: window of a candidate / hit
+  u32 q_row[PW_TILE];      // group queue: block hash of the passing group
+  u16 q_p[PW_TILE];        // group queue: group index inside the tile; later: window of a candidate
 };
 
 // forward / reverse-complement k-mer of window p (0..511) of the tile whose ring base is `rb`
@@ -138,9 +139,11 @@ struct Probe2Params {
   const u32* __restrict__ filt1;  // presence filter of the sub-mers
   u32 filt1_mask;
   TabView tab;
-  u32* hit_read;
+  u32* hit_read;  // hit records (first hit of a run on one group + number of followers), see common.cuh
   u32* hit_w;
   u32* hit_row;
+  u32* hit_gidx;
+  u8* hit_nf;
   u64 hit_cap;
   u32* flags;
   u32* warp_cnt;  // hits found in each span (they sit at span * cap_w in the hit arrays)
@@ -423,7 +426,6 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
       }
       cm |= (S16 << 16);  // remember which candidates are forced-A windows
       // ---- queue candidates in position order ----
-      u32 nh = 0;
       if (__any_sync(ALL, (cm & 0xFFFFu) != 0)) {
         u32 ncand_lane = __popc(cm & 0xFFFFu);
         u32 incl = ncand_lane;
@@ -439,15 +441,42 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           sm.q_p[qo++] = (u16)((16u * lane + i) | (((cm >> (16 + i)) & 1) << 15));
         }
         __syncwarp();
-        // ---- exact lookups, 32 candidates per round ----
+        auto read_of = [&](u32 prel) -> u32 {
+          if (!has_bound) return (u32)(cur0 - 1);
+          if (nb <= PW_MAXB) {
+            u32 rd = (u32)(cur0 - 1), bestpos = 0;
+            bool any = false;
+            for (u32 q = 0; q < nb; q++) {
+              u32 bp = sm.bpos[q], bj = sm.bidx[q];
+              if (bp <= prel && (!any || bp > bestpos || (bp == bestpos && bj > rd))) {
+                any = true;
+                bestpos = bp;
+                rd = bj;
+              }
+            }
+            return rd;
+          }
+          u64 p = ts + prel;
+          u64 l = 1, h2 = P.n_reads;
+          while (l < h2) {
+            u64 mid = (l + h2) >> 1;
+            if (__ldg(P.read_off + mid) > p) h2 = mid; else l = mid + 1;
+          }
+          return (u32)(l - 1);
+        };
+        // ---- exact lookups, 32 candidates per round.  The hits of a round (lane order = position order)
+        //      are written out at once: runs of consecutive hits on one group inside one read collapse
+        //      into ONE record (first hit + number of followers) -- kmerpos_annot3 prints only the first
+        //      (nim:92), the others just shift the positions reported later in the read (Q3).  Runs are
+        //      cut at round and tile boundaries; the emit pass (match.cu) merges what was cut. ----
         for (u32 base = 0; base < ncand; base += 32) {
-          u32 row = GVS_NOHIT;
+          u32 row = GVS_NOHIT, gi = 0, rd = 0;
           u32 pp = 0;
           if (base + lane < ncand) {
             u32 e = sm.q_p[base + lane];
             pp = e & 0x7FFFu;
             u64 canon = p_canon_at<K>(sm, rb, pp, (e >> 15) != 0);
-            row = tab_lookup(P.tab, canon, gvs_mix(canon));
+            row = tab_lookup(P.tab, canon, gvs_mix(canon), &gi);
             if (row == GVS_ROW_MISSING) {
               atomicOr(P.flags, FLAG_KEYERROR);
               row = GVS_NOHIT;
@@ -455,53 +484,30 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
               row = GVS_NOHIT;
             }
           }
-          u32 bal = __ballot_sync(ALL, row != GVS_NOHIT);
-          __syncwarp();
-          if (row != GVS_NOHIT) {
-            u32 d = nh + __popc(bal & ((1u << lane) - 1));
-            sm.q_p[d] = (u16)pp;
-            sm.q_row[d] = row;
+          const bool hit = row != GVS_NOHIT;
+          const u32 bal = __ballot_sync(ALL, hit);
+          if (bal == 0) continue;  // warp-uniform
+          if (hit) rd = read_of(pp);
+          const u32 below = bal & ((1u << lane) - 1);
+          const int prev = below ? 31 - __clz(below) : lane;  // the hit before this one in the round
+          const u32 gi_prev = __shfl_sync(ALL, gi, prev), rd_prev = __shfl_sync(ALL, rd, prev);
+          const bool head = hit && (below == 0 || gi != gi_prev || rd != rd_prev);
+          const u32 hb = __ballot_sync(ALL, head);
+          const u32 nrec = __popc(hb);
+          const bool fits = (u64)wcount + nrec <= P.cap_w;
+          if (!fits && lane == 0) atomicOr(P.flags, FLAG_OVERFLOW);
+          if (head && fits) {
+            const u32 above = lane == 31 ? 0u : (hb >> (lane + 1)) << (lane + 1);
+            const u32 upto = above ? ((1u << (__ffs(above) - 1)) - 1) : 0xFFFFFFFFu;  // lanes below the next head
+            const u32 after = lane == 31 ? 0u : ~((2u << lane) - 1);                    // lanes above this one
+            const u64 o = region * P.cap_w + wcount + __popc(hb & ((1u << lane) - 1));
+            P.hit_read[o] = rd;
+            P.hit_w[o] = (u32)(ts + pp - __ldg(P.read_off + rd));
+            P.hit_row[o] = row;
+            P.hit_gidx[o] = gi;
+            P.hit_nf[o] = (u8)__popc(bal & upto & after);
           }
-          nh += __popc(bal);
-          __syncwarp();
-        }
-      }
-      // ---- append the tile's hits to this span's region (position order, no global atomics) ----
-      if (nh) {
-        const bool fits = (u64)wcount + nh <= P.cap_w;
-        if (!fits && lane == 0) atomicOr(P.flags, FLAG_OVERFLOW);
-        const u64 obase = region * P.cap_w + wcount;
-        wcount += nh;
-        for (u32 idx = lane; fits && idx < nh; idx += 32) {
-          u64 o = obase + idx;
-          u32 prel = sm.q_p[idx];
-          u64 p = ts + prel;
-          u32 rd;
-          if (!has_bound || nb <= PW_MAXB) {
-            rd = (u32)(cur0 - 1);
-            if (has_bound) {
-              u32 bestpos = 0;
-              bool any = false;
-              for (u32 q = 0; q < nb; q++) {
-                u32 bp = sm.bpos[q], bj = sm.bidx[q];
-                if (bp <= prel && (!any || bp > bestpos || (bp == bestpos && bj > rd))) {
-                  any = true;
-                  bestpos = bp;
-                  rd = bj;
-                }
-              }
-            }
-          } else {
-            u64 l = 1, h2 = P.n_reads;
-            while (l < h2) {
-              u64 mid = (l + h2) >> 1;
-              if (__ldg(P.read_off + mid) > p) h2 = mid; else l = mid + 1;
-            }
-            rd = (u32)(l - 1);
-          }
-          P.hit_read[o] = rd;
-          P.hit_w[o] = (u32)(p - __ldg(P.read_off + rd));
-          P.hit_row[o] = sm.q_row[idx];
+          wcount += nrec;
         }
       }
       // ---- tile T is done: its ring slot receives tile T+2 ----
@@ -576,10 +582,13 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   P.blk_stream = ctx->filt_words * 16 > (32ull << 20) ? 1u : 0u;
   P.tab.keys = ctx->tab_keys.as<u64>();
   P.tab.rows = ctx->tab_rows.as<u32>();
+  P.tab.gidx = ctx->tab_gidx.as<u32>();
   P.tab.slots = ctx->tab_slots;
   P.hit_read = ctx->hit_read.as<u32>();
   P.hit_w = ctx->hit_w.as<u32>();
   P.hit_row = ctx->hit_row.as<u32>();
+  P.hit_gidx = ctx->hit_gidx.as<u32>();
+  P.hit_nf = ctx->hit_nf.as<u8>();
   P.hit_cap = ctx->hit_cap;
   P.flags = (u32*)(counters + 1);
   P.warp_cnt = ctx->tile_cnt.as<u32>();

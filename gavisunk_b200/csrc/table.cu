@@ -138,6 +138,20 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
   return 0;
 }
 
+__global__ void k_tab_gidx(const u32* __restrict__ rows, u64 slots, const u32* __restrict__ loc_gidx, u64 n_loc, u32* gidx) {
+  for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
+    u32 r = rows[s];
+    gidx[s] = r < n_loc ? loc_gidx[r] : 0xFFFFFFFFu;
+  }
+}
+// the group index of every slot's row next to it, so that the probe learns it with the row
+int gvs_tab_attach_gidx(gvs_ctx* ctx) {
+  CKR(gvs_reserve(ctx, ctx->tab_gidx, ctx->tab_slots * sizeof(u32)));
+  LAUNCH(k_tab_gidx, grid_for(ctx, ctx->tab_slots, 256), 256, 0, ctx->tab_rows.as<u32>(), ctx->tab_slots, ctx->loc_gidx.as<u32>(),
+         ctx->n_loc, ctx->tab_gidx.as<u32>());
+  return 0;
+}
+
 // dense group index by first appearance of (contig, group) in .loc row order
 static int build_group_index_body(gvs_ctx* ctx, const u32* contig, const u32* group, u64 n, u32* gidx_out, DevBuf& gk,
                                   DevBuf& gm, DevBuf& rep, DevBuf& dense, u64 slots) {
@@ -210,6 +224,7 @@ extern "C" int gvs_db_load_loc(gvs_ctx* ctx, const uint64_t* db_kmer, uint64_t n
     rc = gvs_fail(ctx, GVS_E_ARG, "null db_kmer with n_db > 0");
   }
   if (!rc) rc = build_group_index(ctx);
+  if (!rc) rc = gvs_tab_attach_gidx(ctx);
   cudaStreamSynchronize(ctx->stream);
   gvs_release(dbk);
   if (rc) return rc;

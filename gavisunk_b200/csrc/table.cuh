@@ -13,27 +13,34 @@
 struct TabView {
   const u64* __restrict__ keys;
   const u32* __restrict__ rows;
+  const u32* __restrict__ gidx;  // dense group index of the row's (contig, group)
   u64 slots;
 };
 
 #define GVS_NOHIT 0xFFFFFFFDu
 
-// exact lookup; returns row, GVS_ROW_MISSING, or GVS_NOHIT
-__device__ __forceinline__ u32 tab_lookup(const TabView& t, u64 key, u64 h) {
+// exact lookup; returns the slot of the key or ~0
+__device__ __forceinline__ u64 tab_find(const TabView& t, u64 key, u64 h) {
   u64 nb = t.slots >> 2;
   u64 b = gvs_tab_bucket(h, t.slots);
   for (u64 it = 0; it < nb; it++) {
     const ulonglong2* p = (const ulonglong2*)(t.keys + (b << 2));
     ulonglong2 a = __ldg(p), c = __ldg(p + 1);
-    if (a.x == key) return __ldg(t.rows + (b << 2) + 0);
-    if (a.y == key) return __ldg(t.rows + (b << 2) + 1);
-    if (c.x == key) return __ldg(t.rows + (b << 2) + 2);
-    if (c.y == key) return __ldg(t.rows + (b << 2) + 3);
-    if (a.x == GVS_EMPTY_KEY || a.y == GVS_EMPTY_KEY || c.x == GVS_EMPTY_KEY || c.y == GVS_EMPTY_KEY)
-      return GVS_NOHIT;
+    if (a.x == key) return (b << 2) + 0;
+    if (a.y == key) return (b << 2) + 1;
+    if (c.x == key) return (b << 2) + 2;
+    if (c.y == key) return (b << 2) + 3;
+    if (a.x == GVS_EMPTY_KEY || a.y == GVS_EMPTY_KEY || c.x == GVS_EMPTY_KEY || c.y == GVS_EMPTY_KEY) return ~0ull;
     b = (b + 1) & (nb - 1);
   }
-  return GVS_NOHIT;
+  return ~0ull;
+}
+// returns row, GVS_ROW_MISSING, or GVS_NOHIT; *gidx = group index of the row (valid for a real row)
+__device__ __forceinline__ u32 tab_lookup(const TabView& t, u64 key, u64 h, u32* gidx) {
+  u64 s = tab_find(t, key, h);
+  if (s == ~0ull) return GVS_NOHIT;
+  *gidx = __ldg(t.gidx + s);
+  return __ldg(t.rows + s);
 }
 
 // find-or-insert; returns slot index (never fails while load < 1)
