@@ -55,7 +55,7 @@ struct gvs_ctx {
   u32 n_contigs = 0;
   DevBuf loc_kmer, loc_contig, loc_start, loc_group, loc_gidx;  // per .loc row
   DevBuf grp_contig, grp_start;                                  // per group (index = gidx)
-  DevBuf tab_keys, tab_rows, tab_gidx;                           // open-addressed probe table (+ group index of the row)
+  DevBuf tab_keys, tab_rows, tab_gidx;                           // open-addressed probe table: keys, (build only) rows, (group index << 32 | row)
   u64 tab_slots = 0;                                             // power of two, buckets of 4
   DevBuf filt;                                                   // 32-bit-word blocked Bloom filter
   u64 filt_words = 0;                                            // number of 16-byte blocks, power of two

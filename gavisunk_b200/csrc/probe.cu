@@ -581,8 +581,7 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   P.filt1_mask = (u32)(ctx->filt1_words - 1);
   P.blk_stream = ctx->filt_words * 16 > (32ull << 20) ? 1u : 0u;
   P.tab.keys = ctx->tab_keys.as<u64>();
-  P.tab.rows = ctx->tab_rows.as<u32>();
-  P.tab.gidx = ctx->tab_gidx.as<u32>();
+  P.tab.val = ctx->tab_gidx.as<u64>();
   P.tab.slots = ctx->tab_slots;
   P.hit_read = ctx->hit_read.as<u32>();
   P.hit_w = ctx->hit_w.as<u32>();

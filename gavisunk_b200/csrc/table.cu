@@ -138,17 +138,20 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
   return 0;
 }
 
-__global__ void k_tab_gidx(const u32* __restrict__ rows, u64 slots, const u32* __restrict__ loc_gidx, u64 n_loc, u32* gidx) {
+__global__ void k_tab_gidx(const u32* __restrict__ rows, u64 slots, const u32* __restrict__ loc_gidx, u64 n_loc, u64* val) {
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
     u32 r = rows[s];
-    gidx[s] = r < n_loc ? loc_gidx[r] : 0xFFFFFFFFu;
+    val[s] = ((u64)(r < n_loc ? loc_gidx[r] : 0xFFFFFFFFu) << 32) | r;
   }
 }
-// the group index of every slot's row next to it, so that the probe learns it with the row
+// (row, group index) of every slot in one 8-byte word, so that the probe learns both with one load;
+// the 4-byte row array of the build is released
 int gvs_tab_attach_gidx(gvs_ctx* ctx) {
-  CKR(gvs_reserve(ctx, ctx->tab_gidx, ctx->tab_slots * sizeof(u32)));
+  CKR(gvs_reserve(ctx, ctx->tab_gidx, ctx->tab_slots * sizeof(u64)));
   LAUNCH(k_tab_gidx, grid_for(ctx, ctx->tab_slots, 256), 256, 0, ctx->tab_rows.as<u32>(), ctx->tab_slots, ctx->loc_gidx.as<u32>(),
-         ctx->n_loc, ctx->tab_gidx.as<u32>());
+         ctx->n_loc, ctx->tab_gidx.as<u64>());
+  CK(cudaStreamSynchronize(ctx->stream));
+  gvs_release(ctx->tab_rows);
   return 0;
 }
 

@@ -5,15 +5,16 @@
 //                               sized to stay L2-resident (<= 64 MiB), probed once per read base
 //   tab_keys  u64[tab_slots]    open-addressed canonical k-mers, buckets of 4 slots = one 32-byte
 //                               sector, load factor <= 0.5, EMPTY = all ones (k <= 31 => < 2^62)
-//   tab_rows  u32[tab_slots]    .loc row of the key (or GVS_ROW_MISSING / GVS_ROW_NOTINDB);
+//   tab_gidx  u64[tab_slots]    low word: .loc row of the key (or GVS_ROW_MISSING / GVS_ROW_NOTINDB), high
+//                               word: the row's dense group index; one 8-byte load per key match
+//                               (tab_rows u32[tab_slots] only exists while the table is built);
 //                               touched only on a key match
 #pragma once
 #include "common.cuh"
 
 struct TabView {
   const u64* __restrict__ keys;
-  const u32* __restrict__ rows;
-  const u32* __restrict__ gidx;  // dense group index of the row's (contig, group)
+  const u64* __restrict__ val;  // low word: .loc row (or GVS_ROW_*), high word: dense group index of the row
   u64 slots;
 };
 
@@ -39,8 +40,9 @@ __device__ __forceinline__ u64 tab_find(const TabView& t, u64 key, u64 h) {
 __device__ __forceinline__ u32 tab_lookup(const TabView& t, u64 key, u64 h, u32* gidx) {
   u64 s = tab_find(t, key, h);
   if (s == ~0ull) return GVS_NOHIT;
-  *gidx = __ldg(t.gidx + s);
-  return __ldg(t.rows + s);
+  const u64 v = __ldg(t.val + s);
+  *gidx = (u32)(v >> 32);
+  return (u32)v;
 }
 
 // find-or-insert; returns slot index (never fails while load < 1)
