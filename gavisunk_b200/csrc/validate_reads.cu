@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
   extern __shared__ __align__(16) u8 smem[];
   __shared__ u32 s_n0[GROUPS], s_n1[GROUPS], s_m[GROUPS], s_kept[GROUPS], s_bestroot[GROUPS], s_flag[GROUPS], s_dup[GROUPS];
   __shared__ unsigned long long s_best[GROUPS];
+  __shared__ u32 s_wtot[GROUPS][NT / 32];  // per-warp counts of the order-preserving compaction
   const int grp = threadIdx.x / NT;
   const int tid = threadIdx.x % NT;
   auto gsync = [&]() {
@@ -94,17 +95,42 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     const u32 rd = V.read[a];
     const u32 rlen = V.read_len ? V.read_len[rd] : (u32)(V.read_off[rd + 1] - V.read_off[rd]);
     const bool skip = rlen < V.min_len || mrows < 2;
-    // ---- rows minus bad groups (:70-72); order is restored by the sort below ----
+    // ---- rows minus bad groups (:70-72), input order preserved (a read's rows come in increasing pos) ----
     if (!skip) {
-      for (u32 i = tid; i < mrows; i += NT) {
-        u32 gi = V.gidx[a + i];
-        if (V.bad && V.bad[gi]) continue;
-        u32 d = atomicAdd(&s_m[grp], 1u);
-        w.uP[d] = V.pos[a + i];
-        w.uS[d] = V.start[a + i];
-        w.uID[d] = V.group[a + i];
-        w.uG[d] = gi;
+      u32 kept_so_far = 0;
+      for (u32 base = 0; base < mrows; base += NT) {
+        const u32 i = base + tid;
+        bool keep = false;
+        u32 gi = 0;
+        if (i < mrows) {
+          gi = V.gidx[a + i];
+          keep = !(V.bad && V.bad[gi]);
+        }
+        const u32 bal = __ballot_sync(0xFFFFFFFFu, keep);
+        if (NT > 32) {
+          if ((tid & 31) == 0) s_wtot[grp][tid >> 5] = __popc(bal);
+          gsync();
+        }
+        u32 before = 0, total = __popc(bal);
+        if (NT > 32) {
+          total = 0;
+          for (int wv = 0; wv < NT / 32; wv++) {
+            u32 c = s_wtot[grp][wv];
+            before += wv < (tid >> 5) ? c : 0u;
+            total += c;
+          }
+        }
+        if (keep) {
+          const u32 d = kept_so_far + before + __popc(bal & ((1u << (tid & 31)) - 1));
+          w.uP[d] = V.pos[a + i];
+          w.uS[d] = V.start[a + i];
+          w.uID[d] = V.group[a + i];
+          w.uG[d] = gi;
+        }
+        kept_so_far += total;
+        if (NT > 32) gsync();
       }
+      if (tid == 0) s_m[grp] = kept_so_far;
     }
     gsync();
     const u32 m = s_m[grp];
@@ -113,28 +139,49 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       continue;
     }
     // ---- sort by (start, pos): sort_values(['rname','start']) is stable and rows of a read come in
-    //      increasing pos (:100) ----
+    //      increasing pos (:100).  Reads follow one strand: their starts are usually already strictly
+    //      ascending or strictly descending, which makes the sort a copy; otherwise rank sort. ----
     {
-      u32 dupl = 0;  // some group ID sits on more than one row of this read (rare: the general path below)
+      u32 not_asc = 0, not_desc = 0;
+      for (u32 i = tid; i + 1 < m; i += NT) {
+        const u32 s0 = w.uS[i], s1 = w.uS[i + 1];
+        not_asc |= s0 >= s1;
+        not_desc |= s0 <= s1;
+      }
+      if (not_asc) s_n0[grp] = 1;
+      if (not_desc) s_n1[grp] = 1;
+      gsync();
+      const u32 mono = s_n0[grp] == 0 ? 1u : (s_n1[grp] == 0 ? 2u : 0u);
+      gsync();
+      if (tid == 0) { s_n0[grp] = 0; s_n1[grp] = 0; }
       for (u32 i = tid; i < m; i += NT) {
-        const u32 si = w.uS[i], pi = w.uP[i], idi = w.uID[i];
-        u32 rank = 0;
-        for (u32 j = 0; j < m; j++) {
-          u32 sj = w.uS[j], pj = w.uP[j];
-          rank += (sj < si) | ((sj == si) & (pj < pi));
-          dupl |= (w.uID[j] == idi) & (j != i);
+        const u32 si = w.uS[i], pi = w.uP[i];
+        u32 rank = mono == 1 ? i : m - 1 - i;
+        if (mono == 0) {
+          rank = 0;
+          for (u32 j = 0; j < m; j++) {
+            u32 sj = w.uS[j], pj = w.uP[j];
+            rank += (sj < si) | ((sj == si) & (pj < pi));
+          }
         }
         w.P[rank] = pi;
         w.S[rank] = si;
-        w.ID[rank] = idi;
+        w.ID[rank] = w.uID[i];
         w.G[rank] = w.uG[i];
         w.csize[i] = 0;
         w.tv[i] = NOT64;
         w.ct[i] = NOT64;
       }
-      if (dupl) s_dup[grp] = 1;
     }
     gsync();
+    // some group ID on more than one row (rare: the general path below).  IDs are group starts, so along
+    // ascending SUNK starts they do not decrease and equal IDs are neighbours; rows that break this
+    // (hand-made input) are sent down the general path as well.
+    {
+      u32 dupl = 0;
+      for (u32 i = tid; i + 1 < m; i += NT) dupl |= w.ID[i] >= w.ID[i + 1];
+      if (dupl) s_dup[grp] = 1;
+    }
     // at least two distinct groups (:91-97)
     {
       const u32 id0 = w.ID[0];
@@ -150,36 +197,60 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     // ---- pass AB: masked pairs by sign (:140-152) and, for BOTH candidate orientations at once, the
     //      incidence of every row in the oriented edge list (the (ID,pos) multiset M) with its order of
     //      first appearance in M = [all left ends in edge order] + [all right ends]; the orientation is
-    //      only known after the whole read has been seen, so both variants are kept until then ----
+    //      only known after the whole read has been seen, so both variants are kept until then.
+    //      Rows are sorted by start, so |ds| needs no abs; partners below and above the row are walked
+    //      separately (the row is the right / the left end of the pair); when starts and positions of
+    //      the read span < 2^28 the ratio test 9*ds < 10*dp < 11*ds runs in 32-bit arithmetic. ----
     {
-      u32 n0 = 0, n1 = 0;
+      // span of the positions (starts are sorted: S[m-1] - S[0])
+      u32 pmin = 0xFFFFFFFFu, pmax = 0;
       for (u32 r = tid; r < m; r += NT) {
-        const u32 pr = w.P[r], sr = w.S[r];
-        u32 deg0 = 0, deg1 = 0, ld0 = 0, ld1 = 0, fp0 = NOV, fp1 = NOV, fh0 = NOV, fh1 = NOV;
-        for (u32 q = 0; q < m; q++) {
-          u32 pq = w.P[q], sq = w.S[q];
-          u32 hi = q > r;
-          u32 sg = hi ? (pr > pq) : (pq > pr);  // sign of the pair ordered (min, max)
-          u32 ok = pair_ok(pr, sr, pq, sq) & (q != r);
-          u32 e1 = ok & sg, e0 = ok & (sg ^ 1u);
-          deg0 += e0;
-          deg1 += e1;
-          ld0 += e0 & hi;
-          ld1 += e1 & hi;
-          fp0 = (e0 & (hi ^ 1u) & (fp0 == NOV)) ? q : fp0;  // first edge (q, r) with r as the right end
-          fp1 = (e1 & (hi ^ 1u) & (fp1 == NOV)) ? q : fp1;
-          fh0 = (e0 & hi & (fh0 == NOV)) ? q : fh0;  // first edge (r, q) with r as the left end
-          fh1 = (e1 & hi & (fh1 == NOV)) ? q : fh1;
-        }
-        // the unsorted copies are dead after the sort: they keep the first partners of both orientations
-        w.uP[r] = fp0; w.uS[r] = fh0; w.uID[r] = fp1; w.uG[r] = fh1;
-        n0 += ld0;
-        n1 += ld1;
-        w.deg[r] = deg0;
-        w.label[r] = deg1;
-        w.key[r] = ld0 ? (u64)r : ((1ull << 63) | ((u64)fp0 * m + r));
-        w.ct[r] = ld1 ? (u64)r : ((1ull << 63) | ((u64)fp1 * m + r));
+        u32 p = w.P[r];
+        pmin = p < pmin ? p : pmin;
+        pmax = p > pmax ? p : pmax;
       }
+      if (pmax >= pmin && pmax - pmin >= (1u << 28)) s_flag[grp] = 2;  // (s_flag is 1 here; 2 = wide read)
+      if (tid == 0 && w.S[m - 1] - w.S[0] >= (1u << 28)) s_flag[grp] = 2;
+      gsync();
+      const bool narrow = s_flag[grp] != 2;
+      u32 n0 = 0, n1 = 0;
+      auto walk = [&](auto ok_fn) {
+        for (u32 r = tid; r < m; r += NT) {
+          const u32 pr = w.P[r], sr = w.S[r];
+          u32 dlo0 = 0, dlo1 = 0, dhi0 = 0, dhi1 = 0, fp0 = NOV, fp1 = NOV, fh0 = NOV, fh1 = NOV;
+          for (u32 q = 0; q < r; q++) {  // pair (q, r): r is the right end; sign = pos_q > pos_r
+            const u32 pq = w.P[q], sq = w.S[q];
+            const u32 sg = pq > pr;
+            const u32 ok = ok_fn(sr - sq, sg ? pq - pr : pr - pq);
+            const u32 e1 = ok & sg, e0 = ok & (sg ^ 1u);
+            dlo0 += e0;
+            dlo1 += e1;
+            fp0 = min(fp0, q | (e0 - 1u));  // first edge (q, r) with r as the right end
+            fp1 = min(fp1, q | (e1 - 1u));
+          }
+          for (u32 q = r + 1; q < m; q++) {  // pair (r, q): r is the left end; sign = pos_r > pos_q
+            const u32 pq = w.P[q], sq = w.S[q];
+            const u32 sg = pr > pq;
+            const u32 ok = ok_fn(sq - sr, sg ? pr - pq : pq - pr);
+            const u32 e1 = ok & sg, e0 = ok & (sg ^ 1u);
+            dhi0 += e0;
+            dhi1 += e1;
+            fh0 = min(fh0, q | (e0 - 1u));  // first edge (r, q) with r as the left end
+            fh1 = min(fh1, q | (e1 - 1u));
+          }
+          // the unsorted copies are dead after the sort: they keep the first partners of both orientations
+          w.uP[r] = fp0; w.uS[r] = fh0; w.uID[r] = fp1; w.uG[r] = fh1;
+          n0 += dhi0;
+          n1 += dhi1;
+          w.deg[r] = dlo0 + dhi0;
+          w.label[r] = dlo1 + dhi1;
+          w.key[r] = dhi0 ? (u64)r : ((1ull << 63) | ((u64)fp0 * m + r));
+          w.ct[r] = dhi1 ? (u64)r : ((1ull << 63) | ((u64)fp1 * m + r));
+        }
+      };
+      // 0.9 < dpos/dstart < 1.1 in float64 (:145-147) as exact integers (Q12)
+      if (narrow) walk([](u32 ds, u32 dp) -> u32 { return (9u * ds < 10u * dp) & (10u * dp < 11u * ds); });
+      else walk([](u32 ds, u32 dp) -> u32 { return (9ull * ds < 10ull * dp) & (10ull * dp < 11ull * ds); });
       for (int d = 16; d; d >>= 1) {
         n0 += __shfl_xor_sync(0xFFFFFFFFu, n0, d);
         n1 += __shfl_xor_sync(0xFFFFFFFFu, n1, d);

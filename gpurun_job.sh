@@ -1,6 +1,6 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 for wl in h3100 s150; do
-python bench.py --workload $wl --steps 5 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/bench_${wl}_aa.json 2> gpurun_out/bench_${wl}_aa.err; echo rc=$?; tail -3 gpurun_out/bench_${wl}_aa.err
+python bench.py --workload $wl --steps 5 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/bench_${wl}_ac.json 2> gpurun_out/bench_${wl}_ac.err; echo rc=$?; tail -3 gpurun_out/bench_${wl}_ac.err
 python -c "
-import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['config']['stage_ms'], d['roofline']['frac'], d['config']['results_per_step'])" gpurun_out/bench_${wl}_aa.json
+import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['config']['stage_ms'], d['roofline']['frac'], d['config']['results_per_step'])" gpurun_out/bench_${wl}_ac.json
 done
