@@ -48,6 +48,10 @@ struct gvs_ctx {
   cudaEvent_t ev0[GVS_ST_COUNT], ev1[GVS_ST_COUNT];
   bool ev_valid[GVS_ST_COUNT];
   std::vector<void*> pinned;  // small pinned host staging blocks
+  // side streams for independent launches of one stage (e.g. the row-count tiers of the validation):
+  // gvs_fork makes them wait for everything queued on `stream`, gvs_join makes `stream` wait for them
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
   // ---- database ----
   bool db_ready = false;
@@ -171,6 +175,36 @@ static inline int gvs_fail(gvs_ctx* c, int code, const char* fmt, ...) {
       return gvs_fail(ctx, GVS_E_CUDA, "%s:%d launch %s: %s", __FILE__, __LINE__, #kern,    \
                       cudaGetErrorString(e__));                                             \
   } while (0)
+
+#define LAUNCH_ON(strm, kern, grid, block, smem, ...)                                       \
+  do {                                                                                      \
+    kern<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                                 \
+    ctx->launches++;                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                 \
+      return gvs_fail(ctx, GVS_E_CUDA, "%s:%d launch %s: %s", __FILE__, __LINE__, #kern,    \
+                      cudaGetErrorString(e__));                                             \
+  } while (0)
+
+static inline int gvs_fork(gvs_ctx* ctx) {
+  if (!ctx->aux[0]) {
+    for (int i = 0; i < 2; i++) {
+      CK(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
+  return 0;
+}
+static inline int gvs_join(gvs_ctx* ctx) {
+  for (int i = 0; i < 2; i++) {
+    CK(cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+  }
+  return 0;
+}
 
 static inline int gvs_reserve(gvs_ctx* ctx, DevBuf& b, size_t bytes) {
   if (bytes == 0) bytes = 16;

@@ -52,6 +52,14 @@ extern "C" void gvs_destroy(gvs_ctx* c) {
     cudaEventDestroy(c->ev0[i]);
     cudaEventDestroy(c->ev1[i]);
   }
+  for (int i = 0; i < 2; i++) {
+    if (c->aux[i]) {
+      cudaStreamSynchronize(c->aux[i]);
+      cudaStreamDestroy(c->aux[i]);
+    }
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (cudaEvent_t e : c->seg_ev) cudaEventDestroy(e);
   if (c->ev_reads_free) cudaEventDestroy(c->ev_reads_free);
   if (c->copy_stream) {

@@ -521,6 +521,27 @@ extern "C" int gvs_validate(gvs_ctx* ctx, uint32_t min_read_len, uint64_t* n_pai
     CK(cudaFuncSetAttribute((k_validate<256, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
     attr_set = true;
   }
+  // the three row-count tiers touch disjoint reads and outputs: they run side by side (the few very long
+  // reads of the last tier would otherwise be a serial tail)
+  const bool tiers = max_m > VCAP_WARP;
+  if (tiers) CKR(gvs_fork(ctx));
+  if (max_m > VCAP) {  // the few very long reads first: their blocks get placed before the SMs fill up
+    u32 blocks = (u32)ctx->n_sm;
+    u32 bcap = (max_m + 15) & ~15u;
+    CKR(gvs_reserve(ctx, ctx->scan_tmp2, (u64)blocks * VROW_BYTES * bcap));
+    V.gscratch = ctx->scan_tmp2.as<u8>();
+    V.big_cap = bcap;
+    V.m_lo = VCAP; V.m_hi = 0xFFFFFFFFu;
+    LAUNCH_ON(ctx->aux[1], (k_validate<1024, 1, true>), blocks, 1024, 0, V);
+    V.gscratch = nullptr; V.big_cap = 0;
+  }
+  if (max_m > VCAP_WARP) {
+    V.m_lo = VCAP_WARP; V.m_hi = VCAP;
+    u64 grid = n_seg;
+    u64 capg = (u64)ctx->n_sm * 5;
+    if (grid > capg) grid = capg;
+    LAUNCH_ON(ctx->aux[0], (k_validate<256, 1, false>), (unsigned)grid, 256, sm_blk, V);
+  }
   {  // reads with <= 64 rows: one warp each (includes the reads with < 2 rows, which just report 0)
     V.m_lo = 0; V.m_hi = VCAP_WARP;
     u64 grid = cdiv(n_seg, 8);
@@ -528,22 +549,7 @@ extern "C" int gvs_validate(gvs_ctx* ctx, uint32_t min_read_len, uint64_t* n_pai
     if (grid > capg) grid = capg;
     LAUNCH((k_validate<32, 8, false>), (unsigned)grid, 256, sm_warp, V);
   }
-  if (max_m > VCAP_WARP) {
-    V.m_lo = VCAP_WARP; V.m_hi = VCAP;
-    u64 grid = n_seg;
-    u64 capg = (u64)ctx->n_sm * 5;
-    if (grid > capg) grid = capg;
-    LAUNCH((k_validate<256, 1, false>), (unsigned)grid, 256, sm_blk, V);
-  }
-  if (max_m > VCAP) {
-    u32 blocks = (u32)ctx->n_sm;
-    u32 bcap = (max_m + 15) & ~15u;
-    CKR(gvs_reserve(ctx, ctx->scan_tmp2, (u64)blocks * VROW_BYTES * bcap));
-    V.gscratch = ctx->scan_tmp2.as<u8>();
-    V.big_cap = bcap;
-    V.m_lo = VCAP; V.m_hi = 0xFFFFFFFFu;
-    LAUNCH((k_validate<1024, 1, true>), blocks, 1024, 0, V);
-  }
+  if (tiers) CKR(gvs_join(ctx));
   // compaction of the validated (ID, read) pairs
   u32* tot = (u32*)(ctx->counters.as<u64>() + 25);
   {
