@@ -256,14 +256,35 @@ def main_b200(args):
         np_off = h_off.numpy().view(np.uint64)
         bind_h = lambda: eng.set_reads(np_reads, np_off, wl.chunk_first, wl.chunk_hap)
         run_step(eng, wl, bind_h, coll)
+        eng.pairs(pinned=True)  # warm-up also sizes the page-locked result buffers
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         f0.record()
         d2h = 0
+        split = dict(submit_copy=0.0, match=0.0, filter_validate_intervals=0.0, results_to_host=0.0)
         for _ in range(args.e2e_steps):
-            r, iv2, gaps2 = run_step(eng, wl, bind_h, coll)  # intervals + gaps come back to the host
-            pairs = eng.pairs()                               # inter_outs rows (group, read)
+            # same calls as run_step(), with host-side time stamps between them (where the e2e step goes)
+            c0 = time.perf_counter()
+            bind_h()                                          # queues the 16 H2D segments, returns at once
+            c1 = time.perf_counter()
+            eng.match()                                       # probe launches chase the copy; returns when rows exist
+            c2 = time.perf_counter()
+            eng.diag_filter(wl.contig_hap)
+            hp = eng.group_hist()
+            coll.allreduce_hist(hp, eng.db_groups())
+            eng.bad_groups()
+            eng.validate(10000)
+            pp = eng.components_local()
+            for peer in coll.gather_forests(pp, eng.db_groups()):
+                eng.components_merge(peer)
+            iv2 = eng.intervals()                             # intervals + gaps come back to the host
+            gaps2, _nd = eng.gaps(wl.contig_len.astype(np.uint32))
+            c3 = time.perf_counter()
+            pairs = eng.pairs(pinned=True)                    # inter_outs rows (group, read) into page-locked memory
+            c4 = time.perf_counter()
+            for key, dt in zip(split, (c1 - c0, c2 - c1, c3 - c2, c4 - c3)):
+                split[key] += dt * 1e3 / args.e2e_steps
             d2h = sum(a.nbytes for a in pairs.values()) + sum(a.nbytes for a in iv2.values()) + sum(a.nbytes for a in gaps2.values())
         f1.record()
         barrier()
@@ -274,7 +295,9 @@ def main_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = dict(value=total_bases * args.e2e_steps / (float(t.item()) * 1e-3) / 1e9, unit=UNIT,
                    h2d_bytes_per_step=int(wl.total_bases + 8 * (wl.n_reads + 1)), d2h_bytes_per_step=int(d2h),
-                   steps=args.e2e_steps, ms_per_step=float(t.item()) / args.e2e_steps, host_numa_node=numa.get("numa_node"))
+                   steps=args.e2e_steps, ms_per_step=float(t.item()) / args.e2e_steps, host_numa_node=numa.get("numa_node"),
+                   host_split_ms={k2: round(v, 2) for k2, v in split.items()},
+                   h2d_gbs_if_copy_bound=(wl.total_bases / 1e9) / max(split["match"] * 1e-3, 1e-9))
         del h_reads, h_off
 
     cpu_baseline = None

@@ -26,6 +26,8 @@ PROTOTYPES = {
     "gvs_set_profiling": (C.c_int, [vp, C.c_int]),
     "gvs_stage_ms": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float)]),
     "gvs_launch_count": (C.c_uint64, [vp]),
+    "gvs_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(vp)]),
+    "gvs_host_free": (None, [vp]),
     "gvs_db_load_loc": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64, C.c_uint32]),
     "gvs_db_build": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_int]),
     "gvs_db_size": (C.c_int, [vp, u64p, u64p]),

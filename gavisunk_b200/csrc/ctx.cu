@@ -110,6 +110,20 @@ extern "C" int gvs_set_copy_pipeline(gvs_ctx* ctx, uint64_t min_bytes, uint32_t 
   return 0;
 }
 
+extern "C" int gvs_host_alloc(uint64_t bytes, void** p) {
+  if (!p) return GVS_E_ARG;
+  *p = nullptr;
+  if (cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    *p = nullptr;
+    return GVS_E_NOMEM;
+  }
+  return 0;
+}
+extern "C" void gvs_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 extern "C" uint64_t gvs_launch_count(gvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* read_off, uint64_t n_reads,

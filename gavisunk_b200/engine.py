@@ -105,14 +105,39 @@ class Engine:
                                     "(gavisunk_b200 has no CPU fallback)")
         self.contig_names: List[str] = []
         self._keep = []  # host arrays that must outlive async copies
+        self._pool: Dict[str, Tuple[int, int]] = {}  # page-locked result buffers: name -> (pointer, bytes)
         if stream is not None:
             self._ck(self.lib.gvs_set_stream(self.ctx, C.c_void_p(stream)))
 
     # ------------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "ctx", None):
+            for ptr, _ in getattr(self, "_pool", {}).values():
+                self.lib.gvs_host_free(C.c_void_p(ptr))
+            self._pool = {}
             self.lib.gvs_destroy(self.ctx)
             self.ctx = None
+
+    def _out(self, name: str, n: int, dtype, pinned: bool) -> np.ndarray:
+        """result array of n elements: a fresh numpy array, or (pinned=True) a view of a page-locked buffer
+        owned by this engine that the next call with the same name overwrites (the device->host copy then
+        runs at PCIe speed instead of being staged page by page)"""
+        dt = np.dtype(dtype)
+        if not pinned:
+            return np.zeros(n, dt)
+        need = max(n * dt.itemsize, 16)
+        ptr, cap = self._pool.get(name, (0, 0))
+        if cap < need:
+            if ptr:
+                self.sync()
+                self.lib.gvs_host_free(C.c_void_p(ptr))
+            p = C.c_void_p()
+            cap = need + need // 4
+            self._ck(self.lib.gvs_host_alloc(cap, C.byref(p)))
+            ptr = int(p.value)
+            self._pool[name] = (ptr, cap)
+        buf = (C.c_uint8 * need).from_address(ptr)
+        return np.frombuffer(buf, dtype=dt, count=n)
 
     def __del__(self):
         try:
@@ -254,10 +279,10 @@ class Engine:
         self.n_rows = int(n.value)
         return self.n_rows
 
-    def rows(self, which: int = 0, n: Optional[int] = None) -> Dict[str, np.ndarray]:
+    def rows(self, which: int = 0, n: Optional[int] = None, pinned: bool = False) -> Dict[str, np.ndarray]:
         if n is None:
             n = self.n_rows if which == 0 else self.n_kept
-        out = {c: np.zeros(n, np.uint32) for c in ("read", "pos", "contig", "start", "group")}
+        out = {c: self._out(f"rows{which}.{c}", n, np.uint32, pinned) for c in ("read", "pos", "contig", "start", "group")}
         self._ck(self.lib.gvs_rows_get(self.ctx, which, _ptr(out["read"]), _ptr(out["pos"]), _ptr(out["contig"]),
                                        _ptr(out["start"]), _ptr(out["group"])))
         return out
@@ -371,9 +396,9 @@ class Engine:
         self.n_pairs = int(n.value)
         return self.n_pairs
 
-    def pairs(self) -> Dict[str, np.ndarray]:
+    def pairs(self, pinned: bool = False) -> Dict[str, np.ndarray]:
         n = self.n_pairs
-        out = {c: np.zeros(n, np.uint32) for c in ("read", "contig", "group", "gidx")}
+        out = {c: self._out(f"pairs.{c}", n, np.uint32, pinned) for c in ("read", "contig", "group", "gidx")}
         self._ck(self.lib.gvs_pairs_get(self.ctx, _ptr(out["read"]), _ptr(out["contig"]), _ptr(out["group"]),
                                         _ptr(out["gidx"])))
         return out

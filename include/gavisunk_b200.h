@@ -71,6 +71,10 @@ int gvs_sync(gvs_ctx* ctx);
  * that stage (sum of its kernels), measured with events on the context's stream. */
 int gvs_set_profiling(gvs_ctx* ctx, int on);
 int gvs_stage_ms(gvs_ctx* ctx, int stage, float* ms);
+/* Page-locked host memory for inputs / results (a *_get into pageable memory is staged by the driver and
+ * several times slower; gvs_reads_set only overlaps the copy with the probe from page-locked memory). */
+int gvs_host_alloc(uint64_t bytes, void** p);
+void gvs_host_free(void* p);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gvs_launch_count(gvs_ctx* ctx);
 

@@ -105,3 +105,15 @@ def test_validate_big_read_path():
     _, counts = np.unique(kept["read"], return_counts=True)
     assert counts.max() > 512
     _check_against_oracle(eng, wl, iv, 10000)
+
+
+def test_pinned_result_buffers_match_pageable():
+    """rows()/pairs() into the engine's page-locked pool (views reused by the next call) == fresh arrays"""
+    eng, wl, iv = _pipeline_case(seed=21, contig_lens=[200000, 90000], cov=12.0, n50=12000, min_len=3000)
+    for which in (0, 1):
+        a, b = eng.rows(which), eng.rows(which, pinned=True)
+        assert all(np.array_equal(a[c], b[c]) for c in a) and len(a["read"]) > 100
+    a, b = eng.pairs(), eng.pairs(pinned=True)
+    assert all(np.array_equal(a[c], b[c]) for c in a) and len(a["read"]) > 100
+    b2 = eng.pairs(pinned=True)  # same buffers again
+    assert b2["read"].ctypes.data == b["read"].ctypes.data
