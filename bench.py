@@ -298,6 +298,35 @@ def main_b200(args):
                    steps=args.e2e_steps, ms_per_step=float(t.item()) / args.e2e_steps, host_numa_node=numa.get("numa_node"),
                    host_split_ms={k2: round(v, 2) for k2, v in split.items()},
                    h2d_gbs_if_copy_bound=(wl.total_bases / 1e9) / max(split["match"] * 1e-3, 1e-9))
+        # ---- secondary: the same path with the host batch 2-bit packed by the ingest (gvs_pack_2bit, outside
+        #      the timed region like the parse that produces `h_reads`); NOT the headline e2e ----
+        try:
+            from gavisunk_b200.engine import pack_2bit
+            nw = (wl.total_bases + 15) // 16
+            h_words = torch.zeros(nw + 16, dtype=torch.int32, pin_memory=True)
+            np_words = h_words.numpy().view(np.uint32)
+            pack_2bit(np_reads, out=np_words)
+            bind_p = lambda: eng.set_reads_packed(np_words[:nw], np_off, wl.chunk_first, wl.chunk_hap)
+            rp, _, _ = run_step(eng, wl, bind_p, coll)
+            assert rp == res, "packed host path must reproduce the ASCII path"
+            eng.pairs(pinned=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                run_step(eng, wl, bind_p, coll)
+                eng.pairs(pinned=True)
+            barrier()
+            tp = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            e2e["packed_host_input"] = dict(value=total_bases * args.e2e_steps / (float(tp.item()) * 1e-3) / 1e9, unit=UNIT,
+                                            h2d_bytes_per_step=int(4 * nw + 8 * (wl.n_reads + 1)),
+                                            ms_per_step=float(tp.item()) / args.e2e_steps,
+                                            note="2-bit words from gvs_pack_2bit (kmer.encode's byte map, lossless for this path); "
+                                                 "packing is part of the ingest, outside the timed region")
+            del h_words
+        except Exception as ex:
+            e2e["packed_host_input"] = dict(error=repr(ex)[:200])
         del h_reads, h_off
 
     cpu_baseline = None

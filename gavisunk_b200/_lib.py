@@ -33,6 +33,7 @@ PROTOTYPES = {
     "gvs_db_size": (C.c_int, [vp, u64p, u64p]),
     "gvs_db_export": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "gvs_reads_set": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_int]),
+    "gvs_reads_set_packed": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_int]),
     "gvs_set_copy_pipeline": (C.c_int, [vp, C.c_uint64, C.c_uint32]),
     "gvs_reads_meta": (C.c_int, [vp, vp, C.c_uint64, vp, vp, C.c_uint32]),
     "gvs_rows_set": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32]),
@@ -73,12 +74,14 @@ class FastxStruct(C.Structure):
     """struct gvs_fastx of include/gavisunk_b200.h"""
     _fields_ = [("impl", C.c_void_p), ("seq", C.c_void_p), ("read_off", C.c_void_p), ("names", C.c_void_p),
                 ("name_off", C.c_void_p), ("chunk_first", C.c_void_p), ("n_reads", C.c_uint64), ("total_bases", C.c_uint64),
-                ("n_files", C.c_uint32), ("pinned", C.c_int)]
+                ("n_files", C.c_uint32), ("pinned", C.c_int), ("words", C.c_void_p), ("n_words", C.c_uint64)]
 
 
 PROTOTYPES["gvs_fastx_read"] = (C.c_int, [C.POINTER(C.c_char_p), C.c_uint32, C.c_int, C.c_int, C.POINTER(FastxStruct), C.c_char_p,
                                           C.c_uint64])
 PROTOTYPES["gvs_fastx_free"] = (None, [C.POINTER(FastxStruct)])
+PROTOTYPES["gvs_fastx_pack"] = (C.c_int, [C.POINTER(FastxStruct), C.c_int, C.c_int])
+PROTOTYPES["gvs_pack_2bit"] = (C.c_int, [vp, C.c_uint64, vp, C.c_int])
 
 GVS_E_KEYERROR = -3
 STAGES = {"probe": 0, "emit": 1, "diag": 2, "hist": 3, "validate": 4, "intervals": 5, "dbbuild": 6}

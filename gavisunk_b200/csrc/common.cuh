@@ -69,7 +69,8 @@ struct gvs_ctx {
 
   // ---- reads ----
   bool reads_ready = false;
-  const u8* seq = nullptr;     // device
+  const u8* seq = nullptr;     // device: ASCII bases, or (seq_packed) 2-bit words of 16 bases, big-endian
+  bool seq_packed = false;
   const u64* read_off = nullptr;  // device, n_reads+1
   u64 n_reads = 0, total_bases = 0;
   DevBuf own_seq, own_off;     // when copied from the host

@@ -126,9 +126,9 @@ extern "C" void gvs_host_free(void* p) {
 
 extern "C" uint64_t gvs_launch_count(gvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* read_off, uint64_t n_reads,
-                             const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks,
-                             int on_device) {
+// packed: seq holds 2-bit words (16 bases per big-endian u32, zero-padded to a whole word) instead of ASCII
+static int reads_set_impl(gvs_ctx* ctx, const uint8_t* seq, bool packed, const uint64_t* read_off, uint64_t n_reads,
+                          const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks, int on_device) {
   if (!ctx) return GVS_E_ARG;
   CK(cudaSetDevice(ctx->device));
   if (!read_off || !chunk_first || !chunk_hap || n_chunks == 0) return gvs_fail(ctx, GVS_E_ARG, "null read batch arrays");
@@ -152,16 +152,18 @@ extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* r
     ctx->read_off = read_off;
   } else {
     total = read_off[n_reads];
+    const u64 nbytes = packed ? 4 * cdiv(total, 16) : total;                  // bytes of the sequence buffer
+    const u64 tile_bytes = packed ? GVS_TILE_BASES / 4 : GVS_TILE_BASES;      // ... per probe tile
     // 64 bytes of slack: the probe kernel stages 16-byte vectors and may touch the tail
-    CKR(gvs_reserve(ctx, ctx->own_seq, total + 64));
+    CKR(gvs_reserve(ctx, ctx->own_seq, nbytes + 64));
     CKR(gvs_reserve(ctx, ctx->own_off, (n_reads + 1) * sizeof(u64)));
     CK(cudaMemcpyAsync(ctx->own_off.p, read_off, (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     ctx->seg_tile_end.clear();
     const u64 n_tiles = cdiv(total, GVS_TILE_BASES);
-    u64 n_seg = (total >= ctx->seg_min_bytes && ctx->seg_count > 1) ? ctx->seg_count : 1;
+    u64 n_seg = (nbytes >= ctx->seg_min_bytes && ctx->seg_count > 1) ? ctx->seg_count : 1;
     if (n_seg > n_tiles) n_seg = n_tiles ? n_tiles : 1;
     if (n_seg == 1) {
-      if (total) CK(cudaMemcpyAsync(ctx->own_seq.p, seq, total, cudaMemcpyHostToDevice, ctx->stream));
+      if (nbytes) CK(cudaMemcpyAsync(ctx->own_seq.p, seq, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     } else {
       if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
       if (!ctx->ev_reads_free) CK(cudaEventCreateWithFlags(&ctx->ev_reads_free, cudaEventDisableTiming));
@@ -177,8 +179,8 @@ extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* r
       for (u64 s = 0; s < n_seg; s++) {
         u64 t1 = (s + 1 == n_seg) ? n_tiles : (s + 1) * n_tiles / n_seg;
         // the probe prefetches two tiles past the end of its span (the halo of the last windows)
-        u64 c1 = (s + 1 == n_seg) ? total : (t1 + 2) * GVS_TILE_BASES;
-        if (c1 > total) c1 = total;
+        u64 c1 = (s + 1 == n_seg) ? nbytes : (t1 + 2) * tile_bytes;
+        if (c1 > nbytes) c1 = nbytes;
         if (c1 > c0) CK(cudaMemcpyAsync((u8*)ctx->own_seq.p + c0, seq + c0, c1 - c0, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(ctx->seg_ev[s], ctx->copy_stream));
         ctx->seg_tile_end.push_back(t1);
@@ -188,8 +190,18 @@ extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* r
     ctx->seq = ctx->own_seq.as<u8>();
     ctx->read_off = ctx->own_off.as<u64>();
   }
+  ctx->seq_packed = packed;
   ctx->n_reads = n_reads;
   ctx->total_bases = total;
   ctx->reads_ready = true;
   return 0;
+}
+
+extern "C" int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* read_off, uint64_t n_reads,
+                             const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks, int on_device) {
+  return reads_set_impl(ctx, seq, false, read_off, n_reads, chunk_first, chunk_hap, n_chunks, on_device);
+}
+extern "C" int gvs_reads_set_packed(gvs_ctx* ctx, const uint32_t* words, const uint64_t* read_off, uint64_t n_reads,
+                                    const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks, int on_device) {
+  return reads_set_impl(ctx, (const uint8_t*)words, true, read_off, n_reads, chunk_first, chunk_hap, n_chunks, on_device);
 }

@@ -138,6 +138,8 @@ static void parse(const std::vector<u8>& data, FileReads& out) {
 }  // namespace
 
 struct gvs_fastx_impl {
+  u32* words = nullptr;
+  bool words_pinned = false;
   std::string names;
   std::vector<u64> name_off;
   std::vector<u64> read_off;
@@ -239,9 +241,77 @@ extern "C" int gvs_fastx_read(const char* const* paths, uint32_t n_files, int th
   return 0;
 }
 
+// 2-bit codes of kmer.encode (nim-kmer 0.2.6, pinned by tests/golden/kat_bytes): A/a 0, C/c 1, G/g 2,
+// T/t/U/u 3, bytes 0x01..0x03 themselves, everything else 0 -- for this path the packing loses nothing
+static const u8* code_lut() {
+  static u8 lut[256];
+  static bool init = false;
+  if (!init) {
+    memset(lut, 0, sizeof lut);
+    lut['C'] = lut['c'] = 1;
+    lut['G'] = lut['g'] = 2;
+    lut['T'] = lut['t'] = lut['U'] = lut['u'] = 3;
+    lut[1] = 1; lut[2] = 2; lut[3] = 3;
+    init = true;
+  }
+  return lut;
+}
+
+extern "C" int gvs_pack_2bit(const uint8_t* ascii, uint64_t n, uint32_t* words, int threads) {
+  if ((n && !ascii) || !words) return GVS_E_ARG;
+  const u8* lut = code_lut();
+  const u64 nw = (n + 15) / 16;
+  if (threads < 1) threads = 1;
+  auto work = [&](u64 w0, u64 w1) {
+    for (u64 w = w0; w < w1; w++) {
+      const u64 b = w * 16;
+      u32 v = 0;
+      if (b + 16 <= n) {
+        for (int i = 0; i < 16; i++) v = (v << 2) | lut[ascii[b + i]];
+      } else {
+        for (int i = 0; i < 16; i++) v = (v << 2) | (b + i < n ? lut[ascii[b + i]] : 0);
+      }
+      words[w] = v;  // first base in the two most significant bits
+    }
+  };
+  if (threads == 1 || nw < 65536) {
+    work(0, nw);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back(work, nw * t / threads, nw * (t + 1) / threads);
+    for (auto& t : pool) t.join();
+  }
+  return 0;
+}
+
+extern "C" int gvs_fastx_pack(gvs_fastx* fx, int threads, int pin) {
+  if (!fx || !fx->impl) return GVS_E_ARG;
+  gvs_fastx_impl* R = (gvs_fastx_impl*)fx->impl;
+  if (!R->words) {
+    const u64 nw = (fx->total_bases + 15) / 16;
+    const size_t bytes = (nw + 16) * 4;
+    if (pin && cudaHostAlloc((void**)&R->words, bytes, cudaHostAllocDefault) == cudaSuccess) {
+      R->words_pinned = true;
+    } else {
+      cudaGetLastError();
+      R->words = (u32*)malloc(bytes);
+      if (!R->words) return GVS_E_NOMEM;
+    }
+    memset(R->words + nw, 0, 16 * 4);
+    int rc = gvs_pack_2bit(R->seq, fx->total_bases, R->words, threads);
+    if (rc) return rc;
+  }
+  fx->words = R->words;
+  fx->n_words = (fx->total_bases + 15) / 16;
+  return 0;
+}
+
 extern "C" void gvs_fastx_free(gvs_fastx* fx) {
   if (!fx || !fx->impl) return;
   gvs_fastx_impl* R = (gvs_fastx_impl*)fx->impl;
+  if (R->words) {
+    if (R->words_pinned) cudaFreeHost(R->words); else free(R->words);
+  }
   if (R->seq) {
     if (R->pinned) cudaFreeHost(R->seq); else free(R->seq);
   }

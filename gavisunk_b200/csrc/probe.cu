@@ -176,10 +176,19 @@ __device__ __forceinline__ u32 p_ldg_u32(const u32* ptr, u64 pol) {
   return v;
 }
 
-// asynchronous copy of the 32 x 16 ASCII bases of `tile` into sm.raw (zero beyond the end)
+// asynchronous copy of the 32 x 16 bases of `tile` into sm.raw (zero beyond the end): 16 ASCII bytes per lane,
+// or -- PACKED -- the lane's ready-made 2-bit word (gvs_reads_set_packed: 16 bases per big-endian u32)
+template <bool PACKED>
 __device__ __forceinline__ void p_stage_issue(WarpSmem& sm, const u8* __restrict__ seq, u64 tile, u64 total, int lane) {
   u64 g = tile * PW_TILE + 16ull * lane;
-  if (g + 16 <= total) {
+  if (PACKED) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.raw[lane]);
+    if (g < total) {  // the word array is padded to whole words (bases beyond `total` are zero)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"((const u32*)seq + (g >> 4)) : "memory");
+    } else {
+      sm.raw[lane].x = 0;
+    }
+  } else if (g + 16 <= total) {
     unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.raw[lane]);
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(seq + g), "l"(p_policy_stream())
                  : "memory");
@@ -191,17 +200,23 @@ __device__ __forceinline__ void p_stage_issue(WarpSmem& sm, const u8* __restrict
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
 // pack the landed bases into ring slot `rb` (forward + reverse complement)
+template <bool PACKED>
 __device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, int lane) {
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  uint4 v = sm.raw[lane];
-  u32 bad = 0;
-  u32 w = p_pack16_be_fast(v, bad);
-  if (__any_sync(0xFFFFFFFFu, bad != 0)) w = p_pack16_be(v);  // N runs, U, control bytes: the exact byte map
+  u32 w;
+  if (PACKED) {
+    w = sm.raw[lane].x;
+  } else {
+    uint4 v = sm.raw[lane];
+    u32 bad = 0;
+    w = p_pack16_be_fast(v, bad);
+    if (__any_sync(0xFFFFFFFFu, bad != 0)) w = p_pack16_be(v);  // N runs, U, control bytes: the exact byte map
+  }
   sm.fw[(rb + lane) & 63] = w;
   sm.rc[(rb + lane) & 63] = p_rc16(w);
 }
 
-template <int K>
+template <int K, bool PACKED>
 __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params P) {
   __shared__ WarpSmem sm_all[PW_WARPS];
   const int lane = threadIdx.x & 31;
@@ -244,10 +259,10 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
 
     // prologue: tiles T0 and T0+1 into ring slots 0 and 1
     __syncwarp();
-    p_stage_issue(sm, P.seq, tile0, P.total, lane);
-    p_stage_finish(sm, 0, lane);
-    p_stage_issue(sm, P.seq, tile0 + 1, P.total, lane);
-    p_stage_finish(sm, 32, lane);
+    p_stage_issue<PACKED>(sm, P.seq, tile0, P.total, lane);
+    p_stage_finish<PACKED>(sm, 0, lane);
+    p_stage_issue<PACKED>(sm, P.seq, tile0 + 1, P.total, lane);
+    p_stage_finish<PACKED>(sm, 32, lane);
     __syncwarp();
 
     u32 wcount = 0;  // hits of this span so far
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
       const u64 ts = tile * PW_TILE;
       const u32 rb = (u32)((tile - tile0) & 1) * 32;  // ring base of this tile
       // prefetch tile T+2 (lands in sm.raw while this tile is processed)
-      p_stage_issue(sm, P.seq, tile + 2, P.total, lane);
+      p_stage_issue<PACKED>(sm, P.seq, tile + 2, P.total, lane);
 
       // ---- read boundaries in (ts, ts + 512 + K - 2] ----
       const u64 limit = ts + PW_TILE + (K > 1 ? K - 1 : 1);
@@ -512,7 +527,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
       }
       // ---- tile T is done: its ring slot receives tile T+2 ----
       __syncwarp();
-      p_stage_finish(sm, rb, lane);
+      p_stage_finish<PACKED>(sm, rb, lane);
       __syncwarp();
     }
     if (lane == 0) P.warp_cnt[region] = wcount;
@@ -520,9 +535,9 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
 }
 
 typedef void (*probe_fn)(const Probe2Params);
-static probe_fn probe_table(int k) {
+static probe_fn probe_table(int k, bool packed) {
   switch (k) {
-#define PK(n) case n: return k_probe2<n>;
+#define PK(n) case n: return packed ? k_probe2<n, true> : k_probe2<n, false>;
     PK(1) PK(2) PK(3) PK(4) PK(5) PK(6) PK(7) PK(8) PK(9) PK(10) PK(11) PK(12) PK(13) PK(14) PK(15) PK(16)
     PK(17) PK(18) PK(19) PK(20) PK(21) PK(22) PK(23) PK(24) PK(25) PK(26) PK(27) PK(28) PK(29) PK(30) PK(31)
 #undef PK
@@ -535,7 +550,7 @@ static probe_fn probe_table(int k) {
 int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   u64 total = ctx->total_bases;
   u64 n_tiles = cdiv(total, PW_TILE);
-  probe_fn fn = probe_table(ctx->k);
+  probe_fn fn = probe_table(ctx->k, ctx->seq_packed);
   if (!fn) return gvs_fail(ctx, GVS_E_ARG, "no probe kernel for k=%d", ctx->k);
   u64* counters = ctx->counters.as<u64>();
   Probe2Params P;

@@ -110,9 +110,19 @@ class NativeReads:
     def lengths(self) -> np.ndarray:
         return np.diff(self.read_off).astype(np.uint64)
 
+    def pack(self, threads: int = 0, pin: bool = True) -> np.ndarray:
+        """2-bit words of the batch (gvs_fastx_pack) for Engine.set_reads_packed; view of library memory"""
+        import ctypes as C
+        rc = self._lib.gvs_fastx_pack(C.byref(self._fx), threads or (os.cpu_count() or 1), 1 if pin else 0)
+        if rc != 0:
+            raise MemoryError("gvs_fastx_pack failed")
+        n = int(self._fx.n_words)
+        self.words = np.ctypeslib.as_array(C.cast(self._fx.words, C.POINTER(C.c_uint32)), shape=(n,)) if n else np.zeros(0, np.uint32)
+        return self.words
+
     def close(self):
         if getattr(self, "_fx", None) is not None:
-            self.seq = self.read_off = None
+            self.seq = self.read_off = self.words = None
             self._lib.gvs_fastx_free(self._fx)
             self._fx = None
 

@@ -122,10 +122,18 @@ typedef struct gvs_fastx {
   uint64_t n_reads, total_bases;
   uint32_t n_files;
   int pinned;
+  const uint32_t* words;       /* after gvs_fastx_pack: the same bases as 2-bit words (see gvs_reads_set_packed) */
+  uint64_t n_words;
 } gvs_fastx;
 int gvs_fastx_read(const char* const* paths, uint32_t n_files, int threads, int pin, gvs_fastx* out,
                    char* err, uint64_t err_len);
 void gvs_fastx_free(gvs_fastx* fx);
+/* kmer.encode's byte map (nim-kmer 0.2.6: A/a 0, C/c 1, G/g 2, T/t/U/u 3, bytes 1..3 themselves, everything
+ * else 0 -- workflow/src/kmerpos_annot3.nim:88 `slide`) applied on the host: n ASCII bases -> ceil(n/16)
+ * big-endian words of 16 bases (first base in the top two bits, tail zero-padded).  Lossless for this path
+ * and a quarter of the bytes to move over PCIe.  gvs_fastx_pack does it for a parsed batch (page-locked). */
+int gvs_pack_2bit(const uint8_t* ascii, uint64_t n, uint32_t* words, int threads);
+int gvs_fastx_pack(gvs_fastx* fx, int threads, int pin);
 
 /* ------------------------------------------------------------------------------------------ */
 /* A batch = the reads of one or more chunk files (temp/{sample}/reads/{hap}_{i-of-N}.fq.gz,
@@ -142,6 +150,12 @@ void gvs_fastx_free(gvs_fastx* fx);
 int gvs_reads_set(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* read_off, uint64_t n_reads,
                   const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks,
                   int on_device);
+
+/* The same batch with the bases already packed by gvs_pack_2bit / gvs_fastx_pack (words: ceil(total/16)
+ * uint32; read_off still counts bases).  The probe then skips its own ASCII -> 2-bit step. */
+int gvs_reads_set_packed(gvs_ctx* ctx, const uint32_t* words, const uint64_t* read_off, uint64_t n_reads,
+                         const uint64_t* chunk_first, const uint8_t* chunk_hap, uint32_t n_chunks,
+                         int on_device);
 
 /* Host batches of at least `min_bytes` are copied in `segments` pieces on a second stream and the
  * probe of each piece starts as soon as it has landed (PCIe transfer overlapped with the match).

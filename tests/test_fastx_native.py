@@ -75,3 +75,26 @@ def test_large_multiline_fasta_and_fastq(tmp_path):
     fa = b"".join(b">" + n.encode() + b" d\n" + b"\n".join(s[i:i + 61] for i in range(0, len(s), 61)) + b"\n" for n, s in recs)
     fq = b"".join(b"@" + n.encode() + b"\n" + s + b"\n+\n" + b"@" * len(s) + b"\n" for n, s in recs)
     _check(tmp_path, [fa, fq, fa], gz={1, 2})
+
+
+def test_pack_2bit_is_kmer_encode_byte_map(tmp_path):
+    """gvs_pack_2bit / NativeReads.pack() against the byte map the reference's kmer.encode applies (pinned
+    by tests/golden/kat_bytes through the ELF): all 256 byte values, ragged tails, multi-threaded split"""
+    import gavisunk_oracle as O
+    from gavisunk_b200.engine import pack_2bit
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 15, 16, 17, 255, 256, 4099, 1_200_003):
+        seq = rng.integers(0, 256, n, dtype=np.uint8) if n < 5000 else rng.choice(np.frombuffer(b"ACGTNacgtnU\x01\x02\x03-", np.uint8), n)
+        got = pack_2bit(seq, threads=3)
+        codes = O.codes_of(seq.tobytes()).astype(np.uint64)
+        pad = np.zeros((-n) % 16, np.uint64)
+        c = np.concatenate([codes, pad]).reshape(-1, 16)
+        want = np.zeros(len(c), np.uint64)
+        for i in range(16):
+            want = (want << np.uint64(2)) | c[:, i]
+        assert np.array_equal(got, want.astype(np.uint32)), n
+    fa = b">a\nACGTNNacgtu\n>b\n\n>c\n" + b"GATTACA" * 9 + b"\n"
+    p = tmp_path / "x.fa"
+    p.write_bytes(fa)
+    nr = gio.NativeReads([str(p)], pin=False)
+    assert np.array_equal(nr.pack(pin=False), pack_2bit(nr.seq))

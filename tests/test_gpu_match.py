@@ -48,3 +48,23 @@ def test_match_copy_pipeline(name, segments):
     for _ in range(2):  # second round re-uses the segment events and overwrites the resident batch
         got = run_match_chunks(eng, names, chunks)
         assert got == want
+
+
+@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes", "rand_k20", "rand_k16", "rand_k31", "rand_k20_many"])
+@pytest.mark.parametrize("segments", [1, 5])
+def test_match_packed_host_reads(name, segments):
+    """bases packed to 2 bits on the host (gvs_pack_2bit = kmer.encode's byte map) and matched by the PACKED
+    probe variant: rows identical to the reference ELF output, with and without the copy pipeline"""
+    from conftest import pack_chunks, format_rows
+    from gavisunk_b200.engine import pack_2bit
+    case = load_golden(name)
+    eng, names = engine_from_case(case)
+    eng.set_copy_pipeline(0, segments)
+    chunks = [ch["reads"] for ch in case["chunks"]] if "chunks" in case else [case["reads"]]
+    want = [ch["sunkpos"] for ch in case["chunks"]] if "chunks" in case else [case["out"]]
+    rnames, seq, off, chunk_first = pack_chunks(chunks)
+    eng.set_reads_packed(pack_2bit(seq), off, chunk_first, [0] * len(chunks))
+    eng.match()
+    rows = eng.rows(0)
+    got = [format_rows(rows, rnames, names, chunk_first[i], chunk_first[i + 1]) for i in range(len(chunks))]
+    assert got == want
