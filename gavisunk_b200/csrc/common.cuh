@@ -93,7 +93,8 @@ struct gvs_ctx {
   bool groups_ready = false;   // grp_contig / grp_start / n_groups valid (database or rows-derived)
 
   // ---- match ----
-  DevBuf tile_first, tile_cnt, tile_off, tile_dst;
+  DevBuf tile_first;                  // DB build: first contig of every tile
+  DevBuf tile_cnt, tile_off, tile_dst;  // probe spans: record count, span counters of the launches, dense destination
   // hit records: the first hit of a run of consecutive hits on ONE group inside one read (and one probe
   // tile), with the number of hits that follow it in the run -- kmerpos_annot3 prints only the first
   // (nim:92) and the others merely shift later positions (Q3)

@@ -1,12 +1,11 @@
 // match.cu -- SUNK matching of reads: the GPU replacement of kmerpos_annot3's main loop
 // (workflow/src/kmerpos_annot3.nim:81-97).
 //
-//   k_tile_index   first read boundary after each 4096-base tile (binary search, tiny)
-//   k_probe        ★ hot kernel: 128-bit coalesced loads of ASCII bases -> 2-bit packed tile in
-//                  shared memory -> rolling forward / reverse-complement k-mer per thread strip ->
-//                  canonical min -> L2-resident blocked-Bloom word -> (rare) exact 32-byte bucket
-//                  probe in HBM -> hits appended per tile, in position order inside the tile
-//   k_gather_hits  tiles' hit runs copied into global position order (scan of tile counts)
+//   k_probe2       (probe.cu) ★ hot kernel: every k-mer window of every read through the presence filter,
+//                  the blocked Bloom filter and the exact table; emits hit RECORDS (first hit of a run of
+//                  consecutive hits on one SUNK group inside a read + number of followers) into one
+//                  region per probe span, in position order
+//   k_gather_hits  span regions copied into one dense array in global position order (scan of span counts)
 //   k_emit_flags / scans / k_emit_rows
 //                  consecutive-(contig,group) suppression across the whole chunk (prevLoc is
 //                  never reset between reads, Q4) and the position drift it causes (Q3)
