@@ -76,6 +76,26 @@ __global__ void __launch_bounds__(256) k_db_tile_index(const u64* __restrict__ o
   tile_first[t] = (u32)lo;
 }
 
+// find-or-insert into the count table: buckets of 4 slots, ANY bucket count (multiply-shift range reduction
+// instead of a mask, so that the table can be sized to the memory that is free rather than to a power of
+// two -- half as many passes over a 6.2 Gbp assembly)
+__device__ __forceinline__ u64 cnt_insert(u64* keys, u64 n_buckets, u64 key, u64 h) {
+  u64 b = ((h >> 32) * n_buckets) >> 32;
+  for (;;) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      u64 s = (b << 2) + j;
+      u64 cur = keys[s];
+      if (cur == key) return s;
+      if (cur == GVS_EMPTY_KEY) {
+        u64 old = atomicCAS((unsigned long long*)&keys[s], (unsigned long long)GVS_EMPTY_KEY, (unsigned long long)key);
+        if (old == GVS_EMPTY_KEY || old == key) return s;
+      }
+    }
+    b = b + 1 == n_buckets ? 0 : b + 1;
+  }
+}
+
 struct DbCountParams {
   const u8* __restrict__ seq;
   u64 total;
@@ -153,8 +173,8 @@ __global__ void __launch_bounds__(DT, 2) k_db_count(const DbCountParams P) {
       if (ok && k < 32) {
         u64 c = f < r ? f : r;
         u64 h = gvs_mix(c);
-        if (P.n_parts == 1 || (u32)(h >> 59) % P.n_parts == P.part) {
-          u64 s = tab_insert(P.keys, P.slots, c, h);
+        if (P.n_parts == 1 || (u32)h % P.n_parts == P.part) {  // low hash bits pick the pass, high bits the bucket
+          u64 s = cnt_insert(P.keys, P.slots >> 2, c, h);
           u64 old = atomicCAS((unsigned long long*)&P.vals[s], (unsigned long long)VAL_EMPTY, (unsigned long long)(p0 + i));
           if (old != VAL_EMPTY && !(old & VAL_DUP)) atomicOr((unsigned long long*)&P.vals[s], (unsigned long long)VAL_DUP);
         }
@@ -268,10 +288,11 @@ static int db_build_device(gvs_ctx* ctx, const u8* seq, const u64* contig_off, u
   u32 n_parts = 1;
   u64 slots;
   for (;;) {
-    slots = next_pow2((total / n_parts) * 3 / 2 + 1024);
-    if (slots * 16 <= budget || n_parts >= 32) break;
-    n_parts *= 2;
+    slots = (((total / n_parts) * 3 / 2 + 1024) + 3) & ~3ull;  // load <= 2/3, whole buckets of 4
+    if (slots * 16 <= budget || n_parts >= 64) break;
+    n_parts += 1;
   }
+  if ((slots >> 2) >= (1ull << 32)) return gvs_fail(ctx, GVS_E_OVERFLOW, "SUNK count table has too many buckets");
   if (slots * 16 > budget) return gvs_fail(ctx, GVS_E_NOMEM, "SUNK count table does not fit (%llu slots)", (unsigned long long)slots);
   CKR(gvs_reserve(ctx, keys, slots * 8));
   CKR(gvs_reserve(ctx, vals, slots * 8));
