@@ -1,6 +1,5 @@
-python -m pytest tests/test_gpu_db.py -m gpu -x -q 2>&1 | tail -3
-for wl in h3100 s150; do
-python bench.py --workload $wl --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/bench_${wl}_ai.json 2> gpurun_out/bench_${wl}_ai.err; echo rc=$?; tail -3 gpurun_out/bench_${wl}_ai.err
+for n in 8 4 2; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_h3100_n${n}_r1aj.json 2> gpurun_out/bench_h3100_n${n}_r1aj.err; echo rc=$?; tail -3 gpurun_out/bench_h3100_n${n}_r1aj.err | cut -c1-300
 python -c "
-import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], 'db_build_ms', d['config']['db_build_ms'], d['config']['n_sunks'], d['config']['results_per_step']['rows'])" gpurun_out/bench_${wl}_ai.json
+import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(d['n_gpus'], d['value'], d['ms_per_step'], d['config']['stage_ms'], d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e']['packed_host_input'].get('value'), d['config']['results_per_step'])" gpurun_out/bench_h3100_n${n}_r1aj.json
 done
