@@ -202,6 +202,52 @@ def random_case(seed, k, n_contigs, L, n_reads, mean_len, nchunks=2):
     return case
 
 
+def ragged_case(seed, k):
+    """reads that stress the tile / boundary logic of a batched matcher: empty reads, reads of length 1 .. k+3
+    (k-1 is the bogus-window quirk Q6, k is the shortest real window), hundreds of tiny reads per 512 bases,
+    error-free copies (every SUNK of a group hits: long runs of suppressed hits, position drift Q3), reads that
+    end in N, mixed case; one FASTA chunk and one FASTQ chunk, through the reference executables"""
+    rng = np.random.default_rng(seed)
+    hap1, hap2 = make_asm(rng, 2, 6000)
+    contigs = hap1 + hap2
+    db_txt, loc_txt = db_loc_text(contigs, k)
+    case = dict(k=k, db=db_txt, loc=loc_txt,
+                fai1="".join(f"{n}\t{len(s)}\t0\t60\t61\n" for n, s in hap1),
+                fai2="".join(f"{n}\t{len(s)}\t0\t60\t61\n" for n, s in hap2), chunks=[])
+    for hapi, hap in ((1, hap1), (2, hap2)):
+        reads = []
+        a = np.frombuffer(hap[0][1], dtype=np.uint8)
+        b = np.frombuffer(hap[1][1], dtype=np.uint8)
+        for i in range(420):
+            src = a if i % 3 else b
+            if i % 10 == 0:
+                ln = [0, 1, k - 2, k - 1, k - 1, k, k, k + 1, k + 3, 2 * k][(i // 10) % 10]
+            elif i % 10 < 7:
+                ln = int(rng.integers(1, 3 * k))
+            else:
+                ln = int(rng.integers(200, 1500))
+            st = int(rng.integers(0, len(src) - ln + 1))
+            r = src[st:st + ln].copy()          # error-free: dense runs of hits
+            if i % 4 == 1 and ln > 60:
+                r = mutate(rng, r)
+            if i % 2:
+                r = rc_bytes(r)
+            if i % 9 == 4 and len(r) > 5:
+                r[-3:] = ord("N")
+            if i % 7 == 2:
+                r = np.frombuffer(r.tobytes().lower(), dtype=np.uint8)
+            reads.append((f"g{hapi}r{i:04d}", r.tobytes()))
+        for ci in range(2):
+            part = reads[ci::2]
+            txt = fasta_text(part, fastq=(ci == 1))
+            rc, sunkpos = run_kmerpos(txt, db_txt, loc_txt)
+            assert rc == 0
+            diag, diag2 = run_diag(sunkpos, case["fai1"] if hapi == 1 else case["fai2"])
+            case["chunks"].append(dict(hap=hapi, reads=txt.decode("latin-1"), sunkpos=sunkpos, diag=diag, diag2=diag2,
+                                       rlen=run_rlen(txt)))
+    return case
+
+
 def diag_cases():
     cases = []
     fai = "cA\t1000000\t0\t60\t61\ncB\t1000000\t0\t60\t61\nchr1\t1\t0\t60\t61\nchr2\t1\t0\t60\t61\n"
@@ -320,6 +366,9 @@ def main():
     save("rand_k24", random_case(103, 24, 3, 6000, 14, 2500))
     save("rand_k31", random_case(104, 31, 1, 9000, 10, 3000))
     save("rand_k20_many", random_case(105, 20, 6, 5000, 30, 6000, nchunks=3))
+    save("ragged_k20", ragged_case(106, 20))
+    save("ragged_k31", ragged_case(107, 31))
+    save("ragged_k16", ragged_case(108, 16))
 
 
 if __name__ == "__main__":

@@ -18,7 +18,7 @@ def _fmt_best(best, read_names, contig_names, lo, hi):
     return "".join(out)
 
 
-@pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many"])
+@pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31", "ragged_k16"])
 def test_diag_after_match(name):
     case = load_golden(name)
     eng, names = engine_from_case(case)

@@ -16,7 +16,7 @@ def test_match_kats(name):
     assert got[0] == case["out"]
 
 
-@pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many"])
+@pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31", "ragged_k16"])
 def test_match_random_per_chunk(name):
     case = load_golden(name)
     eng, names = engine_from_case(case)
@@ -25,7 +25,7 @@ def test_match_random_per_chunk(name):
         assert got[0] == ch["sunkpos"]
 
 
-@pytest.mark.parametrize("name", ["rand_k20", "rand_k20_many"])
+@pytest.mark.parametrize("name", ["rand_k20", "rand_k20_many", "ragged_k20", "ragged_k31"])
 def test_match_random_batched_chunks(name):
     """all chunk files of a sample in ONE batch: the prevLoc carry must restart per chunk (Q4)"""
     case = load_golden(name)
@@ -35,7 +35,7 @@ def test_match_random_batched_chunks(name):
         assert g == ch["sunkpos"]
 
 
-@pytest.mark.parametrize("name", ["rand_k20", "rand_k31", "rand_k20_many", "kat_bytes"])
+@pytest.mark.parametrize("name", ["rand_k20", "rand_k31", "rand_k20_many", "kat_bytes", "ragged_k20", "ragged_k16"])
 @pytest.mark.parametrize("segments", [2, 7, 64])
 def test_match_copy_pipeline(name, segments):
     """host batch copied in segments on the copy stream, one probe launch per segment
@@ -50,7 +50,7 @@ def test_match_copy_pipeline(name, segments):
         assert got == want
 
 
-@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes", "rand_k20", "rand_k16", "rand_k31", "rand_k20_many"])
+@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes", "rand_k20", "rand_k16", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31"])
 @pytest.mark.parametrize("segments", [1, 5])
 def test_match_packed_host_reads(name, segments):
     """bases packed to 2 bits on the host (gvs_pack_2bit = kmer.encode's byte map) and matched by the PACKED

@@ -41,7 +41,7 @@ def test_rlen_b8():
     assert "".join(f"{n}\t{len(s)}\n" for n, s in reads) == case["rlen"]
 
 
-@pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many"])
+@pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31", "ragged_k16"])
 def test_match_and_diag_random(name):
     case = load_golden(name)
     db, loc = _parse_db_loc(case)
