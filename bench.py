@@ -512,16 +512,21 @@ def main_reference(args):
     torch.cuda.set_device(0)
     eng = Engine(args.k, device=0)
     wl = build_workload(args, eng, 0)
-    steps = max(1, min(args.steps, 2))
+    # every step = the reference pipeline on a bounded sample (~8 s on 16 cores, most of it each process loading
+    # the SUNK table from text); K steps are run unless that would take more than ~2.5 minutes in total
     vals, last = [], None
     for _ in range(min(args.warmup, 1)):
         cpu_reference_sample(args, wl, eng, per_proc_mbp=args.cpu_sample_mbp or 4.0)
-    for _ in range(steps):
+    t_begin = time.perf_counter()
+    for _ in range(max(1, args.steps)):
         last = cpu_reference_sample(args, wl, eng, per_proc_mbp=args.cpu_sample_mbp or 12.0)
         if "value" not in last:
             print(json.dumps({"impl": "reference", "unavailable": last.get("error", "reference run failed")}))
             return
         vals.append(last["value"])
+        if time.perf_counter() - t_begin > 150.0:
+            break
+    steps = len(vals)
     v = float(np.mean(vals))
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps,
            "warmup": min(args.warmup, 1), "ms_per_step": last["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
