@@ -16,11 +16,17 @@ Parity pinning (see DESIGN.md "Oracle"):
     (``README.md:36``  AMY_h1 284861/324276 adjacent group starts) -- otherwise the third-party
     tools (jellyfish 2.3.0, mrsfast 3.4.2, bedtools 2.30.0) are absent: "parity pinned at 2
     coordinates + published tool semantics".
-  * Python stages (a10, a12, a13, a15, a16): the reference scripts cannot be imported here
-    (graph_tool / pyranges / snakemake absent, pandas 3 vs pinned 1.3.4) -> restated line by
-    line; component *sets*, merged intervals and the covprob root are mathematically determined;
-    the tie rules that are not (pandas value_counts tie order, graph-tool largest-component
-    tie) follow SURVEY.md A.6 and are marked "parity unpinned" where they matter.
+  * Python stages (a10-a13, a15, a16): pinned against the reference's OWN scripts
+    (``workflow/scripts/{badsunks_AR,split_locs,process-by-contig_lowmem_AR,get_gaps,covprob}.py``),
+    run unmodified by ``tests/golden/make_golden_py.py`` on sunkpos rows produced by the reference
+    executables; outputs committed as ``tests/golden/pystages_*.json.gz`` and checked by
+    ``tests/test_oracle_pystages.py``.  graph-tool, pyranges, matplotlib and seaborn cannot be
+    installed in the build container, so the scripts run against minimal stand-ins for exactly the
+    calls they make (``tests/golden/refpy_stubs``), with pandas-1.3 behaviours restored by
+    ``refpy_compat.py``; sympy / scipy / numpy / pandas are real.  What stays unpinned are tie rules
+    that live INSIDE those third-party packages (pandas 1.3 ``value_counts`` tie order in the
+    "multipos" clean-up, graph-tool's choice among equally large components, pyranges' row order):
+    they follow SURVEY.md A.6 / the packages' documented behaviour.
 
 All citations are file:line relative to /root/reference/.
 """

@@ -150,3 +150,59 @@ def test_covprob_lookup_and_errors(tmp_path):
     loc3 = _w(tmp_path / "k3.loc", "chr2\t10\tAAA\t10\nchr2\t3600000\tCCC\t3600000\n")
     bed3 = _w(tmp_path / "g3.bed", "chr2\t11\t3599999\n")
     assert cli.main(["covprob", "--bed", bed3, "--locs", loc3, "--rlen", rl, "--fai", fai, "--sunk-len", str(k), "--tsv", str(tmp_path / "o3.tsv")]) == 1
+
+
+@pytest.mark.parametrize("name", ["pystages_a", "pystages_b"])
+def test_shims_against_reference_python_scripts(tmp_path, name):
+    """every per-rule shim against the files the reference's OWN Python scripts wrote for the same inputs
+    (tests/golden/pystages_*.json.gz, see tests/golden/make_golden_py.py): bad_sunks.txt as a set, breaks/,
+    inter_outs/, bed_files/, gaps / nodata BEDs byte for byte, covprob within 1e-6"""
+    from conftest import load_golden
+    c = load_golden(name)
+    for sub in ("sunkpos", "breaks", "inter_outs", "bed_files", "final_out"):
+        os.makedirs(tmp_path / sub)
+    P = lambda *a: str(tmp_path.joinpath(*a))
+    _w(tmp_path / "kmer.loc", c["loc"])
+    for h in ("1", "2"):
+        _w(tmp_path / "sunkpos" / f"hap{h}.sunkpos", c["hap"][h]["sunkpos"])
+        _w(tmp_path / "sunkpos" / f"hap{h}.rlen", c["hap"][h]["rlen"])
+        _w(tmp_path / f"hap{h}.fai", c[f"fai{h}"])
+    assert cli.main(["badsunks_AR", P("hap1.fai"), P("hap2.fai"), P("sunkpos", "hap1.sunkpos"), P("sunkpos", "hap2.sunkpos"),
+                     P("sunkpos", "bad_sunks.txt")]) == 0
+    assert sorted(open(P("sunkpos", "bad_sunks.txt")).read().split()) == c["bad_sunks"]
+    for h in ("1", "2"):
+        assert cli.main(["split_locs", "--ont-pos", P("sunkpos", f"hap{h}.sunkpos"), "--kmer-loc", P("kmer.loc"),
+                         "--flag", P("breaks", f"hap{h}_splits_pos.done"), "--hap", f"hap{h}"]) == 0
+    for fn, txt in c["breaks"].items():
+        assert open(P("breaks", fn)).read() == txt, fn
+    for stem, tsv in c["inter_outs"].items():
+        h = stem[-1]
+        assert cli.main(["process_by_contig", P("breaks", stem + ".loc"), P("breaks", stem + ".sunkpos"), P("sunkpos", f"hap{h}.rlen"),
+                         P("sunkpos", "bad_sunks.txt"), P("inter_outs", stem + ".tsv"), P("bed_files", stem + ".bed")]) == 0
+        assert open(P("inter_outs", stem + ".tsv")).read() == tsv, stem
+        if c["bed_files"][stem] is None:
+            assert not os.path.exists(P("bed_files", stem + ".bed"))
+            open(P("bed_files", stem + ".bed"), "w").close()  # `touch {output.bed}`
+        else:
+            assert open(P("bed_files", stem + ".bed")).read() == c["bed_files"][stem], stem
+    assert cli.main(["get_gaps", P("hap1.fai"), P("hap2.fai"), "sample", P("bed_files") + "/", P("final_out") + "/"]) == 0
+    n_cov = 0
+    for h in ("1", "2"):
+        for f in ("gaps.bed", "nodata.bed"):
+            assert open(P("final_out", f"hap{h}.{f}")).read() == c["final_out"][f"hap{h}.{f}"], f
+        rc = cli.main(["covprob", "--bed", P("final_out", f"hap{h}.gaps.bed"), "--locs", P("kmer.loc"), "--rlen", P("sunkpos", f"hap{h}.rlen"),
+                       "--fai", P(f"hap{h}.fai"), "--sunk-len", str(c["k"]), "--tsv", P("final_out", f"hap{h}.covprob.tsv")])
+        want = c["final_out"][f"hap{h}.gaps.covprob.tsv"]
+        if c["final_out"][f"hap{h}.covprob_rc"] != 0:
+            assert rc == 1
+            continue
+        assert rc == 0
+        got = open(P("final_out", f"hap{h}.covprob.tsv")).read().splitlines()
+        wl = want.splitlines()
+        assert got[0] == wl[0] and len(got) == len(wl)
+        for a, b in zip(got[1:], wl[1:]):
+            a, b = a.split("\t"), b.split("\t")
+            assert a[:6] == b[:6]
+            assert float(a[6]) == pytest.approx(float(b[6]), rel=1e-6, abs=1e-15)
+            n_cov += 1
+    assert n_cov >= 1
