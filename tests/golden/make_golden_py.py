@@ -45,7 +45,7 @@ def read(path):
     return open(path).read() if os.path.exists(path) else None
 
 
-def elf_case(seed, k, n_contigs, L, n_reads, mean_len):
+def elf_case(seed, k, n_contigs, L, n_reads, mean_len, tandem=0.0):
     """diploid toy assembly + reads through the reference executables; the read set is shaped so that the
     Python stages have something to decide: no read touches the window [40 %, 46 %) of contig 0 (two validated
     intervals with a gap between them), the last contig gets no reads at all when there are >= 3 (nodata), a
@@ -68,6 +68,12 @@ def elf_case(seed, k, n_contigs, L, n_reads, mean_len):
             if ci == 0 and st < 0.46 * len(a) and st + ln > 0.40 * len(a):
                 continue
             r = M.mutate(rng, a[st:st + ln])
+            if rng.random() < tandem and ln > 6000:
+                # the read repeats a stretch of itself (and once more, shifted): the same SUNK groups at two or three
+                # read positions -> the "multipos" clean-up of process-by-contig_lowmem_AR.py:161-181
+                s0 = int(rng.integers(0, ln // 2))
+                seg = a[st + s0:st + s0 + int(rng.integers(2000, ln // 2))]
+                r = np.concatenate([r, M.mutate(rng, seg)] + ([M.mutate(rng, seg[len(seg) // 3:])] if rng.random() < 0.5 else []))
             if rng.random() < 0.5:
                 r = M.rc_bytes(r)
             reads.append((f"h{hapi}r{i:05d}", r.tobytes()))
@@ -85,9 +91,9 @@ def elf_case(seed, k, n_contigs, L, n_reads, mean_len):
     return case
 
 
-def pipeline_case(seed, k, n_contigs, L, n_reads, mean_len):
+def pipeline_case(seed, k, n_contigs, L, n_reads, mean_len, tandem=0.0):
     # match + diag through the reference executables, then the Python scripts
-    base = elf_case(seed, k, n_contigs, L, n_reads, mean_len)
+    base = elf_case(seed, k, n_contigs, L, n_reads, mean_len, tandem)
     case = dict(k=k, loc=base["loc"], fai1=base["fai1"], fai2=base["fai2"], hap={})
     with tempfile.TemporaryDirectory() as d:
         for sub in ("sunkpos", "breaks", "inter_outs", "bed_files", "final_out"):
@@ -139,7 +145,11 @@ def pipeline_case(seed, k, n_contigs, L, n_reads, mean_len):
 
 
 def main():
-    for name, args in (("pystages_a", (211, 20, 2, 90000, 60, 16000)), ("pystages_b", (212, 24, 3, 50000, 50, 14000))):
+    only = sys.argv[1:]
+    for name, args in (("pystages_a", (211, 20, 2, 90000, 60, 16000)), ("pystages_b", (212, 24, 3, 50000, 50, 14000)),
+                       ("pystages_c", (213, 20, 2, 70000, 70, 15000, 0.5))):
+        if only and name not in only:
+            continue
         c = pipeline_case(*args)
         M.save(name, c)
         print(name, "bad", len(c["bad_sunks"]), "inter", {k: (v or "").count("\n") for k, v in c["inter_outs"].items()},

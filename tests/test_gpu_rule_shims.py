@@ -152,7 +152,7 @@ def test_covprob_lookup_and_errors(tmp_path):
     assert cli.main(["covprob", "--bed", bed3, "--locs", loc3, "--rlen", rl, "--fai", fai, "--sunk-len", str(k), "--tsv", str(tmp_path / "o3.tsv")]) == 1
 
 
-@pytest.mark.parametrize("name", ["pystages_a", "pystages_b"])
+@pytest.mark.parametrize("name", ["pystages_a", "pystages_b", "pystages_c"])
 def test_shims_against_reference_python_scripts(tmp_path, name):
     """every per-rule shim against the files the reference's OWN Python scripts wrote for the same inputs
     (tests/golden/pystages_*.json.gz, see tests/golden/make_golden_py.py): bad_sunks.txt as a set, breaks/,

@@ -8,7 +8,7 @@ import gavisunk_oracle as O
 from conftest import load_golden
 from gavisunk_b200 import io as gio
 
-CASES = ["pystages_a", "pystages_b"]
+CASES = ["pystages_a", "pystages_b", "pystages_c"]
 
 
 def _fai(txt):
