@@ -216,7 +216,9 @@ __device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, int lane) {
   sm.rc[(rb + lane) & 63] = p_rc16(w);
 }
 
-template <int K, bool PACKED>
+// SMALL: the blocked filter is L2-resident (<= 32 MiB): few groups pass the presence gate, one window round
+// is the rule and gets a path without the multi-round bookkeeping
+template <int K, bool PACKED, bool SMALL>
 __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params P) {
   __shared__ WarpSmem sm_all[PW_WARPS];
   const int lane = threadIdx.x & 31;
@@ -394,6 +396,18 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         __syncwarp();
         const u32 n_ent = n_grp * J;
         constexpr int RB = 4;  // rounds whose block loads are issued back to back before any window math
+        if (SMALL && n_ent <= 32) {
+          if ((u32)lane < n_ent) {
+            const u32 q = lane / J, w = lane % J;
+            const u32 p = (u32)sm.q_p[q] * J + w;
+            const uint4 b4 = p_ldg_v4((const uint4*)P.filt + (sm.q_row[q] & P.filt_mask), pol_blk);
+            const bool valid = !((sm.inv[p >> 4] >> (p & 15)) & 1u);
+            const u32 h = gvs_fhash(p_canon_at<K>(sm, rb, p, false));
+            const u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
+                          __funnelshift_r(b4.w, 0u, h >> 15);
+            if (valid && (t & 1u)) atomicOr(&sm.cand[p >> 5], 1u << (p & 31));
+          }
+        } else
         for (u32 base = 0; base < n_ent; base += 32 * RB) {
           uint4 b4[RB];
           u32 pw[RB];
@@ -535,9 +549,10 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
 }
 
 typedef void (*probe_fn)(const Probe2Params);
-static probe_fn probe_table(int k, bool packed) {
+static probe_fn probe_table(int k, bool packed, bool small) {
   switch (k) {
-#define PK(n) case n: return packed ? k_probe2<n, true> : k_probe2<n, false>;
+#define PK(n) case n: return packed ? (small ? k_probe2<n, true, true> : k_probe2<n, true, false>) \
+                                    : (small ? k_probe2<n, false, true> : k_probe2<n, false, false>);
     PK(1) PK(2) PK(3) PK(4) PK(5) PK(6) PK(7) PK(8) PK(9) PK(10) PK(11) PK(12) PK(13) PK(14) PK(15) PK(16)
     PK(17) PK(18) PK(19) PK(20) PK(21) PK(22) PK(23) PK(24) PK(25) PK(26) PK(27) PK(28) PK(29) PK(30) PK(31)
 #undef PK
@@ -550,7 +565,7 @@ static probe_fn probe_table(int k, bool packed) {
 int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   u64 total = ctx->total_bases;
   u64 n_tiles = cdiv(total, PW_TILE);
-  probe_fn fn = probe_table(ctx->k, ctx->seq_packed);
+  probe_fn fn = probe_table(ctx->k, ctx->seq_packed, ctx->filt_words * 16 <= (32ull << 20));
   if (!fn) return gvs_fail(ctx, GVS_E_ARG, "no probe kernel for k=%d", ctx->k);
   u64* counters = ctx->counters.as<u64>();
   Probe2Params P;
