@@ -374,6 +374,63 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         for (int g = 0; g < NG; g++)  // both bits of gvs_p1_bits(hb) set in the word (the funnel shift wraps mod 32)
           pass |= (__funnelshift_r(w1[g], 0u, hbv[g]) & __funnelshift_r(w1[g], 0u, hbv[g] >> 5) & 1u) << g;
       }
+      auto read_of = [&](u32 prel) -> u32 {
+        if (!has_bound) return (u32)(cur0 - 1);
+        if (nb <= PW_MAXB) {
+          u32 rd = (u32)(cur0 - 1), bestpos = 0;
+          bool any = false;
+          for (u32 q = 0; q < nb; q++) {
+            u32 bp = sm.bpos[q], bj = sm.bidx[q];
+            if (bp <= prel && (!any || bp > bestpos || (bp == bestpos && bj > rd))) {
+              any = true;
+              bestpos = bp;
+              rd = bj;
+            }
+          }
+          return rd;
+        }
+        u64 p = ts + prel;
+        u64 l = 1, h2 = P.n_reads;
+        while (l < h2) {
+          u64 mid = (l + h2) >> 1;
+          if (__ldg(P.read_off + mid) > p) h2 = mid; else l = mid + 1;
+        }
+        return (u32)(l - 1);
+      };
+      // The hits of a lookup round (lane order = position order) are written out at once: runs of
+      // consecutive hits on one group inside one read collapse into ONE record (first hit + number of
+      // followers) -- kmerpos_annot3 prints only the first (nim:92), the others just shift the positions
+      // reported later in the read (Q3).  Runs are cut at round and tile boundaries; the emit pass
+      // (match.cu) merges what was cut.
+      auto emit_round = [&](u32 row, u32 gi, u32 pp) {
+        u32 rd = 0;
+        const bool hit = row != GVS_NOHIT;
+        const u32 bal = __ballot_sync(ALL, hit);
+        if (bal == 0) return;  // warp-uniform
+        if (hit) rd = read_of(pp);
+        const u32 below = bal & ((1u << lane) - 1);
+        const int prev = below ? 31 - __clz(below) : lane;  // the hit before this one in the round
+        const u32 gi_prev = __shfl_sync(ALL, gi, prev), rd_prev = __shfl_sync(ALL, rd, prev);
+        const bool head = hit && (below == 0 || gi != gi_prev || rd != rd_prev);
+        const u32 hb = __ballot_sync(ALL, head);
+        const u32 nrec = __popc(hb);
+        const bool fits = (u64)wcount + nrec <= P.cap_w;
+        if (!fits && lane == 0) atomicOr(P.flags, FLAG_OVERFLOW);
+        if (head && fits) {
+          const u32 above = lane == 31 ? 0u : (hb >> (lane + 1)) << (lane + 1);
+          const u32 upto = above ? ((1u << (__ffs(above) - 1)) - 1) : 0xFFFFFFFFu;  // lanes below the next head
+          const u32 after = lane == 31 ? 0u : ~((2u << lane) - 1);                    // lanes above this one
+          const u64 o = region * P.cap_w + wcount + __popc(hb & ((1u << lane) - 1));
+          P.hit_read[o] = rd;
+          P.hit_w[o] = (u32)(ts + pp - __ldg(P.read_off + rd));
+          P.hit_row[o] = row;
+          P.hit_gidx[o] = gi;
+          P.hit_nf[o] = (u8)__popc(bal & upto & after);
+        }
+        wcount += nrec;
+      };
+      const bool any_s16 = SMALL && __any_sync(ALL, S16 != 0);
+      bool fused = false;  // SMALL: the tile's hits were already written by the single-round path
       // ---- passing groups -> warp queue (position order); their windows are tested one per lane ----
       if (__any_sync(ALL, pass != 0)) {
         const u32 np_lane = __popc(pass);
@@ -396,17 +453,31 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
         __syncwarp();
         const u32 n_ent = n_grp * J;
         constexpr int RB = 4;  // rounds whose block loads are issued back to back before any window math
-        if (SMALL && n_ent <= 32) {
+        if (SMALL && n_ent <= 32 && !any_s16) {
+          // one round, and the queue order is the position order: test, exact lookup and record output in
+          // one go (no candidate bitmap, no second extraction of the k-mer)
+          u32 row = GVS_NOHIT, gi = 0, p = 0;
           if ((u32)lane < n_ent) {
             const u32 q = lane / J, w = lane % J;
-            const u32 p = (u32)sm.q_p[q] * J + w;
+            p = (u32)sm.q_p[q] * J + w;
             const uint4 b4 = p_ldg_v4((const uint4*)P.filt + (sm.q_row[q] & P.filt_mask), pol_blk);
             const bool valid = !((sm.inv[p >> 4] >> (p & 15)) & 1u);
-            const u32 h = gvs_fhash(p_canon_at<K>(sm, rb, p, false));
+            const u64 canon = p_canon_at<K>(sm, rb, p, false);
+            const u32 h = gvs_fhash(canon);
             const u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
                           __funnelshift_r(b4.w, 0u, h >> 15);
-            if (valid && (t & 1u)) atomicOr(&sm.cand[p >> 5], 1u << (p & 31));
+            if (valid && (t & 1u)) {
+              row = tab_lookup(P.tab, canon, gvs_mix(canon), &gi);
+              if (row == GVS_ROW_MISSING) {
+                atomicOr(P.flags, FLAG_KEYERROR);
+                row = GVS_NOHIT;
+              } else if (row >= GVS_NOHIT) {
+                row = GVS_NOHIT;
+              }
+            }
           }
+          emit_round(row, gi, p);
+          fused = true;
         } else
         for (u32 base = 0; base < n_ent; base += 32 * RB) {
           uint4 b4[RB];
@@ -436,7 +507,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           }
         }
         __syncwarp();
-        cm = (sm.cand[lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu;
+        if (!fused) cm = (sm.cand[lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu;
       }
       if (S16) {  // bogus windows of (K-1)-long reads: last base read as A, always "valid"
         for (u32 s16 = S16; s16; s16 &= s16 - 1) {
@@ -470,36 +541,9 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           sm.q_p[qo++] = (u16)((16u * lane + i) | (((cm >> (16 + i)) & 1) << 15));
         }
         __syncwarp();
-        auto read_of = [&](u32 prel) -> u32 {
-          if (!has_bound) return (u32)(cur0 - 1);
-          if (nb <= PW_MAXB) {
-            u32 rd = (u32)(cur0 - 1), bestpos = 0;
-            bool any = false;
-            for (u32 q = 0; q < nb; q++) {
-              u32 bp = sm.bpos[q], bj = sm.bidx[q];
-              if (bp <= prel && (!any || bp > bestpos || (bp == bestpos && bj > rd))) {
-                any = true;
-                bestpos = bp;
-                rd = bj;
-              }
-            }
-            return rd;
-          }
-          u64 p = ts + prel;
-          u64 l = 1, h2 = P.n_reads;
-          while (l < h2) {
-            u64 mid = (l + h2) >> 1;
-            if (__ldg(P.read_off + mid) > p) h2 = mid; else l = mid + 1;
-          }
-          return (u32)(l - 1);
-        };
-        // ---- exact lookups, 32 candidates per round.  The hits of a round (lane order = position order)
-        //      are written out at once: runs of consecutive hits on one group inside one read collapse
-        //      into ONE record (first hit + number of followers) -- kmerpos_annot3 prints only the first
-        //      (nim:92), the others just shift the positions reported later in the read (Q3).  Runs are
-        //      cut at round and tile boundaries; the emit pass (match.cu) merges what was cut. ----
+        // ---- exact lookups, 32 candidates per round ----
         for (u32 base = 0; base < ncand; base += 32) {
-          u32 row = GVS_NOHIT, gi = 0, rd = 0;
+          u32 row = GVS_NOHIT, gi = 0;
           u32 pp = 0;
           if (base + lane < ncand) {
             u32 e = sm.q_p[base + lane];
@@ -513,30 +557,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
               row = GVS_NOHIT;
             }
           }
-          const bool hit = row != GVS_NOHIT;
-          const u32 bal = __ballot_sync(ALL, hit);
-          if (bal == 0) continue;  // warp-uniform
-          if (hit) rd = read_of(pp);
-          const u32 below = bal & ((1u << lane) - 1);
-          const int prev = below ? 31 - __clz(below) : lane;  // the hit before this one in the round
-          const u32 gi_prev = __shfl_sync(ALL, gi, prev), rd_prev = __shfl_sync(ALL, rd, prev);
-          const bool head = hit && (below == 0 || gi != gi_prev || rd != rd_prev);
-          const u32 hb = __ballot_sync(ALL, head);
-          const u32 nrec = __popc(hb);
-          const bool fits = (u64)wcount + nrec <= P.cap_w;
-          if (!fits && lane == 0) atomicOr(P.flags, FLAG_OVERFLOW);
-          if (head && fits) {
-            const u32 above = lane == 31 ? 0u : (hb >> (lane + 1)) << (lane + 1);
-            const u32 upto = above ? ((1u << (__ffs(above) - 1)) - 1) : 0xFFFFFFFFu;  // lanes below the next head
-            const u32 after = lane == 31 ? 0u : ~((2u << lane) - 1);                    // lanes above this one
-            const u64 o = region * P.cap_w + wcount + __popc(hb & ((1u << lane) - 1));
-            P.hit_read[o] = rd;
-            P.hit_w[o] = (u32)(ts + pp - __ldg(P.read_off + rd));
-            P.hit_row[o] = row;
-            P.hit_gidx[o] = gi;
-            P.hit_nf[o] = (u8)__popc(bal & upto & after);
-          }
-          wcount += nrec;
+          emit_round(row, gi, pp);
         }
       }
       // ---- tile T is done: its ring slot receives tile T+2 ----
