@@ -255,49 +255,77 @@ def main_b200(args):
         np_reads = h_reads.numpy()[:wl.total_bases]
         np_off = h_off.numpy().view(np.uint64)
         bind_h = lambda: eng.set_reads(np_reads, np_off, wl.chunk_first, wl.chunk_hap)
-        run_step(eng, wl, bind_h, coll)
-        eng.pairs(pinned=True)  # warm-up also sizes the page-locked result buffers
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        f0.record()
-        d2h = 0
-        split = dict(submit_copy=0.0, match=0.0, filter_validate_intervals=0.0, results_to_host=0.0)
-        for _ in range(args.e2e_steps):
-            # same calls as run_step(), with host-side time stamps between them (where the e2e step goes)
-            c0 = time.perf_counter()
-            bind_h()                                          # queues the 16 H2D segments, returns at once
-            c1 = time.perf_counter()
-            eng.match()                                       # probe launches chase the copy; returns when rows exist
-            c2 = time.perf_counter()
-            eng.diag_filter(wl.contig_hap)
-            hp = eng.group_hist()
-            coll.allreduce_hist(hp, eng.db_groups())
-            eng.bad_groups()
-            eng.validate(10000)
-            pp = eng.components_local()
-            for peer in coll.gather_forests(pp, eng.db_groups()):
-                eng.components_merge(peer)
-            iv2 = eng.intervals()                             # intervals + gaps come back to the host
-            gaps2, _nd = eng.gaps(wl.contig_len.astype(np.uint32))
-            c3 = time.perf_counter()
-            pairs = eng.pairs(pinned=True)                    # inter_outs rows (group, read) into page-locked memory
-            c4 = time.perf_counter()
-            for key, dt in zip(split, (c1 - c0, c2 - c1, c3 - c2, c4 - c3)):
-                split[key] += dt * 1e3 / args.e2e_steps
-            d2h = sum(a.nbytes for a in pairs.values()) + sum(a.nbytes for a in iv2.values()) + sum(a.nbytes for a in gaps2.values())
-        f1.record()
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        ems = max(f0.elapsed_time(f1), wall_ms)
-        t = torch.tensor([ems], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = dict(value=total_bases * args.e2e_steps / (float(t.item()) * 1e-3) / 1e9, unit=UNIT,
-                   h2d_bytes_per_step=int(wl.total_bases + 8 * (wl.n_reads + 1)), d2h_bytes_per_step=int(d2h),
-                   steps=args.e2e_steps, ms_per_step=float(t.item()) / args.e2e_steps, host_numa_node=numa.get("numa_node"),
+        def time_host_path(bind):
+            """e2e_steps steps of the whole path from the host batch `bind` registers; max over ranks"""
+            r0, _, _ = run_step(eng, wl, bind, coll)
+            assert r0 == res, "the host path must reproduce the resident path"
+            eng.pairs(pinned=True)  # warm-up also sizes the page-locked result and staging buffers
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            f0.record()
+            d2h = 0
+            split = dict(submit_copy=0.0, match=0.0, filter_validate_intervals=0.0, results_to_host=0.0)
+            for _ in range(args.e2e_steps):
+                # same calls as run_step(), with host-side time stamps between them (where the e2e step goes)
+                c0 = time.perf_counter()
+                bind()                                            # starts the segment pipeline, returns at once
+                c1 = time.perf_counter()
+                eng.match()                                       # probe launches chase the segments; returns when rows exist
+                c2 = time.perf_counter()
+                eng.diag_filter(wl.contig_hap)
+                hp = eng.group_hist()
+                coll.allreduce_hist(hp, eng.db_groups())
+                eng.bad_groups()
+                eng.validate(10000)
+                pp = eng.components_local()
+                for peer in coll.gather_forests(pp, eng.db_groups()):
+                    eng.components_merge(peer)
+                iv2 = eng.intervals()                             # intervals + gaps come back to the host
+                gaps2, _nd = eng.gaps(wl.contig_len.astype(np.uint32))
+                c3 = time.perf_counter()
+                pairs = eng.pairs(pinned=True)                    # inter_outs rows (group, read) into page-locked memory
+                c4 = time.perf_counter()
+                for key, dt in zip(split, (c1 - c0, c2 - c1, c3 - c2, c4 - c3)):
+                    split[key] += dt * 1e3 / args.e2e_steps
+                d2h = sum(a.nbytes for a in pairs.values()) + sum(a.nbytes for a in iv2.values()) + sum(a.nbytes for a in gaps2.values())
+            f1.record()
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            ems = max(f0.elapsed_time(f1), wall_ms)
+            t = torch.tensor([ems], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()), split, d2h
+
+        # Headline: the library's default for a pipelined ASCII host batch (gvs_set_host_pack ADAPTIVE): every
+        # segment goes over the link either as ASCII or 2-bit packed by the host threads, whichever keeps link
+        # and cores busy; both the packing and all copies are inside the timed region.
+        n_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        pack_threads = max(1, min(16, n_cores // max(local_world, 1)))
+        eng.set_host_pack(eng.PACK_ADAPTIVE, pack_threads)
+        ems, split, d2h = time_host_path(bind_h)
+        seq_bytes, n_seg, n_seg_packed = eng.copy_stats()
+        e2e = dict(value=total_bases * args.e2e_steps / (ems * 1e-3) / 1e9, unit=UNIT,
+                   h2d_bytes_per_step=int(seq_bytes + 8 * (wl.n_reads + 1)), d2h_bytes_per_step=int(d2h),
+                   steps=args.e2e_steps, ms_per_step=ems / args.e2e_steps, host_numa_node=numa.get("numa_node"),
                    host_split_ms={k2: round(v, 2) for k2, v in split.items()},
-                   h2d_gbs_if_copy_bound=(wl.total_bases / 1e9) / max(split["match"] * 1e-3, 1e-9))
+                   host_input_bytes_per_step=int(wl.total_bases + 8 * (wl.n_reads + 1)),
+                   transfer=dict(mode="adaptive", host_pack_threads=pack_threads, segments=n_seg, segments_packed=n_seg_packed,
+                                 note="input = ASCII bases in page-locked host memory; a segment crosses PCIe as ASCII or 2-bit "
+                                      "packed by the host threads (kmer.encode's byte map), chosen at run time; last step's counts"))
+        # the same call with the host cores idle (every segment as ASCII): the transfer-bound figure
+        try:
+            eng.set_host_pack(eng.PACK_OFF, pack_threads)
+            ems0, split0, _ = time_host_path(bind_h)
+            e2e["ascii_copy_only"] = dict(value=total_bases * args.e2e_steps / (ems0 * 1e-3) / 1e9, unit=UNIT,
+                                          ms_per_step=ems0 / args.e2e_steps, h2d_bytes_per_step=int(wl.total_bases + 8 * (wl.n_reads + 1)),
+                                          host_split_ms={k2: round(v, 2) for k2, v in split0.items()},
+                                          h2d_gbs_if_copy_bound=(wl.total_bases / 1e9) / max(split0["match"] * 1e-3, 1e-9))
+        except Exception as ex:
+            e2e["ascii_copy_only"] = dict(error=repr(ex)[:200])
+        eng.set_host_pack(eng.PACK_ADAPTIVE, pack_threads)
         # ---- secondary: the same path with the host batch 2-bit packed by the ingest (gvs_pack_2bit, outside
         #      the timed region like the parse that produces `h_reads`); NOT the headline e2e ----
         try:
@@ -305,7 +333,10 @@ def main_b200(args):
             nw = (wl.total_bases + 15) // 16
             h_words = torch.zeros(nw + 16, dtype=torch.int32, pin_memory=True)
             np_words = h_words.numpy().view(np.uint32)
-            pack_2bit(np_reads, out=np_words)
+            pack_2bit(np_reads, threads=pack_threads, out=np_words)  # first touch of the output pages
+            tq = time.perf_counter()
+            pack_2bit(np_reads, threads=pack_threads, out=np_words)
+            e2e["transfer"]["host_pack_gbs_alone"] = round(wl.total_bases / (time.perf_counter() - tq) / 1e9, 1)
             bind_p = lambda: eng.set_reads_packed(np_words[:nw], np_off, wl.chunk_first, wl.chunk_hap)
             rp, _, _ = run_step(eng, wl, bind_p, coll)
             assert rp == res, "packed host path must reproduce the ASCII path"

@@ -35,6 +35,8 @@ PROTOTYPES = {
     "gvs_reads_set": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_int]),
     "gvs_reads_set_packed": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_int]),
     "gvs_set_copy_pipeline": (C.c_int, [vp, C.c_uint64, C.c_uint32]),
+    "gvs_set_host_pack": (C.c_int, [vp, C.c_int, C.c_int]),
+    "gvs_copy_stats": (C.c_int, [vp, u64p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "gvs_reads_meta": (C.c_int, [vp, vp, C.c_uint64, vp, vp, C.c_uint32]),
     "gvs_rows_set": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32]),
     "gvs_match": (C.c_int, [vp, u64p]),

@@ -21,6 +21,7 @@ typedef int64_t i64;
 #define GVS_NSM_DEFAULT 148
 #define GVS_TILE_BASES 512                 // window starts per probe tile (probe.cu PW_TILE)
 #define GVS_SEG_COUNT 16                   // copy/probe pipeline depth for host batches
+#define GVS_SEG_COUNT_PACK 48              // ... when segments may be packed on the host (finer hand-over between link and cores)
 #define GVS_SEG_MIN_BYTES (256ull << 20)   // smaller host batches are copied in one piece
 
 // grow-only device buffer: stages re-use their scratch across calls so that the timed loop of
@@ -82,6 +83,17 @@ struct gvs_ctx {
   std::vector<u64> seg_tile_end;        // tile index (512 bases) where segment s ends; empty = one launch
   u64 seg_min_bytes = GVS_SEG_MIN_BYTES;
   u32 seg_count = GVS_SEG_COUNT;
+  bool seg_count_set = false;           // gvs_set_copy_pipeline was called
+  // host batches of ASCII bases: a segment travels either as it is or 2-bit packed by host threads
+  // (hostpack.cpp) through a page-locked staging buffer -- the PCIe link and the host cores work side by
+  // side (ctx.cu HostPipe).  seg_packed[s] selects the probe variant and the device buffer of segment s.
+  DevBuf own_words;
+  std::vector<u8> seg_packed;           // empty: every segment lives in `seq` as seq_packed says
+  struct HostPipe* pipe = nullptr;
+  int pack_mode = GVS_PACK_ADAPTIVE;
+  int pack_threads = 0;                 // 0 = the cores this process may run on, at most 16
+  u64 h2d_bytes = 0;                    // sequence bytes the last host batch put on the link
+  u32 h2d_segs = 0, h2d_segs_packed = 0;
   DevBuf chunk_first, chunk_hap;  // device copies
   std::vector<u64> h_chunk_first;
   std::vector<u8> h_chunk_hap;
@@ -247,6 +259,12 @@ struct StageTimer {
     }
   }
 };
+
+// ctx.cu: segment `seg` of a host batch has been handed to the copy stream (its event is recorded);
+// blocks while the submitter thread is still packing it
+int gvs_pipe_wait(gvs_ctx* ctx, u64 seg);
+// the submitter thread of the last host batch has finished (called before the batch's buffers change)
+int gvs_pipe_join(gvs_ctx* ctx);
 
 static inline u64 next_pow2(u64 x) {
   u64 p = 1;

@@ -242,43 +242,19 @@ extern "C" int gvs_fastx_read(const char* const* paths, uint32_t n_files, int th
 }
 
 // 2-bit codes of kmer.encode (nim-kmer 0.2.6, pinned by tests/golden/kat_bytes): A/a 0, C/c 1, G/g 2,
-// T/t/U/u 3, bytes 0x01..0x03 themselves, everything else 0 -- for this path the packing loses nothing
-static const u8* code_lut() {
-  static u8 lut[256];
-  static bool init = false;
-  if (!init) {
-    memset(lut, 0, sizeof lut);
-    lut['C'] = lut['c'] = 1;
-    lut['G'] = lut['g'] = 2;
-    lut['T'] = lut['t'] = lut['U'] = lut['u'] = 3;
-    lut[1] = 1; lut[2] = 2; lut[3] = 3;
-    init = true;
-  }
-  return lut;
-}
+// T/t/U/u 3, bytes 0x01..0x03 themselves, everything else 0 -- for this path the packing loses nothing.
+// The byte map itself lives in hostpack.cpp (AVX2 with a table for blocks that hold anything but ACGT).
+extern "C" void gvs_hostpack_range(const uint8_t* ascii, uint64_t n, uint32_t* words, uint64_t w0, uint64_t w1);
 
 extern "C" int gvs_pack_2bit(const uint8_t* ascii, uint64_t n, uint32_t* words, int threads) {
   if ((n && !ascii) || !words) return GVS_E_ARG;
-  const u8* lut = code_lut();
   const u64 nw = (n + 15) / 16;
   if (threads < 1) threads = 1;
-  auto work = [&](u64 w0, u64 w1) {
-    for (u64 w = w0; w < w1; w++) {
-      const u64 b = w * 16;
-      u32 v = 0;
-      if (b + 16 <= n) {
-        for (int i = 0; i < 16; i++) v = (v << 2) | lut[ascii[b + i]];
-      } else {
-        for (int i = 0; i < 16; i++) v = (v << 2) | (b + i < n ? lut[ascii[b + i]] : 0);
-      }
-      words[w] = v;  // first base in the two most significant bits
-    }
-  };
   if (threads == 1 || nw < 65536) {
-    work(0, nw);
+    gvs_hostpack_range(ascii, n, words, 0, nw);
   } else {
     std::vector<std::thread> pool;
-    for (int t = 0; t < threads; t++) pool.emplace_back(work, nw * t / threads, nw * (t + 1) / threads);
+    for (int t = 0; t < threads; t++) pool.emplace_back(gvs_hostpack_range, ascii, n, words, nw * t / threads, nw * (t + 1) / threads);
     for (auto& t : pool) t.join();
   }
   return 0;

@@ -1,0 +1,102 @@
+// hostpack.cpp -- kmer.encode's byte map on the host, 128 bases per AVX2 step (plain C++: g++ compiles this
+// file, nvcc never sees the intrinsics).  The map is the one pinned by tests/golden/kat_bytes (nim-kmer 0.2.6,
+// call site workflow/src/kmerpos_annot3.nim:88): A/a 0, C/c 1, G/g 2, T/t/U/u 3, bytes 0x01..0x03 themselves,
+// everything else 0.  Output: big-endian words of 16 bases (first base in the two top bits), the layout the
+// PACKED probe variant reads (probe.cu p_stage_issue).
+#include <stdint.h>
+#include <string.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+static uint8_t g_lut[256];
+static struct LutInit {
+  LutInit() {
+    memset(g_lut, 0, sizeof g_lut);
+    g_lut['C'] = g_lut['c'] = 1;
+    g_lut['G'] = g_lut['g'] = 2;
+    g_lut['T'] = g_lut['t'] = g_lut['U'] = g_lut['u'] = 3;
+    g_lut[1] = 1; g_lut[2] = 2; g_lut[3] = 3;
+  }
+} g_lut_init;
+
+static inline uint32_t pack16_lut(const uint8_t* p) {
+  uint32_t v = 0;
+  for (int i = 0; i < 16; i++) v = (v << 2) | g_lut[p[i]];
+  return v;
+}
+
+// words [w0, w1) of the batch `ascii[0..n)`; the last word may be partial (zero-padded)
+static void pack_scalar(const uint8_t* ascii, uint64_t n, uint32_t* words, uint64_t w0, uint64_t w1) {
+  for (uint64_t w = w0; w < w1; w++) {
+    const uint64_t b = w * 16;
+    if (b + 16 <= n) {
+      words[w] = pack16_lut(ascii + b);
+    } else {
+      uint32_t v = 0;
+      for (int i = 0; i < 16; i++) v = (v << 2) | (b + i < n ? g_lut[ascii[b + i]] : 0);
+      words[w] = v;
+    }
+  }
+}
+
+#if defined(__x86_64__)
+// 128 bases -> eight words per step.  A letter's code is ((x >> 1) ^ (x >> 2)) & 3; the codes are turned back
+// into letters with one PSHUFB and compared with the upper-cased input, and a block that holds anything but
+// A/C/G/T (N runs, U, control bytes) takes the table instead.
+__attribute__((target("avx2"))) static void pack_avx2(const uint8_t* ascii, uint64_t n, uint32_t* words, uint64_t w0,
+                                                      uint64_t w1) {
+  const __m256i m3 = _mm256_set1_epi8(3);
+  const __m256i up = _mm256_set1_epi8((char)0xDF);
+  const __m256i acgt = _mm256_setr_epi8('A', 'C', 'G', 'T', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 'A', 'C', 'G', 'T', 0, 0, 0, 0, 0, 0,
+                                        0, 0, 0, 0, 0, 0);
+  const __m256i mul1 = _mm256_set1_epi16(0x0104);      // c[2i] * 4 + c[2i+1]
+  const __m256i mul2 = _mm256_set1_epi32(0x00010010);  // n[2i] * 16 + n[2i+1]
+  const __m256i bswap = _mm256_setr_epi8(3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12, 3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8,
+                                         15, 14, 13, 12);
+  const __m256i order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+  const uint64_t full = n / 16;  // words whose 16 bases all exist
+  const uint64_t stop = w1 < full ? w1 : full;
+  uint64_t w = w0;
+  for (; w + 8 <= stop; w += 8) {
+    const uint8_t* p = ascii + w * 16;
+    __m256i f[4];
+    __m256i ok = _mm256_set1_epi8(-1);
+    for (int i = 0; i < 4; i++) {
+      const __m256i x = _mm256_loadu_si256((const __m256i*)(p + 32 * i));
+      f[i] = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(x, 1), _mm256_srli_epi16(x, 2)), m3);
+      ok = _mm256_and_si256(ok, _mm256_cmpeq_epi8(_mm256_shuffle_epi8(acgt, f[i]), _mm256_and_si256(x, up)));
+    }
+    if (__builtin_expect(_mm256_movemask_epi8(ok) != -1, 0)) {
+      for (int i = 0; i < 8; i++) words[w + i] = pack16_lut(p + 16 * i);
+      continue;
+    }
+    // 32-bit lanes: four bases in the low byte, first base in its top bits
+    for (int i = 0; i < 4; i++) f[i] = _mm256_madd_epi16(_mm256_maddubs_epi16(f[i], mul1), mul2);
+    // bytes of both 128-bit halves: [f0 f1 f2 f3] x 4 bytes; byte-swapped they are the big-endian words
+    const __m256i b = _mm256_packus_epi16(_mm256_packus_epi32(f[0], f[1]), _mm256_packus_epi32(f[2], f[3]));
+    const __m256i v = _mm256_permutevar8x32_epi32(_mm256_shuffle_epi8(b, bswap), order);
+    _mm256_storeu_si256((__m256i*)(words + w), v);
+  }
+  if (w < w1) pack_scalar(ascii, n, words, w, w1);
+}
+#endif
+
+// exported to fastx.cu / ctx.cu (not part of the C ABI)
+extern "C" void gvs_hostpack_range(const uint8_t* ascii, uint64_t n, uint32_t* words, uint64_t w0, uint64_t w1) {
+#if defined(__x86_64__)
+  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  if (have_avx2) {
+    pack_avx2(ascii, n, words, w0, w1);
+    return;
+  }
+#endif
+  pack_scalar(ascii, n, words, w0, w1);
+}
+extern "C" int gvs_hostpack_simd(void) {
+#if defined(__x86_64__)
+  return __builtin_cpu_supports("avx2") ? 1 : 0;
+#else
+  return 0;
+#endif
+}

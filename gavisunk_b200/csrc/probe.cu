@@ -678,7 +678,18 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
   for (size_t s = 0; s < plan.size(); s++) {
-    if (piped) CK(cudaStreamWaitEvent(ctx->stream, ctx->seg_ev[plan[s].ev], 0));
+    probe_fn fn_s = fn;
+    P.seq = ctx->seq;
+    if (piped) {
+      // a segment of an ASCII host batch may have been packed on the host (ctx.cu HostPipe): wait until the
+      // submitter has queued it, then scan it with the variant of its kind
+      CKR(gvs_pipe_wait(ctx, plan[s].ev));
+      if (!ctx->seg_packed.empty() && ctx->seg_packed[plan[s].ev]) {
+        fn_s = probe_table(ctx->k, true, ctx->filt_words * 16 <= (32ull << 20));
+        P.seq = ctx->own_words.as<u8>();
+      }
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->seg_ev[plan[s].ev], 0));
+    }
     cfg.gridDim = dim3(plan[s].blocks);
     P.tile_begin = plan[s].t0;
     P.tile_stop = plan[s].t1;
@@ -686,10 +697,11 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
     P.n_spans = plan[s].n_spans;
     P.span_base = plan[s].span_base;
     P.span_ctr = ctx->tile_off.as<u32>() + s;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, P);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn_s, P);
     ctx->launches++;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return gvs_fail(ctx, GVS_E_CUDA, "k_probe2 launch: %s", cudaGetErrorString(e));
   }
+  if (piped) CKR(gvs_pipe_join(ctx));
   return 0;
 }

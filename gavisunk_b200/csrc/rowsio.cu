@@ -62,6 +62,9 @@ extern "C" int gvs_reads_meta(gvs_ctx* ctx, const uint32_t* read_len, uint64_t n
   CK(cudaSetDevice(ctx->device));
   if (!chunk_first || !chunk_hap || n_chunks == 0) return gvs_fail(ctx, GVS_E_ARG, "null chunk arrays");
   if (chunk_first[0] != 0 || chunk_first[n_chunks] != n_reads) return gvs_fail(ctx, GVS_E_ARG, "chunk_first must span [0, n_reads]");
+  CKR(gvs_pipe_join(ctx));
+  ctx->seg_tile_end.clear();
+  ctx->seg_packed.clear();
   ctx->reads_ready = false;
   ctx->match_ready = ctx->diag_ready = ctx->val_ready = false;
   ctx->seq = nullptr;

@@ -270,6 +270,20 @@ class Engine:
         """Host batches >= min_bytes are copied in `segments` pieces overlapped with the match."""
         self._ck(self.lib.gvs_set_copy_pipeline(self.ctx, int(min_bytes), int(segments)))
 
+    PACK_OFF, PACK_ADAPTIVE, PACK_ALL, PACK_ALTERNATE = 0, 1, 2, 3
+
+    def set_host_pack(self, mode: int = 1, threads: int = 0):
+        """How the segments of a pipelined ASCII host batch travel: as they are (PACK_OFF), 2-bit packed by
+        `threads` host threads (PACK_ALL), or whichever keeps both the PCIe link and the cores busy
+        (PACK_ADAPTIVE, the default).  Results do not depend on it."""
+        self._ck(self.lib.gvs_set_host_pack(self.ctx, int(mode), int(threads)))
+
+    def copy_stats(self):
+        """(sequence bytes copied host->device, segments, segments sent packed) of the last host batch."""
+        b, n, k = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        self._ck(self.lib.gvs_copy_stats(self.ctx, C.byref(b), C.byref(n), C.byref(k)))
+        return int(b.value), int(n.value), int(k.value)
+
     def set_reads_device(self, seq_ptr: int, off_ptr: int, n_reads: int, chunk_first, chunk_hap):
         chunk_first = _c(chunk_first, np.uint64)
         chunk_hap = _c(chunk_hap, np.uint8)

@@ -162,6 +162,26 @@ int gvs_reads_set_packed(gvs_ctx* ctx, const uint32_t* words, const uint64_t* re
  * Defaults: 256 MiB, 16.  segments <= 1 disables the pipeline. */
 int gvs_set_copy_pipeline(gvs_ctx* ctx, uint64_t min_bytes, uint32_t segments);
 
+/* How the segments of a pipelined ASCII host batch (gvs_reads_set, on_device == 0) reach the GPU.  The
+ * reference reads one ASCII byte per base (readfq, workflow/src/kmerpos_annot3.nim:85); the PCIe link moves
+ * those at ~55 GB/s, so a segment may instead be packed to 2 bits per base on `threads` host threads
+ * (kmer.encode's byte map, as gvs_pack_2bit) into page-locked staging memory and copied at a quarter of the
+ * bytes, after which the PACKED probe variant scans it.  Results are identical either way.
+ *   GVS_PACK_OFF       every segment as ASCII (the host cores stay idle)
+ *   GVS_PACK_ADAPTIVE  (default) a segment goes out as ASCII while the link has less queued than one
+ *                      segment takes to pack, and is packed otherwise: link and cores work side by side;
+ *                      a buffer that is not page-locked is always packed
+ *   GVS_PACK_ALL       every segment packed
+ *   GVS_PACK_ALTERNATE odd segments packed (tests: both kinds in one batch, deterministic)
+ * threads = 0: the cores this process may run on, at most 16.  With packing enabled a background thread of
+ * the library reads `seq` until gvs_match has returned: the buffer must stay unchanged until then (the same
+ * holds for the asynchronous copies of GVS_PACK_OFF). */
+enum { GVS_PACK_OFF = 0, GVS_PACK_ADAPTIVE = 1, GVS_PACK_ALL = 2, GVS_PACK_ALTERNATE = 3 };
+int gvs_set_host_pack(gvs_ctx* ctx, int mode, int threads);
+/* What the last host batch put on the link: sequence bytes copied, segments, segments sent packed (valid
+ * once gvs_match has returned). */
+int gvs_copy_stats(gvs_ctx* ctx, uint64_t* h2d_bytes, uint32_t* segments, uint32_t* segments_packed);
+
 /* Read table without sequences (the CLI shims that start from .sunkpos / .rlen files):
  * read_len[n_reads] = column 2 of {hap}.rlen (workflow/src/rlen.nim:13-14), chunk layout as above. */
 int gvs_reads_meta(gvs_ctx* ctx, const uint32_t* read_len, uint64_t n_reads, const uint64_t* chunk_first,

@@ -156,10 +156,15 @@ def test_host_copy_pipeline_equals_resident(full):
     h = torch.empty(wl.total_bases + 64, dtype=torch.uint8, pin_memory=True)
     h[:wl.total_bases].copy_(wl.reads[:wl.total_bases])
     torch.cuda.synchronize()
-    eng.set_reads(h.numpy()[:wl.total_bases], res["off"].astype(np.uint64), wl.chunk_first, wl.chunk_hap)
-    eng.match()
-    for c in ("read", "pos", "contig", "start", "group"):
-        assert np.array_equal(eng.rows(0)[c], res["rows"][c]), c
+    for mode in (eng.PACK_OFF, eng.PACK_ALL, eng.PACK_ADAPTIVE):  # segments as ASCII / 2-bit packed on the host / mixed
+        eng.set_host_pack(mode)
+        eng.set_reads(h.numpy()[:wl.total_bases], res["off"].astype(np.uint64), wl.chunk_first, wl.chunk_hap)
+        eng.match()
+        for c in ("read", "pos", "contig", "start", "group"):
+            assert np.array_equal(eng.rows(0)[c], res["rows"][c]), (mode, c)
+        nbytes, nseg, npk = eng.copy_stats()
+        assert nseg > 1 and npk == {eng.PACK_OFF: 0, eng.PACK_ALL: nseg}.get(mode, npk)
+        assert wl.total_bases // 4 <= nbytes <= wl.total_bases + 4096 * nseg
     del h
 
 

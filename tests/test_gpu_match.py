@@ -37,17 +37,24 @@ def test_match_random_batched_chunks(name):
 
 @pytest.mark.parametrize("name", ["rand_k20", "rand_k31", "rand_k20_many", "kat_bytes", "ragged_k20", "ragged_k16"])
 @pytest.mark.parametrize("segments", [2, 7, 64])
-def test_match_copy_pipeline(name, segments):
+@pytest.mark.parametrize("pack", [0, 1, 2, 3])
+def test_match_copy_pipeline(name, segments, pack):
     """host batch copied in segments on the copy stream, one probe launch per segment
-    (gvs_set_copy_pipeline): rows identical to the reference ELF output whatever the split"""
+    (gvs_set_copy_pipeline): rows identical to the reference ELF output whatever the split and whichever
+    segments were 2-bit packed by the host threads on their way (gvs_set_host_pack: none / the library's
+    choice / all / every other one, i.e. ASCII and packed probe variants side by side in one batch)"""
     case = load_golden(name)
     eng, names = engine_from_case(case)
     eng.set_copy_pipeline(0, segments)
+    eng.set_host_pack(pack, 3)
     chunks = [ch["reads"] for ch in case["chunks"]] if "chunks" in case else [case["reads"]]
     want = [ch["sunkpos"] for ch in case["chunks"]] if "chunks" in case else [case["out"]]
     for _ in range(2):  # second round re-uses the segment events and overwrites the resident batch
         got = run_match_chunks(eng, names, chunks)
         assert got == want
+        nbytes, nseg, npk = eng.copy_stats()
+        if nseg > 1:
+            assert npk == {0: 0, 1: nseg, 2: nseg, 3: nseg // 2}[pack]  # 1: pageable source, always packed
 
 
 @pytest.mark.parametrize("name", ["kat_b1", "kat_bytes", "rand_k20", "rand_k16", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31"])
