@@ -60,6 +60,10 @@ __attribute__((target("avx2"))) static void pack_avx2(const uint8_t* ascii, uint
   uint64_t w = w0;
   for (; w + 8 <= stop; w += 8) {
     const uint8_t* p = ascii + w * 16;
+    // 2 KiB ahead: +10 % at 16 threads on the bench host (4 KiB pages under nested paging keep the hardware
+    // prefetcher short of the next page)
+    _mm_prefetch((const char*)(p + 2048), _MM_HINT_T0);
+    _mm_prefetch((const char*)(p + 2048 + 64), _MM_HINT_T0);
     __m256i f[4];
     __m256i ok = _mm256_set1_epi8(-1);
     for (int i = 0; i < 4; i++) {

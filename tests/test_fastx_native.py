@@ -83,8 +83,12 @@ def test_pack_2bit_is_kmer_encode_byte_map(tmp_path):
     import gavisunk_oracle as O
     from gavisunk_b200.engine import pack_2bit
     rng = np.random.default_rng(5)
-    for n in (0, 1, 15, 16, 17, 255, 256, 4099, 1_200_003):
+    for n in (0, 1, 15, 16, 17, 127, 128, 129, 255, 256, 4099, 1_200_003, 700_001):
         seq = rng.integers(0, 256, n, dtype=np.uint8) if n < 5000 else rng.choice(np.frombuffer(b"ACGTNacgtnU\x01\x02\x03-", np.uint8), n)
+        if n == 700_001:  # read-like: letters only except for a sprinkle of arbitrary bytes (the 128-base AVX2 step
+            seq = rng.choice(np.frombuffer(b"ACGTacgt", np.uint8), n)  # of hostpack.cpp and its table path side by side)
+            at = rng.integers(0, n, n // 1000)
+            seq[at] = rng.integers(0, 256, len(at), dtype=np.uint8)
         got = pack_2bit(seq, threads=3)
         codes = O.codes_of(seq.tobytes()).astype(np.uint64)
         pad = np.zeros((-n) % 16, np.uint64)
