@@ -598,6 +598,12 @@ def main_reference(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that write to fd 1 on their own (NCCL prints its
+    # version banner there at the first communicator) are pointed at stderr, the JSON goes to the real stdout
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _json_out
     if a.impl == "reference":
         main_reference(a)
     else:

@@ -64,6 +64,8 @@ struct gvs_ctx {
   u64 tab_slots = 0;                                             // power of two, buckets of 4
   DevBuf filt;                                                   // 32-bit-word blocked Bloom filter
   u64 filt_words = 0;                                            // number of 16-byte blocks, power of two
+  bool filt_fp = false;                                          // block layout: word 3 = sub-mer fingerprints (gvs_fp_bit), keys in words 0..2
+  int probe_variant = 0;                                         // gvs_set_probe_variant: 0 by size, 1 small-database, 2 large-database
   DevBuf filt1;                                                  // presence filter of the sub-mers (large databases)
   u64 filt1_words = 0;                                           // 0 = single-level filter
   DevBuf contig_hap, contig_hash, contig_len;
@@ -309,6 +311,11 @@ __host__ __device__ __forceinline__ u32 gvs_bhash(u64 sub) {
   h ^= h >> 13;
   return h;
 }
+// Large databases (blocked filter beyond L2): word 3 of a block does not hold key bits but one fingerprint bit
+// per sub-mer that selected the block (~2 distinct sub-mers per block), so that a window group whose sub-mer
+// merely collided in the presence filter is dropped by ONE bit test on the block before any of its windows is
+// extracted and hashed; the keys keep words 0..2.
+__host__ __device__ __forceinline__ u32 gvs_fp_bit(u32 hb) { return (hb * 0x85EBCA6Bu) >> 27; }
 // Presence filter in front of the blocked filter: one 32-bit word per sub-mer hash, 2 bits; answers "is
 // this (K-J+1)-mer a sub-mer of any SUNK" from L2, so that only the window groups that pass (a few % for
 // a 150 Mbp database, ~20 % for a whole genome whose 1.4e8 sub-mers saturate the 64 MiB that L2 can hold)

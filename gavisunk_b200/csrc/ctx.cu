@@ -241,6 +241,13 @@ extern "C" int gvs_set_copy_pipeline(gvs_ctx* ctx, uint64_t min_bytes, uint32_t 
   return 0;
 }
 
+extern "C" int gvs_set_probe_variant(gvs_ctx* ctx, int variant) {
+  if (!ctx) return GVS_E_ARG;
+  if (variant < 0 || variant > 2) return gvs_fail(ctx, GVS_E_ARG, "probe variant must be 0, 1 or 2");
+  ctx->probe_variant = variant;
+  return 0;
+}
+
 extern "C" int gvs_set_host_pack(gvs_ctx* ctx, int mode, int threads) {
   if (!ctx) return GVS_E_ARG;
   if (mode < GVS_PACK_OFF || mode > GVS_PACK_ALTERNATE) return gvs_fail(ctx, GVS_E_ARG, "unknown host pack mode %d", mode);

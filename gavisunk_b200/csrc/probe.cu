@@ -98,6 +98,8 @@ struct WarpSmem {
   u16 inv[32];             // per lane: invalid windows among its 16
   u32 q_row[PW_TILE];      // group queue: block hash of the passing group
   u16 q_p[PW_TILE];        // group queue: group index inside the tile; later: window of a candidate
+  u32 s_blk[32][3];        // large databases: key words of the blocks whose fingerprint bit was set (one round)
+  u16 s_p[32];             // ... and their group index inside the tile
 };
 
 // forward / reverse-complement k-mer of window p (0..511) of the tile whose ring base is `rb`
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           }
           emit_round(row, gi, p);
           fused = true;
-        } else
+        } else if (SMALL) {
         for (u32 base = 0; base < n_ent; base += 32 * RB) {
           uint4 b4[RB];
           u32 pw[RB];
@@ -506,6 +508,57 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
             }
           }
         }
+        } else {
+        // Large database: ONE lane per passing group fetches the group's block (the loads of up to RB rounds
+        // are issued together) and tests the fingerprint bit of the group's sub-mer in word 3 -- most passing
+        // groups are false positives of the saturated presence filter and end here.  Only the windows of the
+        // surviving groups are extracted, hashed and tested against the key words, which by then sit in
+        // shared memory.
+        for (u32 gbase = 0; gbase < n_grp; gbase += 32 * RB) {
+          uint4 b4[RB];
+          u32 hq[RB];
+#pragma unroll
+          for (int r = 0; r < RB; r++) {
+            const u32 q = gbase + 32 * r + lane;
+            hq[r] = 0;
+            b4[r] = make_uint4(0, 0, 0, 0);
+            if (q < n_grp) {
+              hq[r] = sm.q_row[q];
+              b4[r] = p_ldg_v4((const uint4*)P.filt + (hq[r] & P.filt_mask), pol_blk);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < RB; r++) {
+            if (gbase + 32 * r >= n_grp) break;  // warp-uniform
+            const u32 q = gbase + 32 * r + lane;
+            const bool ok = q < n_grp && ((b4[r].w >> gvs_fp_bit(hq[r])) & 1u);
+            const u32 bal = __ballot_sync(ALL, ok);
+            if (bal == 0) continue;  // warp-uniform
+            if (ok) {
+              const u32 slot = __popc(bal & ((1u << lane) - 1));
+              sm.s_p[slot] = sm.q_p[q];
+              sm.s_blk[slot][0] = b4[r].x;
+              sm.s_blk[slot][1] = b4[r].y;
+              sm.s_blk[slot][2] = b4[r].z;
+            }
+            __syncwarp();
+            const u32 n_win = __popc(bal) * J;
+            for (u32 base = 0; base < n_win; base += 32) {
+              const u32 e = base + lane;
+              if (e < n_win) {
+                const u32 sq = e / J, w = e % J;
+                const u32 p = (u32)sm.s_p[sq] * J + w;
+                const bool valid = !((sm.inv[p >> 4] >> (p & 15)) & 1u);
+                const u32 h = gvs_fhash(p_canon_at<K>(sm, rb, p, false));
+                const u32 t = __funnelshift_r(sm.s_blk[sq][0], 0u, h) & __funnelshift_r(sm.s_blk[sq][1], 0u, h >> 5) &
+                              __funnelshift_r(sm.s_blk[sq][2], 0u, h >> 10);
+                if (valid && (t & 1u)) atomicOr(&sm.cand[p >> 5], 1u << (p & 31));
+              }
+            }
+            __syncwarp();
+          }
+        }
+        }
         __syncwarp();
         if (!fused) cm = (sm.cand[lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu;
       }
@@ -519,8 +572,8 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           u64 subr = gvs_revcomp(sub, L);
           uint4 b4 = __ldg((const uint4*)P.filt + (gvs_bhash(sub < subr ? sub : subr) & P.filt_mask));
           u32 h = gvs_fhash(canon);
-          u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
-                  __funnelshift_r(b4.w, 0u, h >> 15);
+          u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10);
+          if (SMALL) t &= __funnelshift_r(b4.w, 0u, h >> 15);  // large databases keep sub-mer fingerprints in word 3
           if (t & 1u) cm |= 1u << i; else cm &= ~(1u << i);
         }
       }
@@ -586,7 +639,7 @@ static probe_fn probe_table(int k, bool packed, bool small) {
 int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   u64 total = ctx->total_bases;
   u64 n_tiles = cdiv(total, PW_TILE);
-  probe_fn fn = probe_table(ctx->k, ctx->seq_packed, ctx->filt_words * 16 <= (32ull << 20));
+  probe_fn fn = probe_table(ctx->k, ctx->seq_packed, !ctx->filt_fp);  // the variant follows the block layout (table.cu)
   if (!fn) return gvs_fail(ctx, GVS_E_ARG, "no probe kernel for k=%d", ctx->k);
   u64* counters = ctx->counters.as<u64>();
   Probe2Params P;
@@ -685,7 +738,7 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
       // submitter has queued it, then scan it with the variant of its kind
       CKR(gvs_pipe_wait(ctx, plan[s].ev));
       if (!ctx->seg_packed.empty() && ctx->seg_packed[plan[s].ev]) {
-        fn_s = probe_table(ctx->k, true, ctx->filt_words * 16 <= (32ull << 20));
+        fn_s = probe_table(ctx->k, true, !ctx->filt_fp);
         P.seq = ctx->own_words.as<u8>();
       }
       CK(cudaStreamWaitEvent(ctx->stream, ctx->seg_ev[plan[s].ev], 0));

@@ -28,7 +28,7 @@ __global__ void k_tab_mark_db(const u64* __restrict__ kmer, u64 n, u64* keys, u3
   }
 }
 __global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slots, u32* filt, u64 filt_blocks, int k,
-                               u32* filt1, u32 filt1_mask) {
+                               u32* filt1, u32 filt1_mask, int fp_layout) {
   const int J = GVS_FJ(k), L = k - J + 1;
   const u64 lmask = (L >= 32) ? ~0ull : ((1ull << (2 * L)) - 1);
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
@@ -52,7 +52,7 @@ __global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slot
       atomicOr(&filt[4 * blk + 0], 1u << (h & 31));
       atomicOr(&filt[4 * blk + 1], 1u << ((h >> 5) & 31));
       atomicOr(&filt[4 * blk + 2], 1u << ((h >> 10) & 31));
-      atomicOr(&filt[4 * blk + 3], 1u << ((h >> 15) & 31));
+      atomicOr(&filt[4 * blk + 3], 1u << (fp_layout ? gvs_fp_bit(hb) : ((h >> 15) & 31)));
     }
   }
 }
@@ -112,6 +112,8 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
   if (fw < (1ull << 10)) fw = 1ull << 10;
   if (fw > (1ull << 27)) fw = 1ull << 27;
   ctx->filt_words = fw;  // number of blocks
+  // beyond L2 (or forced by gvs_set_probe_variant): the large-database probe variant and its block layout
+  ctx->filt_fp = ctx->probe_variant == 2 || (ctx->probe_variant == 0 && fw * 16 > (32ull << 20));
   CKR(gvs_reserve(ctx, ctx->filt, fw * 16));
   // presence filter of the sub-mers in front of it: ~16 bits per distinct sub-mer, at most 64 MiB (L2)
   {
@@ -134,7 +136,7 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
     LAUNCH(k_tab_mark_db, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
   }
   LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u32>(), fw, ctx->k,
-         ctx->filt1.as<u32>(), (u32)(ctx->filt1_words - 1));
+         ctx->filt1.as<u32>(), (u32)(ctx->filt1_words - 1), ctx->filt_fp ? 1 : 0);
   return 0;
 }
 

@@ -272,6 +272,11 @@ class Engine:
 
     PACK_OFF, PACK_ADAPTIVE, PACK_ALL, PACK_ALTERNATE = 0, 1, 2, 3
 
+    def set_probe_variant(self, variant: int = 0):
+        """0: probe instantiation by database size, 1: small-database, 2: large-database (call before the
+        database is loaded / built; results are identical)."""
+        self._ck(self.lib.gvs_set_probe_variant(self.ctx, int(variant)))
+
     def set_host_pack(self, mode: int = 1, threads: int = 0):
         """How the segments of a pipelined ASCII host batch travel: as they are (PACK_OFF), 2-bit packed by
         `threads` host threads (PACK_ALL), or whichever keeps both the PCIe link and the cores busy

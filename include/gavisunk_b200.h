@@ -99,6 +99,13 @@ int gvs_db_load_loc(gvs_ctx* ctx, const uint64_t* db_kmer, uint64_t n_db,
 int gvs_db_build(gvs_ctx* ctx, const uint8_t* seq, const uint64_t* contig_off, uint32_t n_contigs,
                  int seq_on_device);
 
+/* The probe kernel has two instantiations, chosen by the size of the database when it is loaded / built: one for
+ * databases whose blocked filter stays L2-resident (<= 32 MiB) and one for larger ones (sub-mer fingerprint in
+ * every filter block, grouped block loads).  variant = 0: by size (default), 1: small-database, 2: large-database
+ * -- results are identical; tests force either one on the golden cases.  Takes effect at the next
+ * gvs_db_load_loc / gvs_db_build (the filter layout is part of the database). */
+int gvs_set_probe_variant(gvs_ctx* ctx, int variant);
+
 int gvs_db_size(gvs_ctx* ctx, uint64_t* n_sunks, uint64_t* n_groups);
 /* kmer.loc rows in file order ((contig, start) order for a built database): host buffers of
  * n_sunks entries each; any pointer may be NULL. */

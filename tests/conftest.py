@@ -38,9 +38,12 @@ def parse_case_db(case):
     return db_lines, loc_rows
 
 
-def engine_from_case(case, contig_names=None):
+def engine_from_case(case, contig_names=None, variant=0):
+    """variant: 0 = probe instantiation by database size (small for every golden case), 2 = the large-database
+    instantiation (whole-genome filter layout) forced onto the case"""
     from gavisunk_b200.engine import Engine
     eng = Engine(case["k"])
+    eng.set_probe_variant(variant)
     db_lines, loc_rows = parse_case_db(case)
     eng.load_loc_text(db_lines, loc_rows, contig_names)
     return eng, eng.contig_names

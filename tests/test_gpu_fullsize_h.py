@@ -1,8 +1,9 @@
 """BASELINE.json config 4 at FULL per-GPU size: 3.1 Gbp x2 diploid assembly in 23 contigs per haplotype
 (1.2e8 SUNKs, whole-genome two-level filter with a saturated presence filter), one GPU's shard of the 30x
-ultra-long reads (3.75x = 11.5 Gbp).  Neither the Python oracle nor the reference executables (33 GB and
-minutes of text parsing per process) can hold this database, so the checks are the size-independent ones:
-properties of the reference algorithm, idempotence, and equality of the pipelined host-copy path."""
+ultra-long reads (3.75x = 11.5 Gbp).  The reference executables cannot hold this database (33 GB and minutes
+of text parsing per process), so the checks are the size-independent ones -- properties of the reference
+algorithm, idempotence, equality of the pipelined host-copy path -- plus the oracle's match on a sample of
+reads against the exported 1.2e8-SUNK database (membership vectorised in numpy, row rules by the oracle)."""
 import numpy as np
 import pytest
 
@@ -39,6 +40,45 @@ def test_sizes_are_config4(full_h):
     assert n_sunks > 100_000_000 and n_groups > 5_000_000 and len(wl.contig_names) == 46
     assert wl.total_bases > 11_000_000_000 and len(res["rows"]["read"]) > 8_000_000
     assert len(res["iv"]["start"]) > 10_000 and len(res["gaps"]["start"]) > 10_000
+
+
+def test_sample_of_reads_against_oracle_config4(full_h):
+    """sunkpos rows of the first reads of one chunk per haplotype, produced by the LARGE-database probe
+    instantiation on the whole-genome table, against oracle.match_chunk (kmerpos_annot3.nim:81-97).  The oracle
+    gets the database restricted to the SUNKs the sample can hit at all (found with its own window encoder and a
+    sorted-array membership over all 1.2e8 exported k-mers) -- the restriction cannot change its output."""
+    import gavisunk_oracle as O
+    eng, wl, res = full_h
+    db = eng.db_export()
+    order = np.argsort(db["kmer"], kind="stable")
+    keys = db["kmer"][order]
+    assert np.all(keys[1:] != keys[:-1])
+    off = res["off"]
+    cf = wl.chunk_first.astype(np.int64)
+    rows = res["rows"]
+    n_checked = 0
+    for hap in (0, 1):
+        chunk = int(np.nonzero(np.asarray(wl.chunk_hap) == hap)[0][1])
+        r0 = int(cf[chunk])
+        r1 = r0 + 60
+        seq = wl.reads[int(off[r0]):int(off[r1])].cpu().numpy()
+        reads = [(i, seq[off[i] - off[r0]:off[i + 1] - off[r0]].tobytes()) for i in range(r0, r1)]
+        hit_rows = []
+        for _, s in reads:
+            canon = O.canonical_windows(O.codes_of(s), K)
+            idx = np.minimum(np.searchsorted(keys, canon), len(keys) - 1)
+            hit_rows.append(order[idx[keys[idx] == canon]])
+        sub = np.unique(np.concatenate(hit_rows))
+        loc = [(int(c), int(s), int(k), int(g)) for c, s, k, g in
+               zip(db["contig"][sub], db["start"][sub], db["kmer"][sub], db["group"][sub])]
+        want = O.match_chunk(reads, db["kmer"][sub], loc, K)
+        lo, hi = np.searchsorted(rows["read"], [r0, r1])
+        got = list(zip(rows["read"][lo:hi].tolist(), rows["pos"][lo:hi].tolist(), rows["contig"][lo:hi].tolist(),
+                       rows["start"][lo:hi].tolist(), rows["group"][lo:hi].tolist()))
+        # the chunk starts at r0, so the prevLoc carry of the full batch restarts exactly there
+        assert got == want
+        n_checked += len(want)
+    assert n_checked > 3000
 
 
 def test_properties_config4(full_h):

@@ -8,28 +8,34 @@ from conftest import load_golden, engine_from_case, run_match_chunks
 pytestmark = pytest.mark.gpu
 
 
+VARIANTS = [0, 2]  # probe instantiation: by size (= small-database for the golden cases) / large-database forced
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("name", ["kat_b1", "kat_bytes"])
-def test_match_kats(name):
+def test_match_kats(name, variant):
     case = load_golden(name)
-    eng, names = engine_from_case(case)
+    eng, names = engine_from_case(case, variant=variant)
     got = run_match_chunks(eng, names, [case["reads"]])
     assert got[0] == case["out"]
 
 
 @pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31", "ragged_k16"])
-def test_match_random_per_chunk(name):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_match_random_per_chunk(name, variant):
     case = load_golden(name)
-    eng, names = engine_from_case(case)
+    eng, names = engine_from_case(case, variant=variant)
     for ch in case["chunks"]:
         got = run_match_chunks(eng, names, [ch["reads"]])
         assert got[0] == ch["sunkpos"]
 
 
 @pytest.mark.parametrize("name", ["rand_k20", "rand_k20_many", "ragged_k20", "ragged_k31"])
-def test_match_random_batched_chunks(name):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_match_random_batched_chunks(name, variant):
     """all chunk files of a sample in ONE batch: the prevLoc carry must restart per chunk (Q4)"""
     case = load_golden(name)
-    eng, names = engine_from_case(case)
+    eng, names = engine_from_case(case, variant=variant)
     got = run_match_chunks(eng, names, [ch["reads"] for ch in case["chunks"]])
     for g, ch in zip(got, case["chunks"]):
         assert g == ch["sunkpos"]
@@ -44,7 +50,7 @@ def test_match_copy_pipeline(name, segments, pack):
     segments were 2-bit packed by the host threads on their way (gvs_set_host_pack: none / the library's
     choice / all / every other one, i.e. ASCII and packed probe variants side by side in one batch)"""
     case = load_golden(name)
-    eng, names = engine_from_case(case)
+    eng, names = engine_from_case(case, variant=2 if (pack + segments) % 2 else 0)
     eng.set_copy_pipeline(0, segments)
     eng.set_host_pack(pack, 3)
     chunks = [ch["reads"] for ch in case["chunks"]] if "chunks" in case else [case["reads"]]
@@ -59,13 +65,14 @@ def test_match_copy_pipeline(name, segments, pack):
 
 @pytest.mark.parametrize("name", ["kat_b1", "kat_bytes", "rand_k20", "rand_k16", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31"])
 @pytest.mark.parametrize("segments", [1, 5])
-def test_match_packed_host_reads(name, segments):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_match_packed_host_reads(name, segments, variant):
     """bases packed to 2 bits on the host (gvs_pack_2bit = kmer.encode's byte map) and matched by the PACKED
     probe variant: rows identical to the reference ELF output, with and without the copy pipeline"""
     from conftest import pack_chunks, format_rows
     from gavisunk_b200.engine import pack_2bit
     case = load_golden(name)
-    eng, names = engine_from_case(case)
+    eng, names = engine_from_case(case, variant=variant)
     eng.set_copy_pipeline(0, segments)
     chunks = [ch["reads"] for ch in case["chunks"]] if "chunks" in case else [case["reads"]]
     want = [ch["sunkpos"] for ch in case["chunks"]] if "chunks" in case else [case["out"]]
