@@ -180,7 +180,10 @@ int gvs_set_copy_pipeline(gvs_ctx* ctx, uint64_t min_bytes, uint32_t segments);
  *                      a buffer that is not page-locked is always packed
  *   GVS_PACK_ALL       every segment packed
  *   GVS_PACK_ALTERNATE odd segments packed (tests: both kinds in one batch, deterministic)
- * threads = 0: the cores this process may run on, at most 16.  With packing enabled a background thread of
+ * threads = 0: the cores this process may run on, at most 16.  Processes that share one host should split its
+ * cores (threads = cores / processes) and switch the packing off below ~12 threads each: packers and DMA reads
+ * share the host's memory bandwidth (8 x 4 threads measured 8 % slower than ASCII copies, profiles/README.md).
+ * With packing enabled a background thread of
  * the library reads `seq` until gvs_match has returned: the buffer must stay unchanged until then (the same
  * holds for the asynchronous copies of GVS_PACK_OFF). */
 enum { GVS_PACK_OFF = 0, GVS_PACK_ADAPTIVE = 1, GVS_PACK_ALL = 2, GVS_PACK_ALTERNATE = 3 };
