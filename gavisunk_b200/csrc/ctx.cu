@@ -434,7 +434,7 @@ static int reads_set_impl(gvs_ctx* ctx, const uint8_t* seq, bool packed, const u
     ctx->seg_packed.clear();
     const u64 n_tiles = cdiv(total, GVS_TILE_BASES);
     // ASCII batches large enough for the pipeline may have their segments packed on the host
-    int mode = packed ? GVS_PACK_OFF : ctx->pack_mode;
+    int mode = (packed || ctx->k >= 32) ? GVS_PACK_OFF : ctx->pack_mode;  // k = 32 has its own one-kernel match (match.cu)
     u64 n_seg = (nbytes >= ctx->seg_min_bytes && ctx->seg_count > 1) ? ctx->seg_count : 1;
     if (n_seg > 1 && mode != GVS_PACK_OFF && !ctx->seg_count_set) n_seg = GVS_SEG_COUNT_PACK;
     if (n_seg > n_tiles) n_seg = n_tiles ? n_tiles : 1;

@@ -83,6 +83,121 @@ __global__ void __launch_bounds__(256) k_emit_rows(const u32* __restrict__ hread
 }
 
 
+// ---- SUNK_len = 32 ------------------------------------------------------------------------------------
+// The reference's k-mer iterator breaks at k = 32 (nim-kmer 0.2.6 `forward_add` masks with (1 shl 2k) - 1 = 0,
+// SURVEY Q2) but kmerpos_annot3 still prints rows; tests/golden/kat_k32, kat_k32b and ksweep[k=32] pin what it
+// yields through the executable: window 0 = min(fwd, rc | 3) (the forward value is exact, the reverse
+// complement comes out with its last base read as T), window w >= 1 = min(code(seq[w+31]), rc) (the
+// forward value keeps only the incoming base, the rolling reverse complement stays right).  Outside
+// BASELINE.json's sweep and of no use to anybody, so no tiles and no filters: one thread per window, the hits
+// go straight into the ordered hit arrays and the common emit pass takes over.
+struct K32View {
+  const u8* seq;
+  int packed;
+  const u64* read_off;
+  u64 n_reads, total;
+  TabView tab;
+  u32* flags;
+};
+__device__ __forceinline__ u32 k32_code(const K32View& v, u64 g) {
+  if (v.packed) return (((const u32*)v.seq)[g >> 4] >> (30 - 2 * (int)(g & 15))) & 3u;
+  const u32 x = v.seq[g], l = x | 0x20u;
+  if (l == 'c') return 1;
+  if (l == 'g') return 2;
+  if (l == 't' || l == 'u') return 3;
+  return x <= 3 ? x : 0;  // A/a and everything else 0, bytes 1..3 themselves (kat_bytes)
+}
+// hit of the window that starts at base g: .loc row (or GVS_NOHIT); *rd / *w = read and window index
+__device__ u32 k32_hit(const K32View& v, u64 g, u32* rd, u32* w, u32* gi) {
+  u64 lo = 1, hi = v.n_reads;  // first boundary index j >= 1 with read_off[j] > g
+  while (lo < hi) {
+    u64 mid = (lo + hi) >> 1;
+    if (v.read_off[mid] > g) hi = mid; else lo = mid + 1;
+  }
+  const u64 r = lo - 1, o0 = v.read_off[r], o1 = v.read_off[r + 1];
+  if (g < o0 || g >= o1) return GVS_NOHIT;
+  const u64 len = o1 - o0, win = g - o0;
+  const u64 n_win = len >= 32 ? len - 31 : (len == 31 ? 1 : 0);  // a 31-long read: one window, NUL read as A (Q6)
+  if (win >= n_win) return GVS_NOHIT;
+  u64 f = 0, rc = 0;
+  u32 last = 0;
+  for (int j = 0; j < 32; j++) {
+    last = (g + j < o1) ? k32_code(v, g + j) : 0u;
+    f = (f << 2) | last;
+    rc |= (u64)(3u - last) << (2 * j);
+  }
+  u64 val;
+  if (win == 0) {
+    rc |= 3ull;
+    val = f < rc ? f : rc;
+  } else {
+    val = (u64)last < rc ? (u64)last : rc;
+  }
+  u32 row = tab_lookup(v.tab, val, gvs_mix(val), gi);
+  if (row == GVS_ROW_MISSING) {
+    atomicOr(v.flags, FLAG_KEYERROR);
+    return GVS_NOHIT;
+  }
+  if (row >= GVS_NOHIT) return GVS_NOHIT;
+  *rd = (u32)r;
+  *w = (u32)win;
+  return row;
+}
+
+static int match_k32(gvs_ctx* ctx, u64* n_hits) {
+  StageTimer tm(ctx, GVS_ST_PROBE);
+  u64* counters = ctx->counters.as<u64>();
+  CK(cudaMemsetAsync(counters, 0, 4 * sizeof(u64), ctx->stream));
+  if (!ctx->seg_packed.empty()) return gvs_fail(ctx, GVS_E_STATE, "k = 32: host batches are not packed on the way");
+  K32View v;
+  v.seq = ctx->seq;
+  v.packed = ctx->seq_packed ? 1 : 0;
+  v.read_off = ctx->read_off;
+  v.n_reads = ctx->n_reads;
+  v.total = ctx->total_bases;
+  v.tab.keys = ctx->tab_keys.as<u64>();
+  v.tab.val = ctx->tab_gidx.as<u64>();
+  v.tab.slots = ctx->tab_slots;
+  v.flags = (u32*)(counters + 1);
+  // the segments of a pipelined host batch must have landed (gvs_probe_launch waits per segment)
+  for (size_t s = 0; s < ctx->seg_tile_end.size() && ctx->seq == ctx->own_seq.as<u8>(); s++)
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->seg_ev[s], 0));
+  auto f = [v] __device__(u64 i) -> u64 {
+    u32 rd, w, gi;
+    return k32_hit(v, i, &rd, &w, &gi) != GVS_NOHIT ? 1ull : 0ull;
+  };
+  auto g0 = [] __device__(u64 i, u64 ex, u64 val) {};
+  CKR((device_scan<u64>(ctx, v.total, f, g0, OpSum(), counters)));
+  u64 h[2];
+  CKR(read_dev(ctx, counters, h, 2));
+  if ((u32)h[1] & FLAG_KEYERROR)
+    return gvs_fail(ctx, GVS_E_KEYERROR, "KeyError: a read matched a db k-mer that has no .loc row (kmerpos_annot3.nim:90)");
+  const u64 nh = h[0];
+  *n_hits = nh;
+  if (nh == 0) return 0;
+  if (nh >= 0xFFFFFFF0ull) return gvs_fail(ctx, GVS_E_OVERFLOW, "more than 2^32 hits in one batch");
+  CKR(gvs_reserve(ctx, ctx->ohit_read, nh * 4));
+  CKR(gvs_reserve(ctx, ctx->ohit_w, nh * 4));
+  CKR(gvs_reserve(ctx, ctx->ohit_row, nh * 4));
+  CKR(gvs_reserve(ctx, ctx->ohit_gidx, nh * 4));
+  CKR(gvs_reserve(ctx, ctx->ohit_nf, nh));
+  u32 *o_rd = ctx->ohit_read.as<u32>(), *o_w = ctx->ohit_w.as<u32>(), *o_row = ctx->ohit_row.as<u32>(),
+      *o_gi = ctx->ohit_gidx.as<u32>();
+  u8* o_nf = ctx->ohit_nf.as<u8>();
+  auto g1 = [v, o_rd, o_w, o_row, o_gi, o_nf] __device__(u64 i, u64 ex, u64 val) {
+    if (!val) return;
+    u32 rd = 0, w = 0, gi = 0;
+    u32 row = k32_hit(v, i, &rd, &w, &gi);
+    o_rd[ex] = rd;
+    o_w[ex] = w;
+    o_row[ex] = row;
+    o_gi[ex] = gi;
+    o_nf[ex] = 0;
+  };
+  CKR((device_scan<u64>(ctx, v.total, f, g1, OpSum(), (u64*)nullptr)));
+  return 0;
+}
+
 static int match_once(gvs_ctx* ctx, u64* n_warps, u64* cap_w, bool* overflow, u64* total_hits, u64* max_per_warp) {
   u64* counters = ctx->counters.as<u64>();
   CK(cudaMemsetAsync(counters, 0, 4 * sizeof(u64), ctx->stream));
@@ -127,28 +242,29 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
   }
   if (((uintptr_t)ctx->seq & 15) != 0) return gvs_fail(ctx, GVS_E_ARG, "read buffer must be 16-byte aligned");
   u64 n_warps = 0, cap_w = 0;
-  if (ctx->k >= 32) {  // Q2: k = 32 yields no hits in the reference (mask overflow in kmer.slide)
-    ctx->match_ready = true;
-    return 0;
-  }
-  // hit capacity: start at 1/32 of the windows (typical density is <1 %), retry once with the
-  // exact need if a batch is denser
-  if (ctx->hit_cap == 0) ctx->hit_cap = total / 32 + 4096;
-  for (int attempt = 0;; attempt++) {
-    CKR(gvs_reserve(ctx, ctx->hit_read, ctx->hit_cap * 4));
-    CKR(gvs_reserve(ctx, ctx->hit_w, ctx->hit_cap * 4));
-    CKR(gvs_reserve(ctx, ctx->hit_row, ctx->hit_cap * 4));
-    CKR(gvs_reserve(ctx, ctx->hit_gidx, ctx->hit_cap * 4));
-    CKR(gvs_reserve(ctx, ctx->hit_nf, ctx->hit_cap));
-    bool overflow = false;
-    u64 need = 0, max_w = 0;
-    CKR(match_once(ctx, &n_warps, &cap_w, &overflow, &need, &max_w));
-    if (!overflow) {
-      ctx->n_hits = need;
-      break;
+  const bool k32 = ctx->k >= 32;  // Q2: the reference's broken-but-deterministic k = 32 (match_k32)
+  if (k32) {
+    CKR(match_k32(ctx, &ctx->n_hits));
+  } else {
+    // hit capacity: start at 1/32 of the windows (typical density is <1 %), retry once with the
+    // exact need if a batch is denser
+    if (ctx->hit_cap == 0) ctx->hit_cap = total / 32 + 4096;
+    for (int attempt = 0;; attempt++) {
+      CKR(gvs_reserve(ctx, ctx->hit_read, ctx->hit_cap * 4));
+      CKR(gvs_reserve(ctx, ctx->hit_w, ctx->hit_cap * 4));
+      CKR(gvs_reserve(ctx, ctx->hit_row, ctx->hit_cap * 4));
+      CKR(gvs_reserve(ctx, ctx->hit_gidx, ctx->hit_cap * 4));
+      CKR(gvs_reserve(ctx, ctx->hit_nf, ctx->hit_cap));
+      bool overflow = false;
+      u64 need = 0, max_w = 0;
+      CKR(match_once(ctx, &n_warps, &cap_w, &overflow, &need, &max_w));
+      if (!overflow) {
+        ctx->n_hits = need;
+        break;
+      }
+      if (attempt >= 1) return gvs_fail(ctx, GVS_E_OVERFLOW, "hit buffer overflow after resize");
+      ctx->hit_cap = (max_w + max_w / 4 + 64) * n_warps;  // every warp region must hold the densest span
     }
-    if (attempt >= 1) return gvs_fail(ctx, GVS_E_OVERFLOW, "hit buffer overflow after resize");
-    ctx->hit_cap = (max_w + max_w / 4 + 64) * n_warps;  // every warp region must hold the densest span
   }
   u64 nh = ctx->n_hits;
   if (nh == 0) {
@@ -157,15 +273,17 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
   }
   if (nh >= 0xFFFFFFF0ull) return gvs_fail(ctx, GVS_E_OVERFLOW, "more than 2^32 hits in one batch");
   StageTimer tm(ctx, GVS_ST_EMIT);
-  // ---- order the hits ----
-  CKR(gvs_reserve(ctx, ctx->ohit_read, nh * 4));
-  CKR(gvs_reserve(ctx, ctx->ohit_w, nh * 4));
-  CKR(gvs_reserve(ctx, ctx->ohit_row, nh * 4));
-  CKR(gvs_reserve(ctx, ctx->ohit_gidx, nh * 4));
-  CKR(gvs_reserve(ctx, ctx->ohit_nf, nh));
-  LAUNCH(k_gather_hits, (unsigned)n_warps, 128, 0, ctx->tile_cnt.as<u32>(), ctx->tile_dst.as<u64>(), cap_w, ctx->hit_read.as<u32>(),
-         ctx->hit_w.as<u32>(), ctx->hit_row.as<u32>(), ctx->hit_gidx.as<u32>(), ctx->hit_nf.as<u8>(), ctx->ohit_read.as<u32>(),
-         ctx->ohit_w.as<u32>(), ctx->ohit_row.as<u32>(), ctx->ohit_gidx.as<u32>(), ctx->ohit_nf.as<u8>());
+  if (!k32) {
+    // ---- order the hits ----
+    CKR(gvs_reserve(ctx, ctx->ohit_read, nh * 4));
+    CKR(gvs_reserve(ctx, ctx->ohit_w, nh * 4));
+    CKR(gvs_reserve(ctx, ctx->ohit_row, nh * 4));
+    CKR(gvs_reserve(ctx, ctx->ohit_gidx, nh * 4));
+    CKR(gvs_reserve(ctx, ctx->ohit_nf, nh));
+    LAUNCH(k_gather_hits, (unsigned)n_warps, 128, 0, ctx->tile_cnt.as<u32>(), ctx->tile_dst.as<u64>(), cap_w, ctx->hit_read.as<u32>(),
+           ctx->hit_w.as<u32>(), ctx->hit_row.as<u32>(), ctx->hit_gidx.as<u32>(), ctx->hit_nf.as<u8>(), ctx->ohit_read.as<u32>(),
+           ctx->ohit_w.as<u32>(), ctx->ohit_row.as<u32>(), ctx->ohit_gidx.as<u32>(), ctx->ohit_nf.as<u8>());
+  }
   // ---- suppression + position drift ----
   CKR(gvs_reserve(ctx, ctx->flags_a, nh));          // u8 flags
   CKR(gvs_reserve(ctx, ctx->flags_b, nh * 8));      // packed exclusive counts

@@ -58,8 +58,10 @@ enum {
 /* ------------------------------------------------------------------------------------------ */
 /* context                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
-/* k = SUNK_len (config/config.yaml:2).  1 <= k <= 31 (k = 32 yields no hits in the reference,
- * SURVEY Q2; it is accepted here and produces zero hits as well). */
+/* k = SUNK_len (config/config.yaml:2).  1 <= k <= 32.  At k = 32 the reference's k-mer iterator is broken
+ * (nim-kmer 0.2.6: the forward mask (1 shl 2k) - 1 is 0) but deterministic: window 0 yields min(fwd, rc | 3),
+ * window w >= 1 yields min(code(seq[w+31]), rc) -- pinned through the executable by tests/golden/kat_k32,
+ * kat_k32b, ksweep -- and gvs_match reproduces exactly that (one plain kernel, no filters: of no practical use). */
 gvs_ctx* gvs_create(int device, int k);
 void gvs_destroy(gvs_ctx* ctx);
 const char* gvs_last_error(gvs_ctx* ctx);

@@ -161,7 +161,7 @@ def match_chunk(reads, db_kmers, loc_rows, k):
     for (c, s, km, g) in loc_rows:
         coords[int(km)] = (c, int(s), int(g))
     out = []
-    if k > 31:  # Q2: k=32 yields zero hits (mask overflow inside kmer.slide)
+    if k > 32:
         return out
     prev = ("", 0)  # kmerpos_annot3.nim:82-84, declared outside the read loop (Q4)
     # sorted key array for vectorised membership
@@ -172,6 +172,24 @@ def match_chunk(reads, db_kmers, loc_rows, k):
         if len(seq) < k:
             continue  # shorter reads: reference reads heap garbage (undefined) -> no windows
         canon = canonical_windows(codes_of(seq), k)
+        if k == 32 and len(canon) > 0:
+            # Q2, pinned by tests/golden/kat_k32{,b} + ksweep[k=32] through the ELF.  nim-kmer's forward_add masks
+            # with (1 shl 2k) - 1, which is 0 for k = 32: after the first window the forward value keeps only the
+            # code of the incoming base, while the rolling reverse-complement value stays right.  In the first
+            # window the forward value is exact and the reverse-complement value comes out with its last base
+            # (the complement of the read's first base) read as T.  Hence window 0 yields min(fwd, rc | 3) and
+            # window w >= 1 yields min(code(seq[w+31]), rc).
+            c = codes_of(seq).astype(np.uint64)
+            n = len(canon)
+            f0 = np.uint64(0)
+            for j in range(k):
+                f0 |= c[j] << np.uint64(2 * (k - 1 - j))
+            r = np.zeros(n, dtype=np.uint64)
+            for j in range(k):
+                r |= (np.uint64(3) - c[j:j + n]) << np.uint64(2 * j)
+            canon = canon.copy()
+            canon[0] = min(f0, r[0] | np.uint64(3))
+            canon[1:] = np.minimum(c[k:k + n - 1], r[1:])
         if len(keys) == 0:
             continue
         idx = np.searchsorted(keys, canon)

@@ -354,7 +354,73 @@ def hg02723_asm():
     return dict(h1=open(T + "h1.fa").read(), h2=open(T + "h2.fa").read())
 
 
+KSWEEP = [2, 3, 5, 6, 7, 8, 9, 11, 12, 13, 15, 17, 19, 21, 23, 25, 27, 28, 29, 30, 32]
+
+
+def ksweep_case(seed, k):
+    """every SUNK_len the library accepts besides the ones of BASELINE.json's sweep (16/20/24/31, the rand_* and
+    ragged_* cases) and the k=4 KATs: small related haplotypes sized to the k-mer space (so that SUNKs exist even for
+    k=2), reads that are error-free substrings (dense hit runs), mutated substrings, random sequence, reads of length
+    k-1 / k / k+1, lower case and N tails; k=32 is the reference's mask-overflow case (Q2).  No read is shorter than
+    k-1: the reference then reads whatever the previous records left in readfq's buffer (Q6, undefined), which at
+    small k hits SUNKs by chance (the ragged_* cases hold such reads at k = 16 / 20 / 31, where it cannot).  One FASTA
+    and one FASTQ chunk per haplotype through the reference executables."""
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    L = {2: 7, 3: 14, 5: 120, 6: 400, 7: 1200}.get(k, 3000)
+    hap1, hap2 = [], []
+    for c in range(2):
+        s = alphabet[rng.integers(0, 4, L)]
+        t = s.copy()
+        snp = rng.random(L) < max(0.004, 2.0 / L)
+        snp[int(rng.integers(0, L))] = True
+        t[snp] = alphabet[(O.BASE_LUT[s[snp]] + rng.integers(1, 4, int(snp.sum()))) % 4]
+        hap1.append((f"h1c{c}", s.tobytes()))
+        hap2.append((f"h2c{c}", t.tobytes()))
+    contigs = hap1 + hap2
+    db_txt, loc_txt = db_loc_text(contigs, k)
+    case = dict(k=k, db=db_txt, loc=loc_txt,
+                fai1="".join(f"{n}\t{len(s)}\t0\t60\t61\n" for n, s in hap1),
+                fai2="".join(f"{n}\t{len(s)}\t0\t60\t61\n" for n, s in hap2), chunks=[])
+    for hapi, hap in ((1, hap1), (2, hap2)):
+        reads = []
+        for i in range(64):
+            src = np.frombuffer(hap[i % 2][1], dtype=np.uint8)
+            if i % 8 == 0:
+                ln = [k - 1, k, k + 1, k + 2][(i // 8) % 4]
+            elif i % 8 < 4:
+                ln = int(rng.integers(k - 1, 3 * k + 2))
+            else:
+                ln = int(rng.integers(4 * k, 16 * k + 40))
+            ln = max(min(ln, len(src)), k - 1)
+            st = int(rng.integers(0, len(src) - ln + 1))
+            r = src[st:st + ln].copy()
+            if i % 4 == 1 and ln > 3 * k:
+                r = mutate(rng, r)
+            if i % 8 == 7:
+                r = alphabet[rng.integers(0, 4, int(rng.integers(k, 300)))]  # random sequence: hits by chance (small k)
+            if i % 4 == 1 and len(r) < k - 1:
+                r = src[:k - 1].copy()  # a mutated read may have lost bases
+            if i % 2:
+                r = rc_bytes(r)
+            if i % 9 == 4 and len(r) > 5:
+                r[-2:] = ord("N")
+            if i % 7 == 2:
+                r = np.frombuffer(r.tobytes().lower(), dtype=np.uint8)
+            reads.append((f"s{hapi}r{i:03d}", r.tobytes()))
+        for ci in range(2):
+            part = reads[ci::2]
+            txt = fasta_text(part, fastq=(ci == 1))
+            rc, sunkpos = run_kmerpos(txt, db_txt, loc_txt)
+            assert rc == 0, (k, rc)
+            case["chunks"].append(dict(hap=hapi, reads=txt.decode("latin-1"), sunkpos=sunkpos, rlen=run_rlen(txt)))
+    return case
+
+
 def main():
+    if sys.argv[1:] == ["ksweep"]:
+        save("ksweep", [ksweep_case(300 + k, k) for k in KSWEEP])
+        return
     save("covprob_amy", covprob_case())
     save("hg02723_asm", hg02723_asm())
     save("kat_b1", kat_b1())

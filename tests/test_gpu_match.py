@@ -12,12 +12,28 @@ VARIANTS = [0, 2]  # probe instantiation: by size (= small-database for the gold
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
-@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes"])
+@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes", "kat_k32", "kat_k32b"])
 def test_match_kats(name, variant):
     case = load_golden(name)
     eng, names = engine_from_case(case, variant=variant)
     got = run_match_chunks(eng, names, [case["reads"]])
     assert got[0] == case["out"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("batched", [False, True])
+def test_match_every_sunk_len(variant, batched):
+    """ksweep: every probe instantiation besides K = 4 / 16 / 20 / 24 / 31 (K = 2, 3 have one window per filter
+    group, the others four) and the one-kernel k = 32 path, per chunk file and with all chunk files in one batch"""
+    for case in load_golden("ksweep"):
+        eng, names = engine_from_case(case, variant=variant)
+        if batched:
+            got = run_match_chunks(eng, names, [ch["reads"] for ch in case["chunks"]])
+            assert got == [ch["sunkpos"] for ch in case["chunks"]], case["k"]
+        else:
+            for ch in case["chunks"]:
+                assert run_match_chunks(eng, names, [ch["reads"]])[0] == ch["sunkpos"], case["k"]
+        eng.close()
 
 
 @pytest.mark.parametrize("name", ["rand_k20", "rand_k16", "rand_k24", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31", "ragged_k16"])
@@ -63,7 +79,7 @@ def test_match_copy_pipeline(name, segments, pack):
             assert npk == {0: 0, 1: nseg, 2: nseg, 3: nseg // 2}[pack]  # 1: pageable source, always packed
 
 
-@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes", "rand_k20", "rand_k16", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31"])
+@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes", "kat_k32b", "rand_k20", "rand_k16", "rand_k31", "rand_k20_many", "ragged_k20", "ragged_k31"])
 @pytest.mark.parametrize("segments", [1, 5])
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_match_packed_host_reads(name, segments, variant):

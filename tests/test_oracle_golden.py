@@ -17,7 +17,7 @@ def _parse_db_loc(case):
     return db, loc
 
 
-@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes"])
+@pytest.mark.parametrize("name", ["kat_b1", "kat_bytes", "kat_k32", "kat_k32b"])
 def test_match_kats(name):
     case = load_golden(name)
     db, loc = _parse_db_loc(case)
@@ -56,6 +56,22 @@ def test_match_and_diag_random(name):
         assert "".join("\t".join(str(x) for x in d) + "\n" for d in diag) == ch["diag"]
         kept = O.diag_filter_step2(rows, diag)
         assert gio.format_sunkpos(kept) == ch["diag2"]
+
+
+def test_match_every_sunk_len():
+    """ksweep: every SUNK_len besides 4 / 16 / 20 / 24 / 31 (2 ... 30 and the reference's broken k = 32, Q2)"""
+    cases = load_golden("ksweep")
+    assert sorted(c["k"] for c in cases) == [2, 3, 5, 6, 7, 8, 9, 11, 12, 13, 15, 17, 19, 21, 23, 25, 27, 28, 29, 30, 32]
+    for case in cases:
+        db, loc = _parse_db_loc(case)
+        n_rows = 0
+        for ch in case["chunks"]:
+            reads = gio.read_fastx(ch["reads"].encode("latin-1"))
+            assert "".join(f"{n}\t{len(s)}\n" for n, s in reads) == ch["rlen"]
+            rows = O.match_chunk(reads, db, loc, case["k"])
+            assert gio.format_sunkpos(rows) == ch["sunkpos"], case["k"]
+            n_rows += len(rows)
+        assert n_rows > 0, case["k"]
 
 
 def test_diag_cases():
