@@ -26,6 +26,20 @@ def test_match_kats(name):
     assert gio.format_sunkpos(rows) == case["out"]
 
 
+def test_match_q7_duplicate_loc_rows_and_orphan_db_kmer():
+    """SURVEY Q7 through the executable: a k-mer listed twice in kmer.loc reports its LAST row
+    (kmerpos_annot3.nim:68), a .loc k-mer that is not in the db set never matches (nim:89), a read that hits a db
+    k-mer without a .loc row ends the run with a KeyError (nim:90: exit code 1 after the rows printed so far)"""
+    case = load_golden("kat_q7")
+    db, loc = _parse_db_loc(case)
+    rows = O.match_chunk(gio.read_fastx(case["reads"].encode("latin-1")), db, loc, case["k"])
+    assert gio.format_sunkpos(rows) == case["out"] and case["rc"] == 0
+    assert "c2\t900\t880" in case["out"] and "c1\t100\t100" not in case["out"] and "\t500\t500" not in case["out"]
+    assert case["rc_keyerror"] != 0
+    with pytest.raises(KeyError):
+        O.match_chunk(gio.read_fastx(case["reads_keyerror"].encode("latin-1")), db, loc, case["k"])
+
+
 def test_b1_expected_rows():
     # SURVEY Appendix B.1 literal expectation
     case = load_golden("kat_b1")
