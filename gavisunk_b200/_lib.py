@@ -98,6 +98,15 @@ class GavisunkError(RuntimeError):
         self.code = code
 
 
+class GavisunkKeyError(GavisunkError, KeyError):
+    """GVS_E_KEYERROR: the reference raises KeyError at this point (kmerpos_annot3.nim:90 for a db k-mer
+    without a .loc row, covprob.py:118,130 for a gap without a group / beyond the table); callers may
+    catch it as either."""
+
+    def __str__(self):  # KeyError.__str__ would repr() the message
+        return RuntimeError.__str__(self)
+
+
 def load():
     """Load the shared library (once) and attach prototypes.  Raises if it is not built."""
     global _lib

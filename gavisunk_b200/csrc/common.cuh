@@ -52,6 +52,10 @@ struct gvs_ctx {
   // side streams for independent launches of one stage (e.g. the row-count tiers of the validation):
   // gvs_fork makes them wait for everything queued on `stream`, gvs_join makes `stream` wait for them
   cudaStream_t aux[2] = {nullptr, nullptr};
+  // per-device one-time settings (a process may drive one context per GPU: no function-level statics)
+  bool val_attr_set = false;                  // dynamic shared memory opt-in of k_validate
+  int l2_persist_max = -1, l2_window_max = 0;  // L2 persistence limits of this device
+  size_t l2_carve_set = 0;
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
   // ---- database ----

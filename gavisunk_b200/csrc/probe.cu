@@ -698,12 +698,12 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   // L2 persistence: the structure every window group touches (the presence filter) is pinned in the
   // persisting carve-out of L2; everything outside the window (reads, exact table, hit lists) is
   // treated as streaming.
-  static int persist_max = -1, window_max = 0;
-  if (persist_max < 0) {
-    cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-    cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-    if (persist_max < 0) persist_max = 0;
+  if (ctx->l2_persist_max < 0) {
+    cudaDeviceGetAttribute(&ctx->l2_persist_max, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&ctx->l2_window_max, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    if (ctx->l2_persist_max < 0) ctx->l2_persist_max = 0;
   }
+  const int persist_max = ctx->l2_persist_max, window_max = ctx->l2_window_max;
   const void* hot = ctx->filt1.p;
   size_t hot_bytes = ctx->filt1_words * 4;
   cudaLaunchConfig_t cfg = {};
@@ -714,10 +714,9 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   int n_attr = 0;
   if (persist_max > 0 && window_max > 0) {
     size_t carve = hot_bytes < (size_t)persist_max ? hot_bytes : (size_t)persist_max;
-    static size_t carve_set = 0;
-    if (carve_set != carve) {
+    if (ctx->l2_carve_set != carve) {
       cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-      carve_set = carve;
+      ctx->l2_carve_set = carve;
     }
     size_t win = hot_bytes < (size_t)window_max ? hot_bytes : (size_t)window_max;
     attr[0].id = cudaLaunchAttributeAccessPolicyWindow;

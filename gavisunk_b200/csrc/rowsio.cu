@@ -89,6 +89,19 @@ extern "C" int gvs_rows_set(gvs_ctx* ctx, int which, const uint32_t* read_idx, c
   if (n && (!read_idx || !pos || !contig || !start || !group)) return gvs_fail(ctx, GVS_E_ARG, "null row column");
   if (ctx->n_chunks == 0) return gvs_fail(ctx, GVS_E_STATE, "gvs_rows_set: call gvs_reads_set / gvs_reads_meta first");
   CK(cudaSetDevice(ctx->device));
+  {
+    // rows index the read table and the contig tables of later stages (read_len[read], contig_hap[contig]): a row
+    // outside them would be an out-of-bounds device read there, so it is refused here
+    const u64 nc = ctx->db_ready ? ctx->n_contigs : n_contigs;
+    for (u64 i = 0; i < n; i++) {
+      if (read_idx[i] >= ctx->n_reads)
+        return gvs_fail(ctx, GVS_E_ARG, "row %llu: read index %u outside the read table (%llu reads)", (unsigned long long)i,
+                        read_idx[i], (unsigned long long)ctx->n_reads);
+      if (contig[i] >= nc)
+        return gvs_fail(ctx, GVS_E_ARG, "row %llu: contig %u outside the contig list (%llu contigs)", (unsigned long long)i, contig[i],
+                        (unsigned long long)nc);
+    }
+  }
   Rows& R = which == 0 ? ctx->rows : ctx->kept;
   CKR(gvs_reserve_rows(ctx, R, n));
   if (n) {

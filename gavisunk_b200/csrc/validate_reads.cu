@@ -72,6 +72,7 @@ template <int NT, int GROUPS, bool GLOBAL>
 __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
   extern __shared__ __align__(16) u8 smem[];
   __shared__ u32 s_n0[GROUPS], s_n1[GROUPS], s_m[GROUPS], s_kept[GROUPS], s_bestroot[GROUPS], s_flag[GROUPS], s_dup[GROUPS];
+  __shared__ u32 s_pmin[GROUPS], s_pmax[GROUPS];  // span of the read's positions (all threads of the group)
   __shared__ unsigned long long s_best[GROUPS];
   __shared__ u32 s_wtot[GROUPS][NT / 32];  // per-warp counts of the order-preserving compaction
   const int grp = threadIdx.x / NT;
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     const u32 mrows = b - a;
     if (mrows <= V.m_lo || mrows > V.m_hi) continue;  // another launch owns this read (group-uniform)
     gsync();
-    if (tid == 0) { s_m[grp] = 0; s_n0[grp] = 0; s_n1[grp] = 0; s_kept[grp] = 0; s_best[grp] = 0; s_bestroot[grp] = NOV; s_flag[grp] = 0; s_dup[grp] = 0; }
+    if (tid == 0) { s_m[grp] = 0; s_n0[grp] = 0; s_n1[grp] = 0; s_kept[grp] = 0; s_best[grp] = 0; s_bestroot[grp] = NOV; s_flag[grp] = 0; s_dup[grp] = 0; s_pmin[grp] = 0xFFFFFFFFu; s_pmax[grp] = 0; }
     gsync();
     // read length filter (hard-coded 10000 in the reference, :106-108; Q13)
     const u32 rd = V.read[a];
@@ -209,8 +210,17 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
         pmin = p < pmin ? p : pmin;
         pmax = p > pmax ? p : pmax;
       }
-      if (pmax >= pmin && pmax - pmin >= (1u << 28)) s_flag[grp] = 2;  // (s_flag is 1 here; 2 = wide read)
-      if (tid == 0 && w.S[m - 1] - w.S[0] >= (1u << 28)) s_flag[grp] = 2;
+      // a thread sees only its strided rows: the span is that of the whole group (warp shuffle, then shared atomics)
+      for (int d = 16; d; d >>= 1) {
+        pmin = min(pmin, __shfl_xor_sync(0xFFFFFFFFu, pmin, d));
+        pmax = max(pmax, __shfl_xor_sync(0xFFFFFFFFu, pmax, d));
+      }
+      if ((tid & 31) == 0 && pmax >= pmin) {
+        atomicMin(&s_pmin[grp], pmin);
+        atomicMax(&s_pmax[grp], pmax);
+      }
+      gsync();
+      if (tid == 0 && (s_pmax[grp] - s_pmin[grp] >= (1u << 28) || w.S[m - 1] - w.S[0] >= (1u << 28))) s_flag[grp] = 2;  // (s_flag is 1 here; 2 = wide read)
       gsync();
       const bool narrow = s_flag[grp] != 2;
       u32 n0 = 0, n1 = 0;
@@ -514,12 +524,11 @@ extern "C" int gvs_validate(gvs_ctx* ctx, uint32_t min_read_len, uint64_t* n_pai
   V.min_len = min_read_len;
   V.out_id = out_id; V.out_gidx = out_gidx; V.seg_cnt = seg_cnt;
   V.gscratch = nullptr; V.big_cap = 0; V.stats = stats;
-  static bool attr_set = false;
   const size_t sm_warp = (size_t)VROW_BYTES * VCAP_WARP * 8, sm_blk = (size_t)VROW_BYTES * VCAP;
-  if (!attr_set) {
+  if (!ctx->val_attr_set) {
     CK(cudaFuncSetAttribute((k_validate<32, 8, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
     CK(cudaFuncSetAttribute((k_validate<256, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
-    attr_set = true;
+    ctx->val_attr_set = true;
   }
   // the three row-count tiers touch disjoint reads and outputs: they run side by side (the few very long
   // reads of the last tier would otherwise be a serial tail)

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import GavisunkError
+from ._lib import GavisunkError, GavisunkKeyError
 
 _LUT = np.zeros(256, dtype=np.uint64)
 for _ch, _v in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("U", 3)):
@@ -120,15 +120,17 @@ class Engine:
         self.contig_names: List[str] = []
         self._keep = []  # host arrays that must outlive async copies
         self._pool: Dict[str, Tuple[int, int]] = {}  # page-locked result buffers: name -> (pointer, bytes)
+        self._retired: List[int] = []                # outgrown page-locked buffers (freed by close())
+        self.stream_ptr = int(stream) if stream else 0  # cudaStream_t all work of this context is queued on (0 = legacy default)
         if stream is not None:
             self._ck(self.lib.gvs_set_stream(self.ctx, C.c_void_p(stream)))
 
     # ------------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "ctx", None):
-            for ptr, _ in getattr(self, "_pool", {}).values():
+            for ptr in [p for p, _ in getattr(self, "_pool", {}).values()] + list(getattr(self, "_retired", [])):
                 self.lib.gvs_host_free(C.c_void_p(ptr))
-            self._pool = {}
+            self._pool, self._retired = {}, []
             self.lib.gvs_destroy(self.ctx)
             self.ctx = None
 
@@ -143,10 +145,11 @@ class Engine:
         ptr, cap = self._pool.get(name, (0, 0))
         if cap < need:
             if ptr:
-                self.sync()
-                self.lib.gvs_host_free(C.c_void_p(ptr))
+                # views handed out by earlier rows(pinned=True) / pairs(pinned=True) calls still point into the old
+                # buffer: it is retired, not freed, and lives until close()
+                self._retired.append(ptr)
             p = C.c_void_p()
-            cap = need + need // 4
+            cap = need + need // 2
             self._ck(self.lib.gvs_host_alloc(cap, C.byref(p)))
             ptr = int(p.value)
             self._pool[name] = (ptr, cap)
@@ -163,7 +166,7 @@ class Engine:
         if rc != 0:
             msg = self.lib.gvs_last_error(self.ctx).decode("utf-8", "replace")
             if rc == _lib.GVS_E_KEYERROR:
-                raise KeyError(msg)
+                raise GavisunkKeyError(rc, msg)
             raise GavisunkError(rc, msg)
 
     def sync(self):

@@ -177,13 +177,8 @@ def read_loc(path: str):
     return contig, start, kmer, group
 
 
-def read_sunkpos(path_or_text):
-    """rows (read, pos, contig, start, group)"""
-    if os.path.exists(path_or_text) if isinstance(path_or_text, str) and "\t" not in path_or_text else False:
-        with open_maybe_gz(path_or_text) as f:
-            text = f.read().decode()
-    else:
-        text = path_or_text
+def parse_sunkpos(text: str):
+    """rows (read, pos, contig, start, group) of sunkpos TEXT (tests, in-memory data)"""
     rows = []
     for l in text.splitlines():
         p = l.split("\t")
@@ -191,6 +186,14 @@ def read_sunkpos(path_or_text):
             continue
         rows.append((p[0], int(p[1]), p[2], int(p[3]), int(p[4])))
     return rows
+
+
+def read_sunkpos(path: str):
+    """rows (read, pos, contig, start, group) of a .sunkpos FILE (plain or gz).  The path must open: a missing
+    or unreadable file raises (FileNotFoundError / OSError) exactly where the reference's tools quit with
+    'cannot open the file' (nim `open`) or pandas raises -- never an empty result."""
+    with open_maybe_gz(os.fspath(path)) as f:
+        return parse_sunkpos(f.read().decode())
 
 
 def format_sunkpos(rows) -> str:

@@ -133,18 +133,43 @@ def alias_device_array(ptr: int, n: int, typestr: str, device):
 
 
 class EngineExchange:
-    """Adapters with the signatures Engine.run_all expects (raw device pointers)."""
+    """Adapters with the signatures Engine.run_all / run_batches expect (raw device pointers).
 
-    def __init__(self, device, group=None):
+    The aliased buffers are written and read by kernels queued on the engine's stream, while
+    ProcessGroupNCCL orders its work against torch's CURRENT stream only.  Give the engine
+    (`eng=`) and every collective is bracketed by stream dependencies in both directions, whichever
+    stream the engine was created on; without it the caller must run the engine on torch's current
+    stream."""
+
+    def __init__(self, device, group=None, eng=None):
         self.x = Exchange(group)
         self.device = device
+        self.eng_stream = None
+        if eng is not None and self.x.world > 1:
+            import torch
+            self.eng_stream = (torch.cuda.ExternalStream(eng.stream_ptr, device=device) if eng.stream_ptr
+                               else torch.cuda.default_stream(device))
+
+    def _before(self):
+        if self.eng_stream is not None:
+            import torch
+            torch.cuda.current_stream(self.device).wait_stream(self.eng_stream)
+
+    def _after(self):
+        if self.eng_stream is not None:
+            import torch
+            self.eng_stream.wait_stream(torch.cuda.current_stream(self.device))
 
     def allreduce_hist(self, ptr: int, n_groups: int):
         if self.x.world > 1 and n_groups:
+            self._before()
             self.x.allreduce_hist(alias_device_array(ptr, n_groups, "<i4", self.device))
+            self._after()
 
     def gather_forests(self, ptr: int, n_groups: int):
         if self.x.world == 1 or not n_groups:
             return []
+        self._before()
         peers = self.x.gather_forests(alias_device_array(ptr, n_groups, "<i4", self.device))
+        self._after()
         return [int(p.data_ptr()) for p in peers]

@@ -39,7 +39,7 @@ def test_diag_after_match(name):
 def test_diag_cases_from_rows():
     from gavisunk_b200.engine import Engine
     for case in load_golden("diag_cases"):
-        rows = gio.read_sunkpos(case["sunkpos"])
+        rows = gio.parse_sunkpos(case["sunkpos"])
         fai = [l.split("\t")[0] for l in case["fai"].splitlines()]
         names, cidx = [], {}
         for r in rows:

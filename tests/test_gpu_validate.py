@@ -117,3 +117,46 @@ def test_pinned_result_buffers_match_pageable():
     assert all(np.array_equal(a[c], b[c]) for c in a) and len(a["read"]) > 100
     b2 = eng.pairs(pinned=True)  # same buffers again
     assert b2["read"].ctypes.data == b["read"].ctypes.data
+
+
+@pytest.mark.parametrize("n_rows", [6, 40, 300])
+def test_validate_wide_position_span_uses_64_bit_predicate(n_rows):
+    """.sunkpos rows fed through gvs_rows_set may span >= 2^28 positions: 10*dpos then overflows 32 bits and the
+    ratio test must run in 64-bit arithmetic for the whole read, whichever thread owns which row (the choice is
+    made on the span of ALL rows of the read, in each of the three row-count tiers)"""
+    from gavisunk_b200.engine import Engine
+    rng = np.random.default_rng(n_rows)
+    step = (1 << 29) // n_rows * 2  # total span ~2^30
+    pos = np.arange(n_rows, dtype=np.int64) * step
+    start = 5000 + pos + rng.integers(-40, 40, n_rows)
+    # a few rows far off the diagonal must stay unvalidated
+    off = rng.choice(n_rows, max(1, n_rows // 6), replace=False)
+    start[off] += 3 * step
+    rows = [("rd", int(pos[i]), "c1", int(start[i]), int(start[i])) for i in range(n_rows)]
+    inter, bed = O.process_by_contig(rows, {"rd": int(pos.max()) + 100}, set(), "c1", minlen=10000)
+    assert inter
+    eng = Engine(20)
+    eng.contig_names = ["c1"]
+    eng.set_reads_meta(np.array([int(pos.max()) + 100], np.uint32))
+    eng.set_rows(1, np.zeros(n_rows, np.uint32), [r[1] for r in rows], np.zeros(n_rows, np.uint32), [r[3] for r in rows],
+                 [r[4] for r in rows], n_contigs=1)
+    eng.set_contigs([0])
+    eng.validate(10000)
+    p = eng.pairs()
+    assert [(int(g), "rd") for g in p["group"]] == inter
+    eng.components_local()
+    iv = eng.intervals()
+    assert [("c1", int(s), int(e)) for s, e in zip(iv["start"], iv["end"])] == bed
+
+
+def test_rows_set_rejects_rows_outside_the_tables():
+    """read / contig indices index device tables of later stages: out-of-range rows are an argument error"""
+    from gavisunk_b200.engine import Engine, GavisunkError
+    eng = Engine(20)
+    eng.contig_names = ["c1", "c2"]
+    eng.set_reads_meta(np.array([20000, 20000], np.uint32))
+    with pytest.raises(GavisunkError, match="read index"):
+        eng.set_rows(1, [0, 2], [1, 2], [0, 0], [10, 20], [10, 20], n_contigs=2)
+    with pytest.raises(GavisunkError, match="contig"):
+        eng.set_rows(1, [0, 1], [1, 2], [0, 2], [10, 20], [10, 20], n_contigs=2)
+    eng.set_rows(1, [0, 1], [1, 2], [0, 1], [10, 20], [10, 20], n_contigs=2)

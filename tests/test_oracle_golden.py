@@ -90,7 +90,7 @@ def test_match_every_sunk_len():
 
 def test_diag_cases():
     for case in load_golden("diag_cases"):
-        rows = gio.read_sunkpos(case["sunkpos"])
+        rows = gio.parse_sunkpos(case["sunkpos"])
         contigs = {l.split("\t")[0] for l in case["fai"].splitlines()}
         diag = O.diag_filter_v3(rows, contigs)
         got = "".join("\t".join(str(x) for x in d) + "\n" for d in diag)

@@ -22,7 +22,7 @@ def _rlen(txt):
 @pytest.mark.parametrize("name", CASES)
 def test_bad_sunks(name):
     c = load_golden(name)
-    rows = [gio.read_sunkpos(c["hap"][h]["sunkpos"]) for h in ("1", "2")]
+    rows = [gio.parse_sunkpos(c["hap"][h]["sunkpos"]) for h in ("1", "2")]
     got = O.bad_sunks(rows[0], {n for n, _ in _fai(c["fai1"])}, rows[1], {n for n, _ in _fai(c["fai2"])})
     assert sorted(f"{a}:{b}" for a, b in got) == c["bad_sunks"]
     assert len(got) > 50
@@ -34,7 +34,7 @@ def test_split_and_process_by_contig(name):
     bad = {(b.rsplit(":", 1)[0], int(b.rsplit(":", 1)[1])) for b in c["bad_sunks"]}
     n_iv = 0
     for h in ("1", "2"):
-        rows = gio.read_sunkpos(c["hap"][h]["sunkpos"])
+        rows = gio.parse_sunkpos(c["hap"][h]["sunkpos"])
         rlen = _rlen(c["hap"][h]["rlen"])
         by_c = {}
         for r in rows:
