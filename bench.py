@@ -53,18 +53,28 @@ def parse_args():
     ap.add_argument("--asm-mbp", type=float, default=None, help="override haploid assembly size (Mbp)")
     ap.add_argument("--coverage", type=float, default=None, help="override read coverage per GPU shard")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-batches", type=int, default=2, help="batches per rank of the end-to-end run (0 = all; page-locked host memory)")
+    ap.add_argument("--e2e-headline-only", action="store_true", help="skip the secondary e2e figures (ASCII copies only, packed host input)")
+    ap.add_argument("--batches", type=int, default=None, help="override the number of read batches of the run")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the run (all batches) is the same for every N; weak: one batch per rank")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--resident", default="ascii", choices=["ascii", "packed"],
+                    help="form of the HBM-resident reads of `value`: ASCII bases (what the reference consumes) or the 2-bit words the "
+                         "ingest emits (gvs_fastx_read_packed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-mbp", type=float, default=None, help="read Mbp per CPU process of the baseline sample")
     return ap.parse_args()
 
 
 WORKLOADS = {
-    "tiny": dict(mbp=2.0, human=False, cov=30.0, n50=20000.0,
-                 desc="synthetic 2 Mbp x2 diploid + 30x ONT-like reads (smoke size)"),
-    "s150": dict(mbp=150.0, human=False, cov=30.0, n50=50000.0,
-                 desc="synthetic 150 Mbp single-chromosome x2 diploid assembly + 30x simulated ONT reads (N50 ~50 kb)"),
-    "h3100": dict(mbp=3100.0, human=True, cov=3.75, n50=100000.0,
-                  desc="synthetic 3.1 Gbp x2 diploid assembly (23 contigs) + ONT-like reads N50 ~100 kb, 3.75x (=30x/8) per GPU shard"),
+    "tiny": dict(mbp=2.0, human=False, cov=15.0, batches=2, n50=20000.0,
+                 desc="synthetic 2 Mbp x2 diploid + 30x ONT-like reads in 2 batches (smoke size)"),
+    "s150": dict(mbp=150.0, human=False, cov=30.0, batches=1, n50=50000.0,
+                 desc="synthetic 150 Mbp single-chromosome x2 diploid assembly + 30x simulated ONT reads (N50 ~50 kb), one batch"),
+    "h3100": dict(mbp=3100.0, human=True, cov=3.75, batches=8, n50=100000.0,
+                  desc="synthetic 3.1 Gbp x2 diploid assembly (23 contigs) + 30x ultra-long ONT-like reads (N50 ~100 kb, 93 Gbp) "
+                       "in 8 batches of 3.75x (10 chunk files per haplotype each)"),
 }
 
 
@@ -123,13 +133,24 @@ class ClockSampler:
                     power_w_max=(max(pw) if pw else None), reasons=sorted(reasons), samples=len(sm))
 
 
-def build_workload(args, eng, rank):
+def shard_batches(n_batches: int, world: int):
+    """contiguous blocks of batches per rank (a batch is a group of whole chunk files)"""
+    from gavisunk_b200.parallel import shard_chunks
+    return shard_chunks(n_batches, world)
+
+
+def build_workload(args, eng, rank, world=1, with_reads=True):
+    """assembly + SUNK database on this GPU and the read batches this rank owns.  The run is the SAME for every
+    N (batch b always has seed 2001 + 16 b): rank r owns a contiguous block of the batches (strong scaling), or --
+    --scaling weak -- every rank owns batch `rank` only, a run N times as large as at N = 1."""
     from gavisunk_b200 import workload as W
     spec = dict(WORKLOADS[args.workload])
     if args.asm_mbp is not None:
         spec["mbp"] = args.asm_mbp
     if args.coverage is not None:
         spec["cov"] = args.coverage
+    if args.batches is not None:
+        spec["batches"] = args.batches
     L = int(spec["mbp"] * 1e6)
     contigs = W.human_contigs(spec["mbp"]) if spec["human"] else [L]
     t0 = time.time()
@@ -137,21 +158,44 @@ def build_workload(args, eng, rank):
     eng.set_profiling(True)
     W.build_db(eng, wl)
     db_ms = eng.stage_ms("dbbuild")
-    # every rank draws its own shard of reads (different seed) from the same assembly
-    W.add_reads(eng, wl, coverage=spec["cov"], n50=spec["n50"], sigma=0.8, len_min=1000, len_max=1000000,
-                seed=2001 + 16 * rank, nchunks=10)
-    wl.meta.update(db_build_ms=db_ms, setup_s=time.time() - t0, desc=spec["desc"], asm_mbp=spec["mbp"])
+    nb = int(spec["batches"])
+    if args.scaling == "weak":
+        mine, nb_total = [rank], world
+    else:
+        lo, hi = shard_batches(nb, world)[rank]
+        mine, nb_total = list(range(lo, hi)), nb
+    wl.batch_ids, wl.batches, wl.n_batches_total = mine, [], nb_total
+    wl.batch_args = dict(coverage=spec["cov"], n50=spec["n50"], sigma=0.8, len_min=1000, len_max=1000000, nchunks=10)
+    if with_reads:
+        for b in mine:
+            nbt = W.new_batch(eng, wl, seed=2001 + 16 * b, **wl.batch_args)
+            if args.resident == "packed":
+                W.pack_batch_on_device(nbt, drop_ascii=False)
+            wl.batches.append(nbt)
+    wl.meta.update(db_build_ms=db_ms, setup_s=time.time() - t0, desc=spec["desc"], asm_mbp=spec["mbp"], n50=spec["n50"], sigma=0.8,
+                   cov_per_batch=spec["cov"], n_batches=nb_total)
     return wl
 
 
-def run_step(eng, wl, bind, coll):
-    """one pass of the hot path; returns the result sizes"""
-    bind()
-    iv = eng.run_all(wl.contig_hap, min_read_len=10000, allreduce_hist=coll.allreduce_hist,
-                     gather_forests=coll.gather_forests)
+def run_step(eng, wl, binds, coll):
+    """one pass of the hot path over this rank's batches (two phases, gavisunk_b200.engine.Engine.run_batches);
+    returns the result sizes (rows / best / kept / validated pairs are this rank's, the rest is global)"""
+    iv, bases = eng.run_batches(binds, wl.contig_hap, min_read_len=10000, allreduce_hist=coll.allreduce_hist,
+                                gather_forests=coll.gather_forests)
     gaps, nodata = eng.gaps(wl.contig_len.astype(np.uint32))
     return dict(rows=eng.n_rows, best=eng.n_best, kept=eng.n_kept, bad_groups=eng.n_bad, validated_pairs=eng.n_pairs,
                 intervals=int(len(iv["contig"])), gaps=int(len(gaps["contig"])), nodata=int(len(nodata))), iv, gaps
+
+
+def result_digest(iv, gaps, eng):
+    """sha256 over the run's global results: validated intervals, gaps, bad SUNK groups"""
+    import hashlib
+    h = hashlib.sha256()
+    for d in (iv, gaps):
+        for c in ("contig", "start", "end"):
+            h.update(np.ascontiguousarray(d[c], dtype=np.uint32).tobytes())
+    h.update(np.sort(eng.bad_list()).astype(np.uint32).tobytes())
+    return h.hexdigest()
 
 
 def main_b200(args):
@@ -170,20 +214,34 @@ def main_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine(args.k, device=local, stream=torch.cuda.current_stream().cuda_stream)
-    wl = build_workload(args, eng, rank)
+    wl = build_workload(args, eng, rank, world)
     n_sunks, n_groups = eng.db_size()
     from gavisunk_b200.parallel import EngineExchange
-    coll = EngineExchange(dev)
+    coll = EngineExchange(dev, eng=eng)
+    my_bases = int(sum(b.total_bases for b in wl.batches))
+    my_reads = int(sum(b.n_reads for b in wl.batches))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    bind = lambda: W.bind_reads(eng, wl)
+    def allsum(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def allmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    binds = [(lambda e, b=b: W.bind_batch(e, b)) for b in wl.batches]
     # ---- HBM-resident timing ----
     for _ in range(max(args.warmup, 3)):
-        res, iv, gaps = run_step(eng, wl, bind, coll)
+        res, iv, gaps = run_step(eng, wl, binds, coll)
     launches0 = eng.launches
     sampler = ClockSampler(local)
     sampler.start()
@@ -193,26 +251,35 @@ def main_b200(args):
     tb = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        res, iv, gaps = run_step(eng, wl, bind, coll)
-        for st in STAGES:
-            stage_ms.setdefault(st, []).append(eng.stage_ms(st))
+        res, iv, gaps = run_step(eng, wl, binds, coll)
     e1.record()
     barrier()
     te = time.perf_counter()
     clocks = sampler.stop(tb, te)
     ms = e0.elapsed_time(e1)
     launches = eng.launches - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    bases = torch.tensor([wl.total_bases], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(bases, op=dist.ReduceOp.SUM)
-    total_bases = float(bases.item())
+    ms_max = allmax(ms)
+    total_bases = allsum(my_bases)
     value = total_bases * args.steps / (ms_max * 1e-3) / 1e9
+    digest = result_digest(iv, gaps, eng)
 
-    # ---- roofline of the dominant kernel (k_probe2) ----
+    # ---- per-stage device times (CUDA events of the library around each stage, on its stream): one extra pass with
+    #      the stage times read after every batch / phase-2 stage (reading them waits for the stage, so it is kept out
+    #      of the timed region above) ----
+    per_batch = {st: [] for st in ("probe", "emit", "diag", "hist")}
+
+    def on_batch(e, b, base):
+        for st in per_batch:
+            per_batch[st].append(e.stage_ms(st))
+    for _ in range(2):
+        for st in per_batch:
+            per_batch[st].clear()
+        eng.run_batches(binds, wl.contig_hap, allreduce_hist=coll.allreduce_hist, gather_forests=coll.gather_forests, on_batch=on_batch)
+    phase2 = {st: (eng.stage_ms(st) if wl.batches else 0.0) for st in ("validate", "intervals")}
+    stage_ms = {st: float(np.sum(v)) for st, v in per_batch.items()}
+    stage_ms.update(phase2)
+
+    # ---- roofline of the dominant kernel (k_probe2): one launch per batch ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -220,154 +287,90 @@ def main_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     k = args.k
-    off = wl.read_off.cpu().numpy()
-    lens = np.diff(off)
-    windows = int(np.maximum(lens - k + 1, 0).sum())
-    probe_bytes = float(wl.total_bases) * 1.0 + windows * 16.0  # 1 B/base in + one 16 B slot per window
-    probe_ms = float(np.mean(stage_ms["probe"]))
-    achieved = probe_bytes / (probe_ms * 1e-3) / 1e9
-    traffic = None
-    if k == 20 and args.asm_mbp is None and args.coverage is None:  # the ncu capture is of the default shapes
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "probe_traffic.json"))).get(args.workload)
-        except Exception:
-            pass
-    roofline = dict(bound="hbm", kernel=f"k_probe2<{k}>", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=traffic, traffic_unit="DRAM bytes per launch (ncu --set full, profiles/probe_traffic.json)",
-                    traffic_gbs=(traffic / (probe_ms * 1e-3) / 1e9 if traffic else None),
-                    traffic_frac_of_peak=(traffic / (probe_ms * 1e-3) / 1e9 / peak if traffic else None),
-                    peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                    alg_bytes_per_launch=probe_bytes, kernel_ms=probe_ms,
-                    kernel_share_of_step=probe_ms * args.steps / ms,
-                    whole_path_alg_gbs=(probe_bytes + 24.0 * res["rows"]) * args.steps / (ms * 1e-3) / 1e9,
-                    note=("algorithmic bytes follow SURVEY.md 8d (1 B per base + one 16 B table slot per window); the "
-                          "two-level filter answers ~99 % of the windows without touching their slot, so `achieved` may "
-                          "exceed the DRAM peak -- `traffic_gbs` is what the kernel really moves"))
+    roofline = None
+    if wl.batches:
+        windows = 0
+        for b in wl.batches:
+            lens = np.diff(b.read_off.cpu().numpy())
+            windows += int(np.maximum(lens - k + 1, 0).sum())
+        nbm = len(wl.batches)
+        probe_bytes = (float(my_bases) * 1.0 + windows * 16.0) / nbm  # 1 B/base in + one 16 B slot per window, per launch
+        probe_ms = float(np.mean(per_batch["probe"]))
+        achieved = probe_bytes / (probe_ms * 1e-3) / 1e9
+        traffic = None
+        if k == 20 and args.asm_mbp is None and args.coverage is None:  # the ncu capture is of the default shapes
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "probe_traffic.json"))).get(args.workload)
+            except Exception:
+                pass
+        roofline = dict(bound="hbm", kernel=f"k_probe2<{k}>", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                        traffic=traffic, traffic_unit="DRAM bytes per launch (ncu --set full, profiles/probe_traffic.json)",
+                        traffic_gbs=(traffic / (probe_ms * 1e-3) / 1e9 if traffic else None),
+                        traffic_frac_of_peak=(traffic / (probe_ms * 1e-3) / 1e9 / peak if traffic else None),
+                        peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
+                        alg_bytes_per_launch=probe_bytes, kernel_ms=probe_ms, launches_per_step=nbm,
+                        kernel_share_of_step=probe_ms * nbm * args.steps / ms,
+                        whole_path_alg_gbs=(probe_bytes * nbm + 24.0 * res["rows"]) * args.steps / (ms * 1e-3) / 1e9,
+                        note=("algorithmic bytes follow SURVEY.md 8d (1 B per base + one 16 B table slot per window); the "
+                              "two-level filter answers ~99 % of the windows without touching their slot, so `achieved` may "
+                              "exceed the DRAM peak -- `traffic_gbs` is what the kernel really moves"))
+
+    # ---- N ranks == 1 rank: the same run on rank 0 alone (all batches, no exchange), outside the timed region ----
+    parity_check = None
+    if world > 1 and not args.no_parity_check:
+        pairs_total = allsum(res["validated_pairs"])
+        kept_total = allsum(res["kept"])
+        ok, single = None, None
+        if rank == 0:
+            class _NoColl:
+                allreduce_hist = None
+                gather_forests = None
+            eng1 = eng
+            mine = {b: wl.batches[i] for i, b in enumerate(wl.batch_ids)}
+            cache = {}
+
+            def bind_any(e, b):
+                if b in mine:
+                    W.bind_batch(e, mine[b])
+                else:  # a peer's batch: regenerated here from its seed (one at a time, the buffer is reused)
+                    cache.clear()
+                    cache[b] = W.new_batch(e, wl, seed=2001 + 16 * b, **wl.batch_args)
+                    W.bind_batch(e, cache[b])
+            all_ids = list(range(wl.n_batches_total))
+            iv1, _ = eng1.run_batches([(lambda e, b=b: bind_any(e, b)) for b in all_ids], wl.contig_hap)
+            gaps1, _nd1 = eng1.gaps(wl.contig_len.astype(np.uint32))
+            single = dict(digest=result_digest(iv1, gaps1, eng1), intervals=int(len(iv1["contig"])), gaps=int(len(gaps1["contig"])),
+                          bad_groups=eng1.n_bad, validated_pairs=eng1.n_pairs, kept=eng1.n_kept)
+            cache.clear()
+            ok = (single["digest"] == digest and single["validated_pairs"] == int(pairs_total) and single["kept"] == int(kept_total)
+                  and single["bad_groups"] == res["bad_groups"])
+        flag = torch.tensor([1.0 if (ok or rank != 0) else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        # every rank holds the replicated global result: their digests must agree as well
+        dg = torch.tensor([int(digest[:15], 16)], dtype=torch.int64, device=dev)
+        dmin, dmax = dg.clone(), dg.clone()
+        dist.all_reduce(dmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            parity_check = dict(n_ranks=world, ok=bool(ok and int(dmin.item()) == int(dmax.item())), replicated_result_agrees=int(dmin.item()) == int(dmax.item()),
+                                intervals=res["intervals"], gaps=res["gaps"], bad_groups=res["bad_groups"], validated_pairs=int(pairs_total),
+                                kept_rows=int(kept_total), digest=digest, single_rank=single,
+                                what="rank 0 re-ran ALL batches of the run alone (no exchange) after the timed region: intervals, gaps and bad "
+                                     "SUNK groups (sha256), validated pairs and kept rows equal the N-rank run's")
+        if float(flag.item()) == 0.0 or int(dmin.item()) != int(dmax.item()):
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "parity_check failed: N-rank result differs from the single-rank run",
+                                  "parity_check": parity_check}))
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(3)
+        # the re-run left rank 0's engine holding the single-rank results; restore the distributed state for what follows
+        res, iv, gaps = run_step(eng, wl, binds, coll)
 
     # ---- end to end through the public API with HOST buffers ----
     e2e = None
     if args.e2e_steps > 0:
-        h_reads = torch.empty(wl.total_bases + 64, dtype=torch.uint8, pin_memory=True)
-        h_reads[:wl.total_bases].copy_(wl.reads[:wl.total_bases])
-        h_off = torch.empty(wl.n_reads + 1, dtype=torch.int64, pin_memory=True)
-        h_off.copy_(wl.read_off)
-        torch.cuda.synchronize()
-        np_reads = h_reads.numpy()[:wl.total_bases]
-        np_off = h_off.numpy().view(np.uint64)
-        bind_h = lambda: eng.set_reads(np_reads, np_off, wl.chunk_first, wl.chunk_hap)
-        def time_host_path(bind):
-            """e2e_steps steps of the whole path from the host batch `bind` registers; max over ranks"""
-            r0, _, _ = run_step(eng, wl, bind, coll)
-            assert r0 == res, "the host path must reproduce the resident path"
-            eng.pairs(pinned=True)  # warm-up also sizes the page-locked result and staging buffers
-            barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0 = time.perf_counter()
-            f0.record()
-            d2h = 0
-            split = dict(submit_copy=0.0, match=0.0, filter_validate_intervals=0.0, results_to_host=0.0)
-            for _ in range(args.e2e_steps):
-                # same calls as run_step(), with host-side time stamps between them (where the e2e step goes)
-                c0 = time.perf_counter()
-                bind()                                            # starts the segment pipeline, returns at once
-                c1 = time.perf_counter()
-                eng.match()                                       # probe launches chase the segments; returns when rows exist
-                c2 = time.perf_counter()
-                eng.diag_filter(wl.contig_hap)
-                hp = eng.group_hist()
-                coll.allreduce_hist(hp, eng.db_groups())
-                eng.bad_groups()
-                eng.validate(10000)
-                pp = eng.components_local()
-                for peer in coll.gather_forests(pp, eng.db_groups()):
-                    eng.components_merge(peer)
-                iv2 = eng.intervals()                             # intervals + gaps come back to the host
-                gaps2, _nd = eng.gaps(wl.contig_len.astype(np.uint32))
-                c3 = time.perf_counter()
-                pairs = eng.pairs(pinned=True)                    # inter_outs rows (group, read) into page-locked memory
-                c4 = time.perf_counter()
-                for key, dt in zip(split, (c1 - c0, c2 - c1, c3 - c2, c4 - c3)):
-                    split[key] += dt * 1e3 / args.e2e_steps
-                d2h = sum(a.nbytes for a in pairs.values()) + sum(a.nbytes for a in iv2.values()) + sum(a.nbytes for a in gaps2.values())
-            f1.record()
-            barrier()
-            wall_ms = (time.perf_counter() - t0) * 1e3
-            ems = max(f0.elapsed_time(f1), wall_ms)
-            t = torch.tensor([ems], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item()), split, d2h
-
-        # Headline: the library's default for a pipelined ASCII host batch (gvs_set_host_pack ADAPTIVE): every
-        # segment goes over the link either as ASCII or 2-bit packed by the host threads, whichever keeps link
-        # and cores busy; both the packing and all copies are inside the timed region.
-        n_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-        pack_threads = max(1, min(16, n_cores // max(local_world, 1)))
-        # Ranks that share one host share its memory bandwidth between the DMA reads and the packers: with 8 ranks x 4
-        # threads on a 32-core box the adaptive mode measured 163 Gbp/s against 177 with plain ASCII copies
-        # (profiles/bench_h3100_n8_r1aq.json), with 2 x 12 threads 131 against 104, alone with 16 threads 103 against 53.
-        # So packing is used where a rank has at least 12 cores to itself.
-        pack_mode = eng.PACK_ADAPTIVE if (local_world == 1 or pack_threads >= 12) else eng.PACK_OFF
-        eng.set_host_pack(pack_mode, pack_threads)
-        ems, split, d2h = time_host_path(bind_h)
-        seq_bytes, n_seg, n_seg_packed = eng.copy_stats()
-        e2e = dict(value=total_bases * args.e2e_steps / (ems * 1e-3) / 1e9, unit=UNIT,
-                   h2d_bytes_per_step=int(seq_bytes + 8 * (wl.n_reads + 1)), d2h_bytes_per_step=int(d2h),
-                   steps=args.e2e_steps, ms_per_step=ems / args.e2e_steps, host_numa_node=numa.get("numa_node"),
-                   host_split_ms={k2: round(v, 2) for k2, v in split.items()},
-                   host_input_bytes_per_step=int(wl.total_bases + 8 * (wl.n_reads + 1)),
-                   transfer=dict(mode="adaptive" if pack_mode == eng.PACK_ADAPTIVE else "ascii copies only (host cores shared by the ranks)",
-                                 host_pack_threads=pack_threads, segments=n_seg, segments_packed=n_seg_packed,
-                                 note="input = ASCII bases in page-locked host memory; a segment crosses PCIe as ASCII or 2-bit "
-                                      "packed by the host threads (kmer.encode's byte map), chosen at run time; last step's counts"))
-        # the same call with the host cores idle (every segment as ASCII): the transfer-bound figure
-        if pack_mode == eng.PACK_OFF:
-            e2e["ascii_copy_only"] = dict(value=e2e["value"], unit=UNIT, note="this is the headline run")
-        else:
-            try:
-                eng.set_host_pack(eng.PACK_OFF, pack_threads)
-                ems0, split0, _ = time_host_path(bind_h)
-                e2e["ascii_copy_only"] = dict(value=total_bases * args.e2e_steps / (ems0 * 1e-3) / 1e9, unit=UNIT,
-                                              ms_per_step=ems0 / args.e2e_steps, h2d_bytes_per_step=int(wl.total_bases + 8 * (wl.n_reads + 1)),
-                                              host_split_ms={k2: round(v, 2) for k2, v in split0.items()},
-                                              h2d_gbs_if_copy_bound=(wl.total_bases / 1e9) / max(split0["match"] * 1e-3, 1e-9))
-            except Exception as ex:
-                e2e["ascii_copy_only"] = dict(error=repr(ex)[:200])
-            eng.set_host_pack(pack_mode, pack_threads)
-        # ---- secondary: the same path with the host batch 2-bit packed by the ingest (gvs_pack_2bit, outside
-        #      the timed region like the parse that produces `h_reads`); NOT the headline e2e ----
-        try:
-            from gavisunk_b200.engine import pack_2bit
-            nw = (wl.total_bases + 15) // 16
-            h_words = torch.zeros(nw + 16, dtype=torch.int32, pin_memory=True)
-            np_words = h_words.numpy().view(np.uint32)
-            pack_2bit(np_reads, threads=pack_threads, out=np_words)  # first touch of the output pages
-            tq = time.perf_counter()
-            pack_2bit(np_reads, threads=pack_threads, out=np_words)
-            e2e["transfer"]["host_pack_gbs_alone"] = round(wl.total_bases / (time.perf_counter() - tq) / 1e9, 1)
-            bind_p = lambda: eng.set_reads_packed(np_words[:nw], np_off, wl.chunk_first, wl.chunk_hap)
-            rp, _, _ = run_step(eng, wl, bind_p, coll)
-            assert rp == res, "packed host path must reproduce the ASCII path"
-            eng.pairs(pinned=True)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                run_step(eng, wl, bind_p, coll)
-                eng.pairs(pinned=True)
-            barrier()
-            tp = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-            e2e["packed_host_input"] = dict(value=total_bases * args.e2e_steps / (float(tp.item()) * 1e-3) / 1e9, unit=UNIT,
-                                            h2d_bytes_per_step=int(4 * nw + 8 * (wl.n_reads + 1)),
-                                            ms_per_step=float(tp.item()) / args.e2e_steps,
-                                            note="2-bit words from gvs_pack_2bit (kmer.encode's byte map, lossless for this path); "
-                                                 "packing is part of the ingest, outside the timed region")
-            del h_words
-        except Exception as ex:
-            e2e["packed_host_input"] = dict(error=repr(ex)[:200])
-        del h_reads, h_off
+        e2e = measure_e2e(args, eng, wl, coll, dev, world, rank, numa, barrier, allmax, allsum)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -379,21 +382,131 @@ def main_b200(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": wl.meta["desc"], "k": k, "asm_haploid_mbp": wl.meta["asm_mbp"],
-                       "read_gbp_per_gpu": wl.total_bases / 1e9, "reads_per_gpu": wl.n_reads, "n_sunks": n_sunks,
-                       "n_groups": n_groups, "results_per_step": res, "l2": "inputs larger than L2 (reads >> 126 MB per step)",
+            "config": {"workload": wl.meta["desc"], "k": k, "asm_haploid_mbp": wl.meta["asm_mbp"], "resident_reads": args.resident,
+                       "read_gbp_per_step": total_bases / 1e9, "batches_per_step": wl.n_batches_total,
+                       "read_gbp_rank0": my_bases / 1e9, "reads_rank0": my_reads, "batches_rank0": len(wl.batches),
+                       "n_sunks": n_sunks, "n_groups": n_groups, "results_per_step": res,
+                       "l2": "inputs larger than L2 (every batch's reads >> 126 MB)",
                        "stages": ["match", "diag_filter", "bad_sunks", "validate", "components", "intervals", "gaps"],
-                       "db_build_ms": wl.meta["db_build_ms"],
-                       "stage_ms": {s: float(np.mean(v)) for s, v in stage_ms.items()},
-                       "parallelism": f"reads sharded over {world} GPU(s), SUNK table replicated"},
+                       "phases": "per batch: match -> diag filter -> histogram (accumulated) -> stash; once: all-reduce, bad groups, "
+                                 "validation, components, all-gather, intervals, gaps",
+                       "db_build_ms": wl.meta["db_build_ms"], "stage_ms_per_step_rank0": stage_ms,
+                       "parallelism": f"batches of chunk files sharded over {world} GPU(s), SUNK table replicated; 2 collectives per run"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, "parity_check": parity_check,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_e2e(args, eng, wl, coll, dev, world, rank, numa, barrier, allmax, allsum):
+    """The same run through Engine.run_batches with HOST buffers: every batch's reads start in page-locked host
+    memory as ASCII (what the reference's readfq loop consumes), cross PCIe inside the timed region (as they are or
+    2-bit packed on the way by the library's host threads) and the results (validated pairs, intervals, gaps) come
+    back to the host.  Page-locked memory for the whole run may exceed the host (30x human = 93 GB): the run is then
+    timed over the first `--e2e-batches` batches of every rank (same path, same per-batch sizes; stated)."""
+    import torch
+    from gavisunk_b200 import workload as W
+    nb_e2e = len(wl.batches) if args.e2e_batches <= 0 else min(len(wl.batches), args.e2e_batches)
+    sub = wl.batches[:nb_e2e]
+    sub_bases = int(sum(b.total_bases for b in sub))
+    sub_reads = int(sum(b.n_reads for b in sub))
+    total_sub = allsum(sub_bases)
+    # resident run on the same subset = what the host path must reproduce
+    binds_res = [(lambda e, b=b: W.bind_batch(e, b)) for b in sub]
+    res, _, _ = run_step(eng, wl, binds_res, coll)
+    host = []
+    for b in sub:
+        h_reads = torch.empty(b.total_bases + 64, dtype=torch.uint8, pin_memory=True)
+        h_reads[:b.total_bases].copy_(b.reads[:b.total_bases])
+        h_off = torch.empty(b.n_reads + 1, dtype=torch.int64, pin_memory=True)
+        h_off.copy_(b.read_off)
+        host.append((h_reads, h_off, h_reads.numpy()[:b.total_bases], h_off.numpy().view(np.uint64), b))
+    torch.cuda.synchronize()
+    binds_h = [(lambda e, h=h: e.set_reads(h[2], h[3], h[4].chunk_first, h[4].chunk_hap)) for h in host]
+
+    def time_host_path(binds):
+        r0, _, _ = run_step(eng, wl, binds, coll)
+        assert r0 == res, "the host path must reproduce the resident path"
+        eng.pairs(pinned=True)  # warm-up also sizes the page-locked result and staging buffers
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        f0.record()
+        d2h = h2d = 0
+        for _ in range(args.e2e_steps):
+            h2d = [0]
+
+            def on_batch(e, b, base):
+                h2d[0] += e.copy_stats()[0] + 8 * (sub[b].n_reads + 1)
+            iv2, _ = eng.run_batches(binds, wl.contig_hap, allreduce_hist=coll.allreduce_hist, gather_forests=coll.gather_forests,
+                                     on_batch=on_batch)
+            gaps2, _nd = eng.gaps(wl.contig_len.astype(np.uint32))   # intervals + gaps come back to the host
+            pairs = eng.pairs(pinned=True)                            # inter_outs rows (group, read) into page-locked memory
+            d2h = sum(a.nbytes for a in pairs.values()) + sum(a.nbytes for a in iv2.values()) + sum(a.nbytes for a in gaps2.values())
+        f1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        return allmax(max(f0.elapsed_time(f1), wall_ms)), d2h, h2d[0]
+
+    n_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    pack_threads = max(1, min(16, n_cores // max(local_world, 1)))
+    # Ranks that share one host share its memory bandwidth between the DMA reads and the packers (profiles/README.md): the
+    # adaptive packing is used where a rank has at least 12 cores to itself.
+    pack_mode = eng.PACK_ADAPTIVE if (local_world == 1 or pack_threads >= 12) else eng.PACK_OFF
+    eng.set_host_pack(pack_mode, pack_threads)
+    e2e = None
+    if sub:
+        ems, d2h, h2d = time_host_path(binds_h)
+        seq_bytes, n_seg, n_seg_packed = eng.copy_stats()
+        e2e = dict(value=total_sub * args.e2e_steps / (ems * 1e-3) / 1e9, unit=UNIT,
+                   h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                   steps=args.e2e_steps, ms_per_step=ems / args.e2e_steps, host_numa_node=numa.get("numa_node"),
+                   batches_per_step_per_rank=nb_e2e, read_gbp_per_step=total_sub / 1e9,
+                   host_input_bytes_per_step=int(sub_bases + 8 * (sub_reads + nb_e2e)),
+                   scope=(f"the first {nb_e2e} of this rank's {len(wl.batches)} batches (page-locked host memory for the whole run "
+                          f"would be {sum(b.total_bases for b in wl.batches) / 1e9:.0f} GB); same two-phase path, results checked against "
+                          "the resident run on the same batches") if nb_e2e < len(wl.batches) else "all batches of the run",
+                   transfer=dict(mode="adaptive" if pack_mode == eng.PACK_ADAPTIVE else "ascii copies only (host cores shared by the ranks)",
+                                 host_pack_threads=pack_threads, segments_last_batch=n_seg, segments_packed_last_batch=n_seg_packed,
+                                 note="input = ASCII bases in page-locked host memory; a segment crosses PCIe as ASCII or 2-bit "
+                                      "packed by the host threads (kmer.encode's byte map), chosen at run time"))
+        if pack_mode != eng.PACK_OFF and not args.e2e_headline_only:
+            try:  # the same call with the host cores idle (every segment as ASCII): the transfer-bound figure
+                eng.set_host_pack(eng.PACK_OFF, pack_threads)
+                ems0, _, h2d0 = time_host_path(binds_h)
+                e2e["ascii_copy_only"] = dict(value=total_sub * args.e2e_steps / (ems0 * 1e-3) / 1e9, unit=UNIT,
+                                              ms_per_step=ems0 / args.e2e_steps, h2d_bytes_per_step=int(h2d0))
+            except Exception as ex:
+                e2e["ascii_copy_only"] = dict(error=repr(ex)[:200])
+            eng.set_host_pack(pack_mode, pack_threads)
+        if not args.e2e_headline_only:
+            # secondary: host batches that the ingest delivered 2-bit packed (gvs_fastx_read's native output /
+            # gvs_pack_2bit; the packing is outside the timed region like the parse that produces the ASCII buffers)
+            try:
+                from gavisunk_b200.engine import pack_2bit
+                packed = []
+                for h in host:
+                    nw = (h[4].total_bases + 15) // 16
+                    hw = torch.zeros(nw + 16, dtype=torch.int32, pin_memory=True)
+                    npw = hw.numpy().view(np.uint32)
+                    pack_2bit(h[2], threads=pack_threads, out=npw)
+                    packed.append((hw, npw[:nw], h[3], h[4]))
+                binds_p = [(lambda e, q=q: e.set_reads_packed(q[1], q[2], q[3].chunk_first, q[3].chunk_hap)) for q in packed]
+                emsp, _, h2dp = time_host_path(binds_p)
+                e2e["packed_host_input"] = dict(value=total_sub * args.e2e_steps / (emsp * 1e-3) / 1e9, unit=UNIT,
+                                                h2d_bytes_per_step=int(h2dp), ms_per_step=emsp / args.e2e_steps,
+                                                note="2-bit words (kmer.encode's byte map, lossless for this path) as the library's ingest "
+                                                     "emits them; packing is part of the ingest, outside the timed region")
+                del packed
+            except Exception as ex:
+                e2e["packed_host_input"] = dict(error=repr(ex)[:200])
+    del host
+    return e2e
 
 
 # --------------------------------------------------------------------------------------------
@@ -460,6 +573,15 @@ def _prepare_reference_sample(args, wl, eng, per_proc_mbp, cores):
             sample_note = (f"database restricted to contigs {wl.contig_names[lo]}..{wl.contig_names[hi - 1]} of both haplotypes "
                            f"({sub_len / 1e6:.0f} Mbp x2; the full {n_sunks / 1e6:.0f} M-SUNK table needs ~33 GB and minutes of text "
                            "parsing per reference process), reads drawn from them by the same generator; ")
+            wl = swl
+        else:  # small database: the sample is cut from the run's first batch
+            import copy
+            from gavisunk_b200 import workload as W
+            if not wl.batches:
+                wl.batches.append(W.new_batch(eng, wl, seed=2001, **wl.batch_args))
+            b0 = wl.batches[0]
+            swl = copy.copy(wl)
+            swl.reads, swl.read_off, swl.n_reads, swl.total_bases = b0.reads, b0.read_off, b0.n_reads, b0.total_bases
             wl = swl
         dbp, locp, fais = _write_db_files(eng, wl, workdir, contig_sel)
         off = wl.read_off.cpu().numpy()
@@ -579,7 +701,7 @@ def main_reference(args):
     from gavisunk_b200.engine import Engine
     torch.cuda.set_device(0)
     eng = Engine(args.k, device=0)
-    wl = build_workload(args, eng, 0)
+    wl = build_workload(args, eng, 0, 1, with_reads=False)  # assembly + SUNK database; the sample's reads are drawn below
     # every step = the reference pipeline on a bounded sample (~8 s on 16 cores, most of it each process loading
     # the SUNK table from text); K steps are run unless that would take more than ~2.5 minutes in total
     vals, last = [], None

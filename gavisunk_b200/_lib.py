@@ -53,6 +53,9 @@ PROTOTYPES = {
     "gvs_bad_set": (C.c_int, [vp, vp, vp, C.c_uint64, u64p]),
     "gvs_groups_count": (C.c_int, [vp, u64p]),
     "gvs_groups_get": (C.c_int, [vp, vp, vp, vp]),
+    "gvs_batches_begin": (C.c_int, [vp]),
+    "gvs_batch_stash": (C.c_int, [vp, u64p]),
+    "gvs_batches_bind": (C.c_int, [vp, u64p, u64p]),
     "gvs_validate": (C.c_int, [vp, C.c_uint32, u64p]),
     "gvs_pairs_get": (C.c_int, [vp, vp, vp, vp, vp]),
     "gvs_components_local": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
@@ -85,6 +88,17 @@ PROTOTYPES["gvs_fastx_read"] = (C.c_int, [C.POINTER(C.c_char_p), C.c_uint32, C.c
 PROTOTYPES["gvs_fastx_free"] = (None, [C.POINTER(FastxStruct)])
 PROTOTYPES["gvs_fastx_pack"] = (C.c_int, [C.POINTER(FastxStruct), C.c_int, C.c_int])
 PROTOTYPES["gvs_pack_2bit"] = (C.c_int, [vp, C.c_uint64, vp, C.c_int])
+PROTOTYPES["gvs_fastx_read_packed"] = (C.c_int, [C.POINTER(C.c_char_p), C.c_uint32, C.c_int, C.c_int, C.c_uint64, C.POINTER(FastxStruct),
+                                                 C.c_char_p, C.c_uint64])
+
+
+class ColStruct(C.Structure):
+    """struct gvs_col of include/gavisunk_b200.h"""
+    _fields_ = [("kind", C.c_int32), ("k", C.c_int32), ("data", C.c_void_p), ("names", C.c_void_p), ("name_off", C.c_void_p),
+                ("prefix", C.c_char), ("sep", C.c_char)]
+
+
+PROTOTYPES["gvs_format_rows"] = (C.c_int64, [C.POINTER(ColStruct), C.c_uint32, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, C.c_int])
 
 GVS_E_KEYERROR = -3
 STAGES = {"probe": 0, "emit": 1, "diag": 2, "hist": 3, "validate": 4, "intervals": 5, "dbbuild": 6}

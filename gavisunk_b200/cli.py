@@ -10,7 +10,10 @@
   python -m gavisunk_b200.cli slop_gaps <gaps.bed> <asm.fai> <out.bed>
   python -m gavisunk_b200.cli covprob --bed B --locs L --rlen R --fai F --sunk-len K --tsv OUT
   python -m gavisunk_b200.cli split_locs --ont-pos P --kmer-loc L --flag results/S/breaks/hapN_splits_pos.done --hap hapN
+  python -m gavisunk_b200.cli split_ont --reads R.. --out temp/S/reads/hapN_1-of-10.fq.gz ..   (seqtk seq -F '#' | rustybam fastq-split)
+  python -m gavisunk_b200.cli combine_ont_nofilt <chunk.sunkpos>.. <hapN_detailed.sunkpos>
   python -m gavisunk_b200.cli fused --sample S --k K --hap1-asm .. --hap2-asm .. --hap1-reads f.. --hap2-reads f.. --outdir D
+                                    [--devices 0,1,..] [--batch-files N] [--detailed]
 
 The first four replace workflow/scripts/{kmerpos_annot3,rlen,diag_filter_v3,diag_filter_step2}
 (workflow/rules/tagONT.smk:36,73,92,110) one to one; the next six replace badsunks_AR.py,
@@ -64,16 +67,20 @@ def cmd_kmerpos_annot3(argv):
     k = _k_from_db(db_lines)
     eng = Engine(k if 1 <= k <= 32 else 20)
     eng.load_loc_text(db_lines, list(zip(contig, start, [km.encode() for km in kmer], group)))
-    reads = gio.NativeReads([reads_p])  # multi-threaded gz/parse into page-locked memory (csrc/fastx.cu)
-    eng.set_reads(reads.seq, reads.read_off)
+    reads = gio.NativeReads([reads_p], packed=True)  # parse + 2-bit pack in one pass into page-locked memory (csrc/fastx.cu)
+    eng.set_reads_packed(reads.words, reads.read_off)
     eng.match()
-    _atomic_write(out_p, _fmt_rows(eng.rows(0), reads.names, eng.contig_names))
+    rows = eng.rows(0)
+    rtab, ctab = gio.NameTable(blob=reads.name_blob, off=reads.name_off), gio.NameTable(eng.contig_names)
+    _write_bytes(out_p, gio.format_rows([("name", rows["read"], rtab), ("u32", rows["pos"]), ("name", rows["contig"], ctab),
+                                         ("u32", rows["start"]), ("u32", rows["group"])]))
 
 
 def cmd_rlen(argv):
     reads_p, out_p = argv
-    reads = gio.NativeReads([reads_p], pin=False)
-    _atomic_write(out_p, "".join(f"{n}\t{l}\n" for n, l in zip(reads.names, reads.lengths().tolist())))
+    reads = gio.NativeReads([reads_p], pin=False, packed=True)
+    rtab = gio.NameTable(blob=reads.name_blob, off=reads.name_off)
+    _write_bytes(out_p, gio.format_rows([("name", np.arange(reads.n_reads, dtype=np.uint32), rtab), ("u64", reads.lengths())]))
 
 
 def _rows_from_sunkpos(path):
@@ -391,7 +398,65 @@ def cmd_split_locs(argv):
 
 
 # ------------------------------------------------------------------------------------------------
-# fused: defineSUNKs.smk + tagONT.smk (SUNK_annot .. get_gaps) for one sample
+# split_ONT (workflow/rules/tagONT.smk:2-18): cat reads | seqtk seq -F '#' | rustybam fastq-split outs
+# ------------------------------------------------------------------------------------------------
+def split_ont(reads_paths: Sequence[str], out_paths: Sequence[str], threads: int = 0):
+    """The scatter step of the reference: every record becomes a 4-line FASTQ record with a fake quality of '#'
+    (`seqtk seq -F '#'`) and record i goes to output i mod N (`rustybam fastq-split`), outputs gzip-compressed when
+    they end in .gz.  seqtk and rustybam are not installed here, so this step is PARITY UNPINNED: the round-robin
+    distribution is rustybam's documented behaviour, and the header comment seqtk would keep is dropped (no
+    consumer reads past the name: kmerpos_annot3.nim:85, rlen.nim:13).  Outputs that depend on the chunking (the
+    prevLoc carry and the Table capacity of a chunk) are identical to the reference's whenever
+    the chunk files are."""
+    import gzip
+    from concurrent.futures import ThreadPoolExecutor
+    reads = gio.NativeReads(list(reads_paths), pin=False)
+    n_out = len(out_paths)
+    off = reads.read_off
+    seq = reads.seq
+    nt = gio.NameTable(blob=reads.name_blob, off=reads.name_off)
+    no = nt.off.tolist()
+
+    def write(c):
+        opener = (lambda p: gzip.open(p, "wb", compresslevel=1)) if out_paths[c].endswith(".gz") else (lambda p: open(p, "wb"))
+        tmp = out_paths[c] + ".tmp%d" % os.getpid()
+        with opener(tmp) as f:
+            for r in range(c, reads.n_reads, n_out):
+                a, b = int(off[r]), int(off[r + 1])
+                f.write(b"@" + nt.blob[no[r]:no[r + 1]] + b"\n")
+                f.write(seq[a:b].tobytes())
+                f.write(b"\n+\n" + b"#" * (b - a) + b"\n")
+        os.replace(tmp, out_paths[c])
+    with ThreadPoolExecutor(max_workers=threads or min(n_out, os.cpu_count() or 1)) as ex:
+        list(ex.map(write, range(n_out)))
+    reads.close()
+
+
+def cmd_split_ont(argv):
+    ap = argparse.ArgumentParser(prog="gavisunk_b200.cli split_ont")
+    ap.add_argument("--reads", nargs="+", required=True)
+    ap.add_argument("--out", nargs="+", required=True, help="temp/{sample}/reads/{hap}_{i}-of-{N}.fq.gz in scatter order")
+    a = ap.parse_args(argv)
+    split_ont(a.reads, a.out)
+
+
+def cmd_combine_ont_nofilt(argv):
+    """combine_ont_nofilt (workflow/rules/tagONT.smk:39-55): cat of the unfiltered chunk outputs in gather order"""
+    *ins, out_p = argv
+    tmp = out_p + ".tmp%d" % os.getpid()
+    with open(tmp, "wb") as o:
+        for p in ins:
+            with open(p, "rb") as f:
+                while True:
+                    blk = f.read(1 << 24)
+                    if not blk:
+                        break
+                    o.write(blk)
+    os.replace(tmp, out_p)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused: defineSUNKs.smk + tagONT.smk (SUNK_annot .. slop_gaps) for one sample, on one or several GPUs
 # ------------------------------------------------------------------------------------------------
 def decode_kmers(km: np.ndarray, k: int) -> List[str]:
     if len(km) == 0:
@@ -402,95 +467,316 @@ def decode_kmers(km: np.ndarray, k: int) -> List[str]:
     return letters.view(f"S{k}").ravel().astype(str).tolist()
 
 
-def run_fused(k: int, hap_asm: Sequence[str], hap_reads: Sequence[Sequence[str]], outdir: str, device: int = 0):
-    """hap_asm: two FASTA paths; hap_reads: two lists of chunk files in scatter order."""
+def _write_bytes(path: str, data):
+    tmp = path + ".tmp%d" % os.getpid()
+    with open(tmp, "wb") as f:
+        f.write(data)
+    os.replace(tmp, path)
+
+
+def plan_batches(files: Sequence[str], n_devices: int, batch_files: int = 0, batch_gbp: float = 12.0) -> List[List[int]]:
+    """groups of consecutive chunk files (scatter order: hap1 chunks, then hap2 chunks).  batch_files > 0 fixes the
+    group size; otherwise groups hold about `batch_gbp` Gbp (estimated from the file sizes: FASTQ = 2 bytes per
+    base, gzip ~ 4x) and there are at least as many groups as devices when the files allow it."""
+    n = len(files)
+    if n == 0:
+        return []
+    if batch_files > 0:
+        return [list(range(i, min(n, i + batch_files))) for i in range(0, n, batch_files)]
+
+    def est_bases(p):
+        try:
+            sz = os.path.getsize(p)
+        except OSError:
+            return 0
+        with open(p, "rb") as f:
+            head = f.read(2)
+        gz = head == b"\x1f\x8b"
+        fq = p.endswith((".fq", ".fastq", ".fq.gz", ".fastq.gz"))
+        return sz * (4 if gz else 1) // (2 if fq else 1)
+    est = [est_bases(p) for p in files]
+    want = max(1.0, min(batch_gbp * 1e9, sum(est) / max(1, n_devices)))
+    out, cur, acc = [], [], 0
+    for i, e in enumerate(est):
+        if cur and acc + e > want * 1.05 and len(out) + 1 + (n - i) >= n_devices:
+            out.append(cur)
+            cur, acc = [], 0
+        cur.append(i)
+        acc += e
+    if cur:
+        out.append(cur)
+    return out
+
+
+class ThreadExchange:
+    """The two exchanges of the path between the engines of one process (one host thread per GPU): the histogram
+    sum and the forest gather of gavisunk_b200.parallel, done with torch copies between the devices (plumbing)."""
+
+    def __init__(self, engines):
+        import threading
+        self.engines = engines
+        self.n = len(engines)
+        self.bar = threading.Barrier(self.n)
+        self.slots = [None] * self.n
+        self.keep = [None] * self.n
+        self.failed = False
+
+    def abort(self):
+        self.failed = True
+        self.bar.abort()
+
+    def for_rank(self, r):
+        x = self
+
+        class _R:
+            @staticmethod
+            def allreduce_hist(ptr, n_groups):
+                if x.n == 1 or not n_groups:
+                    return
+                import torch
+                from .parallel import alias_device_array
+                dev = torch.device("cuda", x.engines[r].device)
+                x.engines[r].sync()
+                x.slots[r] = alias_device_array(ptr, n_groups, "<i4", dev)
+                x.bar.wait()
+                if r == 0:
+                    tot = x.slots[0].clone()
+                    for p in range(1, x.n):
+                        tot += x.slots[p].to(tot.device)
+                    for p in range(x.n):
+                        x.slots[p].copy_(tot.to(x.slots[p].device))
+                    for p in range(x.n):
+                        torch.cuda.synchronize(x.slots[p].device)
+                x.bar.wait()
+
+            @staticmethod
+            def gather_forests(ptr, n_groups):
+                if x.n == 1 or not n_groups:
+                    return []
+                import torch
+                from .parallel import alias_device_array
+                dev = torch.device("cuda", x.engines[r].device)
+                x.engines[r].sync()
+                x.slots[r] = alias_device_array(ptr, n_groups, "<i4", dev)
+                x.bar.wait()
+                peers = [x.slots[p].to(dev) for p in range(x.n) if p != r]
+                torch.cuda.synchronize(dev)
+                x.keep[r] = peers
+                x.bar.wait()  # nobody unions into its own forest while a peer still copies it
+                return [int(t.data_ptr()) for t in peers]
+        return _R
+
+
+def run_fused(k: int, hap_asm: Sequence[str], hap_reads: Sequence[Sequence[str]], outdir: str, device: int = 0,
+              devices: Sequence[int] = None, batch_files: int = 0, batch_gbp: float = 12.0, detailed: bool = False,
+              threads: int = 0, mrsfast_palindromes: bool = False):
+    """hap_asm: two FASTA paths; hap_reads: two lists of chunk files in scatter order.  The chunk files are
+    grouped into batches (plan_batches); every GPU of `devices` owns a contiguous block of the batches and runs
+    Engine.run_batches on it (one host thread per GPU, two exchanges per run).  Reads are parsed and 2-bit packed
+    in one pass (gio.NativeReads(packed=True)) while the previous batch is on the GPU.  Returns the first
+    device's engine."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    from .parallel import shard_chunks
+    devices = list(devices) if devices else [device]
     contigs, contig_hap, fai = [], [], [[], []]
     for hap in range(2):
         for n, s in gio.read_fastx(hap_asm[hap]):
             contigs.append((n, s))
             contig_hap.append(hap)
             fai[hap].append((n, len(s)))
-    eng = Engine(k, device=device)
-    eng.build_db(contigs)
-    names = eng.contig_names
     files = list(hap_reads[0]) + list(hap_reads[1])
-    chunk_hap = [0] * len(hap_reads[0]) + [1] * len(hap_reads[1])
-    reads = gio.NativeReads(files)  # one chunk per file, in scatter order
-    rnames, lens, chunk_first = reads.names, reads.lengths().tolist(), reads.chunk_first.tolist()
-    eng.set_reads(reads.seq, reads.read_off, chunk_first, chunk_hap)
-    iv = eng.run_all(contig_hap)
+    file_hap = [0] * len(hap_reads[0]) + [1] * len(hap_reads[1])
+    for p in files:
+        if not os.path.exists(p):
+            raise FileNotFoundError(p)
+    batches = plan_batches(files, len(devices), batch_files, batch_gbp)
+    shards = shard_chunks(len(batches), len(devices))
+    n_cpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ingest_threads = threads or max(1, n_cpu // len(devices))
+    engines = [None] * len(devices)
+    results = [None] * len(devices)
+    errors = []
+    xch = None
+    ready = threading.Barrier(len(devices))
+
+    def worker(di):
+        nonlocal xch
+        try:
+            eng = Engine(k, device=devices[di])
+            engines[di] = eng
+            eng.build_db(contigs)
+            ready.wait()
+            if di == 0:
+                xch = ThreadExchange(engines)
+            ready.wait()
+            coll = xch.for_rank(di)
+            mine = batches[shards[di][0]:shards[di][1]]
+            load = lambda fl: gio.NativeReads([files[i] for i in fl], threads=ingest_threads, packed=True)
+            info = dict(names=[], lens=[], chunk_first=[], chunk_hap=[], rows0=[], n_reads=0)
+            with ThreadPoolExecutor(max_workers=1) as pre:
+                fut = pre.submit(load, mine[0]) if mine else None
+                held = []
+
+                def bind_for(bi):
+                    def bind(e):
+                        nonlocal fut
+                        reads = fut.result()
+                        fut = pre.submit(load, mine[bi + 1]) if bi + 1 < len(mine) else None
+                        for old in held:  # the previous batch's words: its copies finished with its match
+                            old.close()
+                        held.clear()
+                        held.append(reads)
+                        ch = [file_hap[i] for i in mine[bi]]
+                        e.set_reads_packed(reads.words, reads.read_off, reads.chunk_first, ch)
+                        info["names"].append(gio.NameTable(blob=reads.name_blob, off=reads.name_off))
+                        info["lens"].append(reads.lengths().astype(np.uint32))
+                        info["chunk_first"].append(reads.chunk_first.astype(np.int64) + info["n_reads"])
+                        info["chunk_hap"].append(np.asarray(ch, np.uint8))
+                        info["n_reads"] += reads.n_reads
+                    return bind
+
+                def on_batch(e, b, base):
+                    if detailed:
+                        r0 = e.rows(0)
+                        r0["read"] = r0["read"] + np.uint32(base)
+                        info["rows0"].append(r0)
+                iv, bases = eng.run_batches([bind_for(bi) for bi in range(len(mine))], contig_hap,
+                                            allreduce_hist=coll.allreduce_hist, gather_forests=coll.gather_forests,
+                                            on_batch=on_batch)
+                for old in held:
+                    old.close()
+            info.update(kept=eng.rows(1), pairs=eng.pairs(), iv=iv)
+            results[di] = info
+        except BaseException as ex:  # noqa: BLE001 -- reported by the caller; peers must not wait for this rank
+            errors.append(ex)
+            ready.abort()
+            if xch is not None:
+                xch.abort()
+
+    if len(devices) == 1:
+        worker(0)
+    else:
+        ths = [threading.Thread(target=worker, args=(i,)) for i in range(len(devices))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    if errors:
+        first = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)] or errors
+        raise first[0]
+    eng = engines[0]
+    names = eng.contig_names
+    iv = results[0]["iv"]
     gaps, nodata = eng.gaps(np.asarray([len(s) for _, s in contigs], dtype=np.uint32))
-    # ---- files (SURVEY Appendix C) ----
+    _write_outputs(k, eng, results, contigs, contig_hap, fai, names, iv, gaps, nodata, outdir, detailed, mrsfast_palindromes)
+    for e in engines[1:]:
+        e.close()
+    return eng
+
+
+def _write_outputs(k, eng, results, contigs, contig_hap, fai, names, iv, gaps, nodata, outdir, detailed, palindromes):
+    """every file of SURVEY Appendix C that the rules between jellyfish_count and slop_gaps produce"""
     d = lambda *p: os.path.join(outdir, *p)
     for sub in ("db", "mrsfast", "sunkpos", "breaks", "inter_outs", "bed_files", "final_out"):
         os.makedirs(d(sub), exist_ok=True)
-    db = eng.db_export()
-    kmers = decode_kmers(db["kmer"], k)
-    _atomic_write(d("db", "jellyfish.db"), "".join(km + "\n" for km in kmers))
-    _atomic_write(d("db", "jellyfish.fa"), "".join(f">{km}\n{km}\n" for km in kmers))
-    _atomic_write(d("mrsfast", "kmer.loc"), "".join(
-        f"{names[c]}\t{s}\t{km}\t{g}\n" for c, s, km, g in zip(db["contig"].tolist(), db["start"].tolist(), kmers, db["group"].tolist())))
-    kept = eng.rows(1)
-    first_read_of_hap = [chunk_first[chunk_hap.index(h)] if h in chunk_hap else len(rnames) for h in (0, 1)] + [len(rnames)]
-    hap_of_read = lambda r: 0 if r < first_read_of_hap[1] else 1
-    for hap in range(2):
-        lo, hi = (0, first_read_of_hap[1]) if hap == 0 else (first_read_of_hap[1], len(rnames))
-        sel = (kept["read"] >= lo) & (kept["read"] < hi)
-        sub = {c: v[sel] for c, v in kept.items()}
-        _atomic_write(d("sunkpos", f"hap{hap + 1}.sunkpos"), _fmt_rows(sub, rnames, names))
-        _atomic_write(d("sunkpos", f"hap{hap + 1}.rlen"), "".join(f"{rnames[r]}\t{lens[r]}\n" for r in range(lo, hi)))
-    gidx_name = {}
-    for c, g, gi in zip(db["contig"].tolist(), db["group"].tolist(), db["gidx"].tolist()):
-        gidx_name[gi] = f"{names[c]}:{g}"
-    _atomic_write(d("sunkpos", "bad_sunks.txt"), "".join(gidx_name[int(g)] + "\n" for g in eng.bad_list()))
-    # per-contig files: breaks/*.sunkpos|.loc (split_locs.py:5-22), inter_outs/*.tsv, bed_files/*.bed
+    ctab = gio.NameTable(names)
     safe = lambda n: n.replace("#", "_")
-    by_c = defaultdict(list)
-    for i, c in enumerate(kept["contig"].tolist()):
-        by_c[c].append(i)
-    for c, idx in by_c.items():
-        idx = np.asarray(idx)
-        sub = {col: v[idx] for col, v in kept.items()}
-        _atomic_write(d("breaks", f"{safe(names[c])}_hap{contig_hap[c] + 1}.sunkpos"), _fmt_rows(sub, rnames, names))
-    loc_by_c = defaultdict(list)
-    for c, s, km, g in zip(db["contig"].tolist(), db["start"].tolist(), kmers, db["group"].tolist()):
-        loc_by_c[c].append(f"{names[c]}\t{s}\t{km}\t{g}\n")
-    for c, lines in loc_by_c.items():
-        if c in by_c:
-            _atomic_write(d("breaks", f"{safe(names[c])}_hap{contig_hap[c] + 1}.loc"), "".join(lines))
-    pairs = eng.pairs()
-    inter = defaultdict(list)
-    for r, c, g in zip(pairs["read"].tolist(), pairs["contig"].tolist(), pairs["group"].tolist()):
-        inter[c].append((rnames[r], r, g))
-    bed = defaultdict(list)
-    for c, s, e in zip(iv["contig"].tolist(), iv["start"].tolist(), iv["end"].tolist()):
-        bed[c].append((names[c], s, e))
-    for c in by_c:
-        hapn = contig_hap[c] + 1
-        rows = inter.get(c, [])
-        if rows:
-            # `for rname, g in grouped`: groupby sorts read names (process-by-contig_lowmem_AR.py:135-136);
-            # the sort is stable, so the vertex order inside a read is preserved
-            rows = sorted(rows, key=lambda t: t[0])
-            _atomic_write(d("inter_outs", f"{safe(names[c])}_hap{hapn}.tsv"), "".join(f"{g}\t{n}\n" for n, _, g in rows))
-            _atomic_write(d("bed_files", f"{safe(names[c])}_hap{hapn}.bed"), "".join(f"{a}\t{s}\t{e}\n" for a, s, e in bed.get(c, [])))
+    # ---- run-wide read table: devices in order, batches in order ----
+    read_base, nreads = [], 0
+    for r in results:
+        read_base.append(nreads)
+        nreads += r["n_reads"]
+    rtab = gio.NameTable.concat([t for r in results for t in r["names"]])
+    lens = np.concatenate([l for r in results for l in r["lens"]] + [np.zeros(0, np.uint32)])
+    chunk_first = np.concatenate([cf[:-1] + read_base[i] for i, r in enumerate(results) for cf in r["chunk_first"]] + [np.array([nreads])])
+    chunk_hap = np.concatenate([ch for r in results for ch in r["chunk_hap"]] + [np.zeros(0, np.uint8)])
+    read_hap = np.zeros(nreads, np.uint8)
+    for c in range(len(chunk_hap)):
+        read_hap[int(chunk_first[c]):int(chunk_first[c + 1])] = chunk_hap[c]
+
+    def cat_rows(key, cols):
+        out = {}
+        for c in cols:
+            parts = []
+            for i, r in enumerate(results):
+                tabs = r[key] if isinstance(r[key], list) else [r[key]]
+                for t in tabs:
+                    parts.append(t[c] + np.uint32(read_base[i]) if c == "read" else t[c])
+            out[c] = np.concatenate(parts) if parts else np.zeros(0, np.uint32)
+        return out
+    kept = cat_rows("kept", ("read", "pos", "contig", "start", "group"))
+    pairs = cat_rows("pairs", ("read", "contig", "group"))
+    sunk_cols = lambda t: [("name", t["read"], rtab), ("u32", t["pos"]), ("name", t["contig"], ctab), ("u32", t["start"]), ("u32", t["group"])]
+    # ---- SUNK database files (defineSUNKs.smk:59-60, 126) ----
+    db = eng.db_export()
+    loc_cols = [("name", db["contig"], ctab), ("u32", db["start"]), ("kmer", db["kmer"], k), ("u32", db["group"])]
+    loc_sel = None
+    if palindromes and k % 2 == 0 and len(db["kmer"]):
+        # mrsfast reports a k-mer that is its own reverse complement on both strands: two identical rows (SURVEY A.2)
+        from .engine import revcomp_kmers
+        pal = db["kmer"] == revcomp_kmers(db["kmer"], k)
+        loc_sel = np.repeat(np.arange(len(pal), dtype=np.uint64), 1 + pal.astype(np.int64))
+    _write_bytes(d("db", "jellyfish.db"), gio.format_rows([("kmer", db["kmer"], k)]))
+    _write_bytes(d("db", "jellyfish.fa"), gio.format_rows([("kmer", db["kmer"], k, dict(prefix=b">", sep=b"\n")), ("kmer", db["kmer"], k)]))
+    _write_bytes(d("mrsfast", "kmer.loc"), gio.format_rows(loc_cols, sel=loc_sel))
+    # ---- per-haplotype row files (combine_ont, combine_ont_nofilt, read_lengths) ----
+    khap = read_hap[kept["read"]] if len(kept["read"]) else np.zeros(0, np.uint8)
+    all_reads = np.arange(nreads, dtype=np.uint32)
+    if detailed:
+        rows0 = cat_rows("rows0", ("read", "pos", "contig", "start", "group"))
+        r0hap = read_hap[rows0["read"]] if len(rows0["read"]) else np.zeros(0, np.uint8)
+    for hap in range(2):
+        _write_bytes(d("sunkpos", f"hap{hap + 1}.sunkpos"), gio.format_rows(sunk_cols(kept), sel=np.flatnonzero(khap == hap)))
+        _write_bytes(d("sunkpos", f"hap{hap + 1}.rlen"), gio.format_rows([("name", all_reads, rtab), ("u32", lens)], sel=np.flatnonzero(read_hap == hap)))
+        if detailed:  # unfiltered rows for plot_detailed (viz_detailed.py:48)
+            _write_bytes(d("sunkpos", f"hap{hap + 1}_detailed.sunkpos"), gio.format_rows(sunk_cols(rows0), sel=np.flatnonzero(r0hap == hap)))
+    gtab = eng.groups()
+    bad = eng.bad_list()
+    _write_bytes(d("sunkpos", "bad_sunks.txt"), gio.format_rows([("name", gtab["contig"][bad], ctab, dict(sep=b":")), ("u32", gtab["group"][bad])]))
+    # ---- per-contig files: breaks/*.sunkpos|.loc (split_locs.py:5-22), inter_outs/*.tsv, bed_files/*.bed ----
+    def by_contig(col):
+        order = np.argsort(col, kind="stable")
+        cs, first = np.unique(col[order], return_index=True)
+        ends = list(first[1:]) + [len(order)]
+        return {int(c): order[a:b] for c, a, b in zip(cs, first, ends)}
+    kept_c, loc_c, pair_c = by_contig(kept["contig"]), by_contig(db["contig"]), by_contig(pairs["contig"])
+    iv_c = by_contig(iv["contig"])
+    # `for rname, g in grouped`: groupby sorts read names (process-by-contig_lowmem_AR.py:135-136); rank of every read
+    # name in that order (stable for equal names), pairs of a read stay in vertex order
+    name_rank = np.empty(nreads, np.int64)
+    if nreads:
+        name_rank[np.argsort(rtab.as_bytes_array(), kind="stable")] = np.arange(nreads)
+    for c, idx in kept_c.items():
+        stem = f"{safe(names[c])}_hap{contig_hap[c] + 1}"
+        _write_bytes(d("breaks", stem + ".sunkpos"), gio.format_rows(sunk_cols(kept), sel=idx))
+        if c in loc_c:
+            sel = loc_c[c]
+            if loc_sel is not None:
+                sel = np.repeat(sel, 1 + (db["kmer"][sel] == revcomp_kmers(db["kmer"][sel], k)).astype(np.int64))
+            _write_bytes(d("breaks", stem + ".loc"), gio.format_rows(loc_cols, sel=sel))
+        if c in pair_c:
+            pidx = pair_c[c]
+            pidx = pidx[np.argsort(name_rank[pairs["read"][pidx]], kind="stable")]
+            _write_bytes(d("inter_outs", stem + ".tsv"), gio.format_rows([("u32", pairs["group"]), ("name", pairs["read"], rtab)], sel=pidx))
+            _write_bytes(d("bed_files", stem + ".bed"), gio.format_rows([("name", iv["contig"], ctab), ("u32", iv["start"]), ("u32", iv["end"])],
+                                                                    sel=iv_c.get(c, np.zeros(0, np.uint64))))
         else:  # "no usable reads": contig name only, bed touched empty by the rule (tagONT.smk:190)
-            _atomic_write(d("inter_outs", f"{safe(names[c])}_hap{hapn}.tsv"), names[c] + "\n")
-            _atomic_write(d("bed_files", f"{safe(names[c])}_hap{hapn}.bed"), "")
+            _write_bytes(d("inter_outs", stem + ".tsv"), (names[c] + "\n").encode("latin-1"))
+            _write_bytes(d("bed_files", stem + ".bed"), b"")
+    clen = np.asarray([len(s) for _, s in contigs], dtype=np.uint32)
+    chap = np.asarray(contig_hap, np.uint8)
     for hap in range(2):
         hn = hap + 1
-        valid = [f"{names[c]}\t{s}\t{e}\n" for c, s, e in zip(iv["contig"].tolist(), iv["start"].tolist(), iv["end"].tolist())
-                 if contig_hap[c] == hap]
-        _atomic_write(d("final_out", f"hap{hn}.valid.bed"), "".join(valid))
-        g_rows = [(names[c], s, e) for c, s, e in zip(gaps["contig"].tolist(), gaps["start"].tolist(), gaps["end"].tolist())
-                  if contig_hap[c] == hap]
-        _atomic_write(d("final_out", f"hap{hn}.gaps.bed"), "".join(f"{a}\t{s}\t{e}\n" for a, s, e in g_rows))
-        _atomic_write(d("final_out", f"hap{hn}.nodata.bed"), "".join(
-            f"{names[c]}\t0\t{len(contigs[c][1])}\n" for c in nodata.tolist() if contig_hap[c] == hap))
-        clen = {n: l for n, l in fai[hap]}
-        _atomic_write(d("final_out", f"hap{hn}.gaps.slop.bed"), "".join(  # bedtools slop -b 200000 (tagONT.smk:249)
-            f"{a}\t{max(0, s - 200000)}\t{min(clen[a], e + 200000)}\n" for a, s, e in g_rows))
-    return eng
+        open(d("breaks", f"hap{hn}_splits_pos.done"), "a").close()  # touch() of the checkpoint (tagONT.smk:158)
+        bed3 = lambda t: [("name", t["contig"], ctab), ("u32", t["start"]), ("u32", t["end"])]
+        _write_bytes(d("final_out", f"hap{hn}.valid.bed"), gio.format_rows(bed3(iv), sel=np.flatnonzero(chap[iv["contig"]] == hap)))
+        gsel = np.flatnonzero(chap[gaps["contig"]] == hap)
+        _write_bytes(d("final_out", f"hap{hn}.gaps.bed"), gio.format_rows(bed3(gaps), sel=gsel))
+        nd = nodata[chap[nodata] == hap]
+        _write_bytes(d("final_out", f"hap{hn}.nodata.bed"), gio.format_rows([("name", nd, ctab), ("u32", np.zeros(len(nd), np.uint32)), ("u32", clen[nd])]))
+        s2, e2 = eng.slop(gaps["contig"][gsel], gaps["start"][gsel], gaps["end"][gsel], clen, 200000)  # bedtools slop -b 200000 (tagONT.smk:249)
+        _write_bytes(d("final_out", f"hap{hn}.gaps.slop.bed"), gio.format_rows([("name", gaps["contig"][gsel], ctab), ("i64", s2), ("i64", e2)]))
 
 
 def cmd_fused(argv):
@@ -503,14 +789,24 @@ def cmd_fused(argv):
     ap.add_argument("--hap2-reads", nargs="+", required=True)
     ap.add_argument("--outdir", required=True)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--devices", default=None, help="comma-separated GPU indices: the chunk files are sharded over them")
+    ap.add_argument("--batch-files", type=int, default=0, help="chunk files per batch (0 = by size, about --batch-gbp each)")
+    ap.add_argument("--batch-gbp", type=float, default=12.0)
+    ap.add_argument("--detailed", action="store_true", help="also write sunkpos/{hap}_detailed.sunkpos (plot_detailed: true)")
+    ap.add_argument("--threads", type=int, default=0, help="ingest threads per GPU")
+    ap.add_argument("--mrsfast-palindromes", action="store_true",
+                    help="write a palindromic SUNK twice into kmer.loc, as mrsfast reports it on both strands (SURVEY A.2; unpinned)")
     a = ap.parse_args(argv)
-    run_fused(a.k, [a.hap1_asm, a.hap2_asm], [a.hap1_reads, a.hap2_reads], a.outdir, a.device)
+    devs = [int(x) for x in a.devices.split(",")] if a.devices else [a.device]
+    run_fused(a.k, [a.hap1_asm, a.hap2_asm], [a.hap1_reads, a.hap2_reads], a.outdir, devices=devs, batch_files=a.batch_files,
+              batch_gbp=a.batch_gbp, detailed=a.detailed, threads=a.threads, mrsfast_palindromes=a.mrsfast_palindromes)
 
 
 COMMANDS = {"kmerpos_annot3": (cmd_kmerpos_annot3, 4), "rlen": (cmd_rlen, 2), "diag_filter_v3": (cmd_diag_filter_v3, 2),
             "diag_filter_step2": (cmd_diag_filter_step2, 2), "badsunks_AR": (cmd_badsunks, 5),
             "process_by_contig": (cmd_process_by_contig, None), "get_gaps": (cmd_get_gaps, 5), "slop_gaps": (cmd_slop_gaps, 3),
-            "covprob": (cmd_covprob, None), "split_locs": (cmd_split_locs, None), "fused": (cmd_fused, None)}
+            "covprob": (cmd_covprob, None), "split_locs": (cmd_split_locs, None), "fused": (cmd_fused, None),
+            "split_ont": (cmd_split_ont, None), "combine_ont_nofilt": (cmd_combine_ont_nofilt, None)}
 
 
 def main(argv=None):

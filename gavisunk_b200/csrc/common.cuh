@@ -133,6 +133,10 @@ struct gvs_ctx {
   DevBuf best_read, best_contig, best_good, best_dir;
   u64 n_best = 0;
   bool diag_ready = false;
+  // kept rows + read lengths of the batches of one run (batches.cu): read indices count through the batches
+  Rows stash;
+  DevBuf stash_len;
+  u64 stash_reads = 0;
 
   // ---- histogram / bad groups ----
   DevBuf hist, cnt_hist, bad_flag, bad_list;

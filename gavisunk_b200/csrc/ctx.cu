@@ -178,6 +178,8 @@ extern "C" void gvs_destroy(gvs_ctx* c) {
   for (DevBuf* b : all) gvs_release(*b);
   release_rows(c->rows);
   release_rows(c->kept);
+  release_rows(c->stash);
+  gvs_release(c->stash_len);
   for (int i = 0; i < GVS_ST_COUNT; i++) {
     cudaEventDestroy(c->ev0[i]);
     cudaEventDestroy(c->ev1[i]);

@@ -9,6 +9,10 @@
 // records are emitted, FASTA and FASTQ records may be mixed, a truncated quality string still
 // yields its record.  No CUDA kernel here: decompression and line splitting are host work; pinning
 // is what lets gvs_reads_set overlap the PCIe copy with the probe.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <atomic>
@@ -294,3 +298,386 @@ extern "C" void gvs_fastx_free(gvs_fastx* fx) {
   delete R;
   memset(fx, 0, sizeof(*fx));
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused parse + 2-bit pack: the ingest's native path.  The ASCII bases never land in memory as a batch: every file
+// is streamed block by block (plain files straight out of the page cache through mmap, gzip files through a
+// cache-sized inflate window), the readfq state machine above runs as a push parser across block boundaries, and
+// the sequence bytes go through kmer.encode's byte map (hostpack.cpp, pinned by tests/golden/kat_bytes) into
+// per-file 2-bit words.  The files' word strings are then shifted into ONE page-locked array of big-endian
+// 16-base words: the layout gvs_reads_set_packed hands to the PACKED probe variant, a quarter of the ASCII bytes
+// on the PCIe link.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct PackedFile {
+  std::vector<u32> words;  // 2-bit words of this file's bases, starting at base 0 of the file
+  u64 n_bases = 0;
+  u8 pend[16];             // bases of the unfinished last word
+  u32 n_pend = 0;
+  std::vector<u64> len;
+  std::string names;
+  std::vector<u64> name_end;
+  std::string err;
+
+  void append(const u8* b, const u8* e) {
+    u64 n = (u64)(e - b);
+    if (!n) return;
+    n_bases += n;
+    if (n_pend) {
+      while (n_pend < 16 && b < e) pend[n_pend++] = *b++;
+      if (n_pend < 16) return;
+      u32 w;
+      gvs_hostpack_range(pend, 16, &w, 0, 1);
+      words.push_back(w);
+      n_pend = 0;
+      n = (u64)(e - b);
+    }
+    const u64 full = n / 16;
+    if (full) {
+      const size_t at = words.size();
+      words.resize(at + full);
+      gvs_hostpack_range(b, full * 16, words.data() + at, 0, full);
+      b += full * 16;
+    }
+    while (b < e) pend[n_pend++] = *b++;
+  }
+  void finish() {
+    if (n_pend) {
+      u32 w;
+      gvs_hostpack_range(pend, n_pend, &w, 0, 1);  // zero-padded partial word
+      words.push_back(w);
+      n_pend = 0;
+    }
+  }
+};
+
+// readfq as a push parser: feed() takes the file's bytes in arbitrary pieces, end() flushes the last line.
+// Lines are classified by their first byte at the moment they start; sequence bytes are packed as they come
+// (trailing CRs of a line are held back until the line's end is seen: rstrip), header bytes are collected,
+// quality bytes are only counted.
+struct FastxPush {
+  PackedFile& out;
+  enum State { SEEK, SEQ, QUAL } st = SEEK;   // SEEK: before the first header / after a finished FASTQ record
+  enum Line { L_NONE, L_SKIP, L_HDR, L_SEQ, L_QUAL, L_PLUS } line = L_NONE;
+  bool at_line_start = true;
+  std::string hdr;        // bytes of the current header line (after the marker)
+  u64 held_cr = 0;        // trailing '\r' of the current sequence / quality line seen so far
+  u64 seq_len = 0;        // bases of the current record
+  u64 qual = 0;           // quality bytes of the current record (rstripped lines)
+  u64 line_len = 0;       // rstripped length of the current quality line so far
+  bool in_record = false;
+
+  explicit FastxPush(PackedFile& o) : out(o) {}
+
+  void open_record() {  // header line complete: name = up to the first white space ("" when it starts with a blank)
+    size_t he = hdr.size();
+    while (he > 0 && (hdr[he - 1] == '\r' || hdr[he - 1] == '\n')) he--;
+    size_t ne = 0;
+    if (he > 0 && hdr[0] != ' ' && hdr[0] != '\t')
+      while (ne < he && !is_ws((u8)hdr[ne])) ne++;
+    bool all_ws = true;
+    for (size_t q = 0; q < he; q++)
+      if (!is_ws((u8)hdr[q])) { all_ws = false; break; }
+    if (all_ws) ne = 0;
+    out.names.append(hdr.data(), ne);
+    out.name_end.push_back(out.names.size());
+    hdr.clear();
+    seq_len = 0;
+    qual = 0;
+    in_record = true;
+    st = SEQ;
+  }
+  void close_record() {
+    if (in_record) out.len.push_back(seq_len);
+    in_record = false;
+  }
+  void seq_bytes(const u8* b, const u8* e) {
+    // hold back the trailing CRs of what we have of the line; CRs followed by other bytes are sequence
+    const u8* t = e;
+    while (t > b && t[-1] == '\r') t--;
+    if (t > b) {
+      if (held_cr) {
+        static const u8 crs[16] = {'\r', '\r', '\r', '\r', '\r', '\r', '\r', '\r', '\r', '\r', '\r', '\r', '\r', '\r', '\r', '\r'};
+        seq_len += held_cr;
+        while (held_cr) {
+          u64 c = held_cr < 16 ? held_cr : 16;
+          out.append(crs, crs + c);
+          held_cr -= c;
+        }
+      }
+      out.append(b, t);
+      seq_len += (u64)(t - b);
+    }
+    held_cr += (u64)(e - t);
+  }
+  void qual_bytes(const u8* b, const u8* e) {
+    const u8* t = e;
+    while (t > b && t[-1] == '\r') t--;
+    if (t > b) {
+      line_len += held_cr + (u64)(t - b);
+      held_cr = 0;
+    }
+    held_cr += (u64)(e - t);
+  }
+  void start_line(u8 c) {
+    held_cr = 0;
+    line_len = 0;
+    switch (st) {
+      case SEEK:
+        line = (c == '>' || c == '@') ? L_HDR : L_SKIP;
+        break;
+      case SEQ:
+        if (c == '>' || c == '@') {
+          close_record();
+          line = L_HDR;
+        } else if (c == '+') {
+          line = L_PLUS;
+        } else {
+          line = L_SEQ;
+        }
+        break;
+      case QUAL:
+        line = L_QUAL;
+        break;
+    }
+  }
+  void end_line() {  // the line's '\n' (or the end of the data) has been seen
+    switch (line) {
+      case L_HDR:
+        open_record();
+        break;
+      case L_PLUS:
+        st = QUAL;
+        break;
+      case L_QUAL:
+        qual += line_len;
+        if (qual >= seq_len) {  // quality covers the sequence (at least one line was read): record complete
+          close_record();
+          st = SEEK;
+        }
+        break;
+      default:
+        break;
+    }
+    held_cr = 0;
+    line = L_NONE;
+    at_line_start = true;
+  }
+  void feed(const u8* p, const u8* end) {
+    while (p < end) {
+      if (at_line_start) {
+        if (*p == '\n') {  // empty line: never a marker; an empty quality line still counts as a line read
+          if (st == QUAL) {
+            line = L_QUAL;
+            line_len = 0;
+            end_line();
+          }
+          p++;
+          continue;
+        }
+        start_line(*p);
+        at_line_start = false;
+        if (line == L_HDR) p++;  // the marker itself
+        if (p >= end) break;
+      }
+      const u8* nl = (const u8*)memchr(p, '\n', (size_t)(end - p));
+      const u8* e = nl ? nl : end;
+      switch (line) {
+        case L_HDR: hdr.append((const char*)p, (size_t)(e - p)); break;
+        case L_SEQ: seq_bytes(p, e); break;
+        case L_QUAL: qual_bytes(p, e); break;
+        default: break;
+      }
+      if (!nl) return;
+      end_line();
+      p = nl + 1;
+    }
+  }
+  void end() {
+    if (!at_line_start) end_line();  // last line without '\n'
+    close_record();                  // FASTA record at the end of the data / truncated FASTQ
+    out.finish();
+  }
+};
+
+static bool is_gzip(int fd) {
+  u8 m[2] = {0, 0};
+  return pread(fd, m, 2, 0) == 2 && m[0] == 0x1f && m[1] == 0x8b;
+}
+
+static void ingest_file(const char* path, u64 block, PackedFile& out) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) {
+    out.err = std::string("cannot open ") + path;
+    return;
+  }
+  struct stat sb;
+  if (fstat(fd, &sb) != 0) {
+    out.err = std::string("cannot stat ") + path;
+    close(fd);
+    return;
+  }
+  FastxPush P(out);
+  if (is_gzip(fd) || !S_ISREG(sb.st_mode)) {
+    gzFile f = gzdopen(fd, "rb");  // takes the descriptor over
+    if (!f) {
+      out.err = std::string("cannot open ") + path;
+      close(fd);
+      return;
+    }
+    gzbuffer(f, 1 << 18);
+    std::vector<u8> buf(block);  // cache-sized: the inflated bytes are packed while they are still in L2
+    for (;;) {
+      int r = gzread(f, buf.data(), (unsigned)buf.size());
+      if (r < 0) {
+        int en = 0;
+        out.err = std::string(path) + ": " + gzerror(f, &en);
+        gzclose(f);
+        return;
+      }
+      if (r == 0) break;
+      P.feed(buf.data(), buf.data() + r);
+    }
+    gzclose(f);
+  } else if (sb.st_size > 0) {
+    const u64 size = (u64)sb.st_size;
+    void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) {
+      out.err = std::string("cannot map ") + path;
+      close(fd);
+      return;
+    }
+    madvise(m, size, MADV_SEQUENTIAL);
+    out.words.reserve(size / 16 / 2 + 64);
+    const u8* p = (const u8*)m;
+    for (u64 o = 0; o < size; o += block) P.feed(p + o, p + (o + block < size ? o + block : size));
+    munmap(m, size);
+    close(fd);
+  } else {
+    close(fd);
+  }
+  P.end();
+}
+
+}  // namespace
+
+// value of global word g of a file whose base 0 sits at global base B: local words shifted by B % 16 bases
+static inline u32 shifted_word(const std::vector<u32>& loc, i64 j, u32 sh) {
+  const u32 hi = (j - 1 >= 0 && (u64)(j - 1) < loc.size()) ? loc[(size_t)(j - 1)] : 0u;
+  const u32 lo = (j >= 0 && (u64)j < loc.size()) ? loc[(size_t)j] : 0u;
+  return sh ? ((hi << (32 - 2 * sh)) | (lo >> (2 * sh))) : lo;
+}
+
+extern "C" int gvs_fastx_read_packed(const char* const* paths, uint32_t n_files, int threads, int pin, uint64_t block_bytes,
+                                     gvs_fastx* out, char* err, uint64_t err_len) {
+  auto fail = [&](const std::string& m) {
+    if (err && err_len) snprintf(err, (size_t)err_len, "%s", m.c_str());
+    return GVS_E_ARG;
+  };
+  if (!out || (n_files && !paths)) return fail("gvs_fastx_read_packed: null argument");
+  memset(out, 0, sizeof(*out));
+  if (block_bytes == 0) block_bytes = 1u << 20;
+  std::vector<PackedFile> files(n_files);
+  if (threads < 1) threads = 1;
+  if ((u32)threads > n_files) threads = (int)(n_files ? n_files : 1);
+  {
+    std::atomic<u32> next{0};
+    auto work = [&]() {
+      for (;;) {
+        u32 i = next.fetch_add(1);
+        if (i >= n_files) break;
+        ingest_file(paths[i], block_bytes, files[i]);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+  }
+  for (u32 i = 0; i < n_files; i++)
+    if (!files[i].err.empty()) return fail(files[i].err);
+  gvs_fastx_impl* R = new gvs_fastx_impl();
+  u64 n_reads = 0, total = 0;
+  std::vector<u64> base(n_files + 1, 0);
+  R->chunk_first.push_back(0);
+  for (u32 i = 0; i < n_files; i++) {
+    n_reads += files[i].len.size();
+    total += files[i].n_bases;
+    base[i + 1] = total;
+    R->chunk_first.push_back(n_reads);
+  }
+  R->read_off.reserve(n_reads + 1);
+  R->name_off.reserve(n_reads + 1);
+  R->read_off.push_back(0);
+  R->name_off.push_back(0);
+  for (u32 i = 0; i < n_files; i++) {
+    u64 o = base[i];
+    for (u64 l : files[i].len) {
+      o += l;
+      R->read_off.push_back(o);
+    }
+    const u64 nb = R->names.size();
+    R->names += files[i].names;
+    for (u64 ne : files[i].name_end) R->name_off.push_back(nb + ne);
+  }
+  const u64 nw = (total + 15) / 16;
+  const size_t bytes = (nw + 16) * 4;  // slack: the probe stages whole vectors
+  if (pin && cudaHostAlloc((void**)&R->words, bytes, cudaHostAllocDefault) == cudaSuccess) {
+    R->words_pinned = true;
+  } else {
+    cudaGetLastError();
+    R->words = (u32*)malloc(bytes);
+    if (!R->words) {
+      delete R;
+      return fail("gvs_fastx_read_packed: out of host memory");
+    }
+  }
+  memset(R->words + nw, 0, 16 * 4);
+  // every file's words shifted to its place: words that lie entirely inside one file are written in parallel, the
+  // words that files share (first / last word of a file) are OR-ed together afterwards
+  for (u32 i = 0; i < n_files; i++) {
+    if (base[i + 1] == base[i]) continue;
+    R->words[base[i] / 16] = 0;
+    R->words[(base[i + 1] - 1) / 16] = 0;
+  }
+  {
+    std::atomic<u32> nx{0};
+    auto place = [&]() {
+      for (;;) {
+        u32 i = nx.fetch_add(1);
+        if (i >= n_files) break;
+        if (base[i + 1] == base[i]) continue;
+        const u64 g0 = base[i] / 16, g1 = (base[i + 1] - 1) / 16;  // first / last global word the file touches
+        const u32 sh = (u32)(base[i] % 16);
+        for (u64 g = g0 + 1; g < g1; g++) R->words[g] = shifted_word(files[i].words, (i64)(g - g0), sh);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(place);
+    place();
+    for (auto& t : pool) t.join();
+  }
+  for (u32 i = 0; i < n_files; i++) {
+    if (base[i + 1] == base[i]) continue;
+    const u64 g0 = base[i] / 16, g1 = (base[i + 1] - 1) / 16;
+    const u32 sh = (u32)(base[i] % 16);
+    R->words[g0] |= shifted_word(files[i].words, 0, sh);
+    if (g1 != g0) R->words[g1] |= shifted_word(files[i].words, (i64)(g1 - g0), sh);
+    std::vector<u32>().swap(files[i].words);
+  }
+  out->impl = R;
+  out->seq = nullptr;
+  out->read_off = R->read_off.data();
+  out->names = R->names.data();
+  out->name_off = R->name_off.data();
+  out->chunk_first = R->chunk_first.data();
+  out->n_reads = n_reads;
+  out->total_bases = total;
+  out->n_files = n_files;
+  out->pinned = R->words_pinned ? 1 : 0;
+  out->words = R->words;
+  out->n_words = nw;
+  return 0;
+}
+

@@ -44,6 +44,16 @@ def encode_kmers(lines: Sequence[bytes], k: Optional[int] = None) -> np.ndarray:
     return out
 
 
+def revcomp_kmers(km: np.ndarray, k: int) -> np.ndarray:
+    """reverse complement of 2-bit big-endian k-mers (vectorised)"""
+    x = ~np.ascontiguousarray(km, np.uint64)
+    m = [(0x3333333333333333, 2), (0x0F0F0F0F0F0F0F0F, 4), (0x00FF00FF00FF00FF, 8), (0x0000FFFF0000FFFF, 16), (0x00000000FFFFFFFF, 32)]
+    for mask, sh in m:
+        mk = np.uint64(mask)
+        x = ((x >> np.uint64(sh)) & mk) | ((x & mk) << np.uint64(sh))
+    return x >> np.uint64(64 - 2 * k)
+
+
 def pack_2bit(seq: np.ndarray, threads: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
     """kmer.encode's byte map applied to a whole batch on the host (gvs_pack_2bit): uint8[n] -> uint32[ceil(n/16)]"""
     import os
@@ -299,6 +309,14 @@ class Engine:
         self._ck(self.lib.gvs_reads_set(self.ctx, C.c_void_p(seq_ptr), C.c_void_p(off_ptr), n_reads, _ptr(chunk_first),
                                         _ptr(chunk_hap), len(chunk_hap), 1))
 
+    def set_reads_packed_device(self, words_ptr: int, off_ptr: int, n_reads: int, chunk_first, chunk_hap):
+        """batch resident in HBM as 2-bit words (device pointers; see set_reads_packed)"""
+        chunk_first = _c(chunk_first, np.uint64)
+        chunk_hap = _c(chunk_hap, np.uint8)
+        self.n_reads = n_reads
+        self._ck(self.lib.gvs_reads_set_packed(self.ctx, C.c_void_p(words_ptr), C.c_void_p(off_ptr), n_reads, _ptr(chunk_first),
+                                               _ptr(chunk_hap), len(chunk_hap), 1))
+
     def set_reads_meta(self, read_len, chunk_first=None, chunk_hap=None):
         """Read table without sequences ({hap}.rlen, workflow/src/rlen.nim:13-14)."""
         read_len = _c(read_len, np.uint32)
@@ -387,6 +405,64 @@ class Engine:
             for peer in gather_forests(pp, self.db_groups()):
                 self.components_merge(peer)
         return self.intervals()
+
+    # ------------------------------------------------------------------------------------
+    # several batches of one run (two phases; csrc/batches.cu)
+    # ------------------------------------------------------------------------------------
+    def batches_begin(self):
+        self._ck(self.lib.gvs_batches_begin(self.ctx))
+
+    def batch_stash(self) -> int:
+        """keeps the batch's kept rows + read lengths resident; returns the run-wide index of its first read"""
+        b = C.c_uint64()
+        self._ck(self.lib.gvs_batch_stash(self.ctx, C.byref(b)))
+        return int(b.value)
+
+    def batches_bind(self) -> Tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.gvs_batches_bind(self.ctx, C.byref(a), C.byref(b)))
+        self.n_kept, self.n_reads = int(a.value), int(b.value)
+        return self.n_kept, self.n_reads
+
+    def run_batches(self, binds, contig_hap: Sequence[int], min_read_len: int = 10000, allreduce_hist=None,
+                    gather_forests=None, on_batch=None):
+        """The hot path over a run whose reads come in several batches (a sample's chunk files, or the shard of
+        them this GPU owns).  The reference gathers all chunks of a haplotype before the global stages
+        (workflow/Snakefile:23-24, workflow/rules/tagONT.smk:112-131; badsunks_AR.py:20-27 counts over every
+        row), so the run has two phases:
+          1. per batch: bind(self) registers the batch's reads (set_reads / set_reads_packed /
+             set_reads_device ...), then match -> diag filter -> histogram (accumulated) -> stash of the kept rows;
+             on_batch(self, b, read_base) may fetch the batch's rows (rows(0) / rows(1), best()) for file egress;
+          2. ONE histogram all-reduce (`allreduce_hist`), bad groups, validation of all stashed rows, local
+             forest, ONE forest all-gather (`gather_forests`), intervals.
+        Results equal run_all() on the concatenation of the batches; read indices of rows(1) / pairs() count
+        through the batches in order.  Returns (intervals, [read_base of every batch])."""
+        self.batches_begin()
+        bases, hp = [], 0
+        rows = best = 0
+        for b, bind in enumerate(binds):
+            bind(self)
+            rows += self.match()
+            best += self.diag_filter(contig_hap)[0]
+            hp = self.group_hist(accumulate=True)
+            base = self.batch_stash()
+            if on_batch is not None:
+                on_batch(self, b, base)
+            bases.append(base)
+        self.batches_bind()
+        self.n_rows, self.n_best = rows, best
+        if not bases:  # a rank without a batch still takes part in both exchanges
+            self.set_contigs(contig_hap)
+            hp = self.group_hist(accumulate=True)
+        if allreduce_hist is not None:
+            allreduce_hist(hp, self.db_groups())
+        self.bad_groups()
+        self.validate(min_read_len)
+        pp = self.components_local()
+        if gather_forests is not None:
+            for peer in gather_forests(pp, self.db_groups()):
+                self.components_merge(peer)
+        return self.intervals(), bases
 
     def db_groups(self) -> int:
         a, b = C.c_uint64(), C.c_uint64()

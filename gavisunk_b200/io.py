@@ -39,10 +39,13 @@ def iter_fastx(fp) -> Iterator[Tuple[str, bytes]]:
             if last is None:
                 return
         hdr = last[1:]
-        # name = up to first whitespace
-        name = hdr.split(None, 1)[0] if hdr.strip() else b""
-        if hdr[:1] in (b" ", b"\t"):
-            name = b""
+        # name = header up to the first white-space byte, without skipping leading white space (pinned through the
+        # reference's `rlen`: ">\r@\rT" -> "", ">a\rb c" -> "a", "> y" -> "", ">\x0bz" -> "")
+        name = hdr
+        for i, ch in enumerate(hdr):
+            if ch in b" \t\n\r\x0b\x0c":
+                name = hdr[:i]
+                break
         seqs: List[bytes] = []
         last = None
         for l in it:
@@ -81,7 +84,9 @@ class NativeReads:
     chunk per file, sequences back to back in one (page-locked when possible) host buffer.  The numpy
     arrays are views of library memory: keep this object alive while they are in use."""
 
-    def __init__(self, paths, threads: int = 0, pin: bool = True):
+    def __init__(self, paths, threads: int = 0, pin: bool = True, packed: bool = False, block_bytes: int = 0):
+        """packed=True: the fused parse + 2-bit pack path (gvs_fastx_read_packed): `words` instead of `seq`, the
+        ASCII bases never materialise -- what Engine.set_reads_packed takes."""
         import ctypes as C
         from . import _lib
         lib = _lib.load()
@@ -90,22 +95,33 @@ class NativeReads:
         paths = [os.fspath(p) for p in paths]
         arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
         err = C.create_string_buffer(512)
-        rc = lib.gvs_fastx_read(arr, len(paths), threads or min(len(paths), os.cpu_count() or 1), 1 if pin else 0,
-                                C.byref(self._fx), err, 512)
+        nthr = threads or min(len(paths), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+        if packed:
+            rc = lib.gvs_fastx_read_packed(arr, len(paths), nthr, 1 if pin else 0, int(block_bytes), C.byref(self._fx), err, 512)
+        else:
+            rc = lib.gvs_fastx_read(arr, len(paths), nthr, 1 if pin else 0, C.byref(self._fx), err, 512)
         if rc != 0:
             self._fx = None
             raise IOError(err.value.decode("utf-8", "replace"))
         fx = self._fx
         n, tot = int(fx.n_reads), int(fx.total_bases)
         as_np = lambda ptr, ctype, cnt: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(cnt,)) if cnt else np.zeros(0, ctype)
-        self.seq = as_np(fx.seq, C.c_uint8, tot)
+        self.seq = None if packed else as_np(fx.seq, C.c_uint8, tot)
+        self.words = as_np(fx.words, C.c_uint32, int(fx.n_words)) if packed else None
         self.read_off = as_np(fx.read_off, C.c_uint64, n + 1)
         self.chunk_first = as_np(fx.chunk_first, C.c_uint64, int(fx.n_files) + 1).copy()
-        name_off = as_np(fx.name_off, C.c_uint64, n + 1)
-        raw = C.string_at(fx.names, int(name_off[-1])) if n else b""
-        no = name_off.tolist()
-        self.names = [raw[no[i]:no[i + 1]].decode("latin-1") for i in range(n)]
+        self.name_off = as_np(fx.name_off, C.c_uint64, n + 1).copy()
+        self.name_blob = C.string_at(fx.names, int(self.name_off[-1])) if n else b""
+        self._names = None
         self.n_reads, self.total_bases, self.pinned = n, tot, bool(fx.pinned)
+
+    @property
+    def names(self):
+        """read names as Python strings (built on first use; the formatter works on name_blob / name_off)"""
+        if self._names is None:
+            raw, no = self.name_blob, self.name_off.tolist()
+            self._names = [raw[no[i]:no[i + 1]].decode("latin-1") for i in range(self.n_reads)]
+        return self._names
 
     def lengths(self) -> np.ndarray:
         return np.diff(self.read_off).astype(np.uint64)
@@ -122,7 +138,7 @@ class NativeReads:
 
     def close(self):
         if getattr(self, "_fx", None) is not None:
-            self.seq = self.read_off = self.words = None
+            self.seq = self.read_off = self.words = None  # (name_blob / name_off / chunk_first are copies)
             self._lib.gvs_fastx_free(self._fx)
             self._fx = None
 
@@ -204,3 +220,80 @@ def write_bed(path: str, rows):
     with open(path, "w") as f:
         for r in rows:
             f.write("\t".join(str(x) for x in r) + "\n")
+
+
+# ------------------------------------------------------------------------------------------------
+# native text egress (gvs_format_rows, csrc/format.cu)
+# ------------------------------------------------------------------------------------------------
+class NameTable:
+    """names back to back + offsets: what a GVS_COL_NAME column indexes"""
+
+    def __init__(self, names=None, blob: bytes = None, off: np.ndarray = None):
+        if blob is None:
+            enc = [n.encode("latin-1") for n in names]
+            blob = b"".join(enc)
+            off = np.zeros(len(enc) + 1, np.uint64)
+            if enc:
+                off[1:] = np.cumsum(np.fromiter((len(e) for e in enc), np.uint64, len(enc)))
+        self.blob = blob
+        self.off = np.ascontiguousarray(off, np.uint64)
+
+    @staticmethod
+    def concat(tables):
+        blob = b"".join(t.blob for t in tables)
+        offs, base = [np.zeros(1, np.uint64)], 0
+        for t in tables:
+            offs.append(t.off[1:] + np.uint64(base))
+            base += len(t.blob)
+        return NameTable(blob=blob, off=np.concatenate(offs))
+
+    def __len__(self):
+        return len(self.off) - 1
+
+    def as_bytes_array(self) -> np.ndarray:
+        """numpy 'S' array of the names (sorting, uniqueness)"""
+        no = self.off.tolist()
+        return np.array([self.blob[no[i]:no[i + 1]] for i in range(len(no) - 1)], dtype=object).astype("S") if len(no) > 1 else np.zeros(0, "S1")
+
+
+def format_rows(cols, n_rows: int = None, sel: np.ndarray = None, threads: int = 0) -> bytes:
+    """cols: list of ('u32'|'u64'|'i64', array) | ('name', index array, NameTable) | ('kmer', u64 array, k), each
+    optionally followed by a dict(prefix=..., sep=...); cells are tab-separated, the last one ends the line.
+    sel: row indices to write (in that order) instead of all rows.  -> the text as bytes"""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    kinds = {"u32": (0, np.uint32), "u64": (1, np.uint64), "i64": (2, np.int64), "name": (3, np.uint32), "kmer": (4, np.uint64)}
+    arr = (_lib.ColStruct * len(cols))()
+    keep = []
+    n = n_rows
+    for i, c in enumerate(cols):
+        opt = c[-1] if isinstance(c[-1], dict) else {}
+        kind, dt = kinds[c[0]]
+        data = np.ascontiguousarray(c[1], dtype=dt)
+        keep.append(data)
+        if n is None:
+            n = len(data)
+        arr[i].kind = kind
+        arr[i].data = data.ctypes.data
+        arr[i].k = int(c[2]) if c[0] == "kmer" else 0
+        if c[0] == "name":
+            nt = c[2]
+            keep.append(nt)
+            arr[i].names = C.cast(C.c_char_p(nt.blob), C.c_void_p)
+            arr[i].name_off = nt.off.ctypes.data
+        arr[i].prefix = opt.get("prefix", b"\0")
+        arr[i].sep = opt.get("sep", b"\n" if i == len(cols) - 1 else b"\t")
+    sel_a = None if sel is None else np.ascontiguousarray(sel, dtype=np.uint64)
+    n_sel = 0 if sel_a is None else len(sel_a)
+    sp = None if sel_a is None else C.c_void_p(sel_a.ctypes.data)
+    thr = threads or min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    need = lib.gvs_format_rows(arr, len(cols), n or 0, sp, n_sel, None, 0, thr)
+    if need < 0:
+        raise ValueError(f"gvs_format_rows: error {need}")
+    buf = bytearray(need)
+    if need:
+        got = lib.gvs_format_rows(arr, len(cols), n or 0, sp, n_sel, (C.c_char * need).from_buffer(buf), need, thr)
+        if got != need:
+            raise ValueError(f"gvs_format_rows: error {got}")
+    return bytes(buf) if need < (1 << 20) else buf

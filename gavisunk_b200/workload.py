@@ -58,6 +58,63 @@ def make_assembly(eng: Engine, contig_len_per_hap, snp_rate=1e-3, dup_frac=0.01,
                     contig_off=torch.from_numpy(off).to(device))
 
 
+@dataclass
+class ReadBatch:
+    """one batch of reads resident in HBM (a group of chunk files: `nchunks` per haplotype)"""
+    reads: torch.Tensor             # uint8 device (+64 pad)
+    read_off: torch.Tensor          # int64 device, n_reads+1
+    n_reads: int
+    total_bases: int
+    chunk_first: np.ndarray
+    chunk_hap: np.ndarray
+    seed: int = 0
+
+
+def new_batch(eng: Engine, wl: Workload, coverage: float, n50: float = 50000.0, sigma: float = 0.8, len_min=1000,
+              len_max=1000000, seed=2001, nchunks=10, device=None, contig_range=None) -> ReadBatch:
+    """a batch of reads drawn from wl's assembly (same arguments as add_reads); wl itself is not changed"""
+    import copy
+    tmp = copy.copy(wl)
+    tmp.meta = dict(wl.meta)
+    add_reads(eng, tmp, coverage, n50, sigma, len_min, len_max, seed, nchunks, device, contig_range)
+    return ReadBatch(tmp.reads, tmp.read_off, tmp.n_reads, tmp.total_bases, tmp.chunk_first, tmp.chunk_hap, seed)
+
+
+def bind_batch(eng: Engine, b: ReadBatch):
+    if getattr(b, "words", None) is not None:
+        eng.set_reads_packed_device(_dev_ptr(b.words), _dev_ptr(b.read_off), b.n_reads, b.chunk_first, b.chunk_hap)
+    else:
+        eng.set_reads_device(_dev_ptr(b.reads), _dev_ptr(b.read_off), b.n_reads, b.chunk_first, b.chunk_hap)
+
+
+def pack_batch_on_device(b: ReadBatch, drop_ascii: bool = True):
+    """the batch's bases as resident 2-bit words (kmer.encode's byte map: the layout the ingest emits and
+    gvs_reads_set_packed takes), made with torch in slices -- bench / test set-up only"""
+    dev = b.reads.device
+    lut = torch.zeros(256, dtype=torch.uint8, device=dev)
+    for ch, v in (("C", 1), ("G", 2), ("T", 3), ("U", 3)):
+        lut[ord(ch)] = v
+        lut[ord(ch.lower())] = v
+    lut[1], lut[2], lut[3] = 1, 2, 3
+    nw = (b.total_bases + 15) // 16
+    words = torch.zeros(nw + 16, dtype=torch.int32, device=dev)
+    sh = torch.tensor([30 - 2 * i for i in range(16)], dtype=torch.int64, device=dev)
+    step = 1 << 24  # words per slice
+    for w0 in range(0, nw, step):
+        w1 = min(nw, w0 + step)
+        seg = b.reads[16 * w0:min(16 * w1, b.total_bases)]
+        codes = lut[seg.long()].long()
+        if codes.numel() < 16 * (w1 - w0):
+            codes = torch.cat([codes, torch.zeros(16 * (w1 - w0) - codes.numel(), dtype=torch.int64, device=dev)])
+        v = (codes.view(-1, 16) << sh).sum(dim=1)
+        words[w0:w1] = (v & 0xFFFFFFFF).to(torch.int64).where(v < (1 << 31), v - (1 << 32)).to(torch.int32)
+    b.words = words
+    if drop_ascii:
+        b.reads = None
+    torch.cuda.synchronize(dev)
+    return b
+
+
 def add_reads(eng: Engine, wl: Workload, coverage: float, n50: float = 50000.0, sigma: float = 0.8, len_min=1000,
               len_max=1000000, seed=2001, nchunks=10, device=None, contig_range=None) -> Workload:
     """coverage = total read bases / haploid size of the sampled contigs, split evenly across the two
@@ -103,6 +160,8 @@ def add_reads(eng: Engine, wl: Workload, coverage: float, n50: float = 50000.0, 
             cf.append(hap * n_per_hap + (c * n_per_hap) // nchunks)
             ch.append(hap)
     cf.append(n_reads)
+    if reads.numel() > total + 64 + (64 << 20):  # the estimate left > 64 MiB of slack: a run keeps many batches resident
+        reads = reads[:total + 64].clone()
     wl.reads = reads[:total + 64] if reads.numel() > total + 64 else reads
     wl.read_off = read_off
     wl.n_reads = n_reads

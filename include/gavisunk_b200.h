@@ -143,6 +143,34 @@ void gvs_fastx_free(gvs_fastx* fx);
  * and a quarter of the bytes to move over PCIe.  gvs_fastx_pack does it for a parsed batch (page-locked). */
 int gvs_pack_2bit(const uint8_t* ascii, uint64_t n, uint32_t* words, int threads);
 int gvs_fastx_pack(gvs_fastx* fx, int threads, int pin);
+/* The ingest's native path: parse and 2-bit pack fused.  Same record semantics and chunk layout as gvs_fastx_read,
+ * but the ASCII bases never land in memory as a batch: files are streamed in blocks of `block_bytes` (0 = 1 MiB;
+ * plain files out of the page cache through mmap, gzip files through an inflate window of that size), packed with
+ * kmer.encode's byte map as they are parsed and laid out as ONE (page-locked) array of 16-base words --
+ * out->words / n_words, ready for gvs_reads_set_packed; out->seq stays NULL.  Free with gvs_fastx_free. */
+int gvs_fastx_read_packed(const char* const* paths, uint32_t n_files, int threads, int pin, uint64_t block_bytes,
+                          gvs_fastx* out, char* err, uint64_t err_len);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Text egress at the reference's file boundary: rows of .sunkpos (kmerpos_annot3.nim:93), */
+/* .rlen (rlen.nim:14), kmer.loc / jellyfish.db / jellyfish.fa (defineSUNKs.smk:59-60,126), inter_outs / BED files  */
+/* (process-by-contig_lowmem_AR.py:203-207,260) formatted from column arrays on host threads.  Host memory only.  */
+/* ------------------------------------------------------------------------------------------ */
+enum { GVS_COL_U32 = 0, GVS_COL_U64 = 1, GVS_COL_I64 = 2, GVS_COL_NAME = 3, GVS_COL_KMER = 4 };
+typedef struct gvs_col {
+  int32_t kind;              /* GVS_COL_*                                                                  */
+  int32_t k;                 /* GVS_COL_KMER: letters per k-mer (2-bit big-endian value, A C G T)         */
+  const void* data;          /* per row: the u32 / u64 / i64 value, the u32 index into the name table, the u64 k-mer */
+  const char* names;         /* GVS_COL_NAME: names back to back ...                                       */
+  const uint64_t* name_off;  /* ... and their offsets (entries + 1)                                        */
+  char prefix;               /* written before the cell when non-zero ('>' of jellyfish.fa)                */
+  char sep;                  /* written after the cell: '\t', or '\n' for the last column                  */
+} gvs_col;
+/* Formats rows [0, n_rows) -- or, with sel != NULL, the n_sel rows sel[i] in that order (one contig's rows of a
+ * batch) -- as n_cols cells each.  out == NULL: returns the number of bytes needed; otherwise writes them (no
+ * terminator) and returns the count, GVS_E_OVERFLOW when cap is too small. */
+int64_t gvs_format_rows(const gvs_col* cols, uint32_t n_cols, uint64_t n_rows, const uint64_t* sel, uint64_t n_sel, char* out,
+                        uint64_t cap, int threads);
 
 /* ------------------------------------------------------------------------------------------ */
 /* A batch = the reads of one or more chunk files (temp/{sample}/reads/{hap}_{i-of-N}.fq.gz,
@@ -263,6 +291,25 @@ int gvs_bad_set(gvs_ctx* ctx, const uint32_t* contig, const uint32_t* group, uin
  * count of gvs_group_hist (badsunks_AR.py:24-27 `counts`).  Host buffers of gvs_groups_count entries. */
 int gvs_groups_count(gvs_ctx* ctx, uint64_t* n_groups);
 int gvs_groups_get(gvs_ctx* ctx, uint32_t* contig, uint32_t* group, int32_t* hist);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Several batches of ONE run.  The reference scatters a sample's reads into chunk files, matches and
+ * filters per chunk and gathers per haplotype before anything global happens (workflow/Snakefile:23-24
+ * scattergather, workflow/rules/tagONT.smk:112-131 combine_ont): badsunks_AR.py:20-27 counts the rows of ALL
+ * chunks, process-by-contig_lowmem_AR.py sees every read of a contig.  A run whose reads do not fit one batch
+ * has two phases:
+ *   gvs_batches_begin
+ *   per batch:  gvs_reads_set* -> gvs_match -> gvs_diag_filter -> gvs_group_hist(accumulate = 1) -> gvs_batch_stash
+ *   (several GPUs: ONE all-reduce of the histogram)  gvs_hist_mode -> gvs_bad_groups
+ *   gvs_batches_bind -> gvs_validate -> gvs_components_local
+ *   (several GPUs: ONE all-gather of the forests, gvs_components_merge)  gvs_intervals -> gvs_gaps
+ * gvs_batch_stash keeps the batch's kept rows (24 B each) and read lengths resident and returns the index its
+ * first read has in the run (*read_base); gvs_batches_bind makes the stashed rows of all batches the input of
+ * gvs_validate (as if one gvs_diag_filter had kept them; gvs_rows_get(1) / gvs_pairs_get then report run-wide
+ * read indices) and ends the run's phase 1. */
+int gvs_batches_begin(gvs_ctx* ctx);
+int gvs_batch_stash(gvs_ctx* ctx, uint64_t* read_base);
+int gvs_batches_bind(gvs_ctx* ctx, uint64_t* n_rows, uint64_t* n_reads);
 
 /* process-by-contig_lowmem_AR.py:50-207 per-read part: validated (group, read) pairs = rows of
  * inter_outs/{contig}_{hap}.tsv.  min_read_len is the reference's hard-coded 10000 (:106). */

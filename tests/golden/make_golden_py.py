@@ -93,7 +93,13 @@ def elf_case(seed, k, n_contigs, L, n_reads, mean_len, tandem=0.0):
 
 def pipeline_case(seed, k, n_contigs, L, n_reads, mean_len, tandem=0.0):
     # match + diag through the reference executables, then the Python scripts
-    base = elf_case(seed, k, n_contigs, L, n_reads, mean_len, tandem)
+    return python_stages(elf_case(seed, k, n_contigs, L, n_reads, mean_len, tandem), k)
+
+
+def python_stages(base, k):
+    """base: loc, fai1, fai2 (texts) and chunks [{hap, diag2, rlen}] in scatter order -> the files the reference's
+    Python scripts write for them (combine_ont's cat, badsunks_AR.py, split_locs.py, process-by-contig_lowmem_AR.py per
+    contig, get_gaps.py, covprob.py)"""
     case = dict(k=k, loc=base["loc"], fai1=base["fai1"], fai2=base["fai2"], hap={})
     with tempfile.TemporaryDirectory() as d:
         for sub in ("sunkpos", "breaks", "inter_outs", "bed_files", "final_out"):
