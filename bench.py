@@ -64,6 +64,8 @@ def parse_args():
                          "ingest emits (gvs_fastx_read_packed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-mbp", type=float, default=None, help="read Mbp per CPU process of the baseline sample")
+    ap.add_argument("--ref-asm-mbp", type=float, default=40.0, help="--impl reference: haploid size of the sample assembly (numpy + oracle set-up)")
+    ap.add_argument("--e2e-files-gbp", type=float, default=None, help="read Gbp of the files -> files run (default: 4 at N = 1, skipped at N > 1; 0 = skip)")
     return ap.parse_args()
 
 
@@ -371,6 +373,16 @@ def main_b200(args):
     e2e = None
     if args.e2e_steps > 0:
         e2e = measure_e2e(args, eng, wl, coll, dev, world, rank, numa, barrier, allmax, allsum)
+        # files -> files: by default at N = 1 only (a rank that failed in there would leave its peers waiting in a collective)
+        if (args.e2e_files_gbp is None and world == 1) or (args.e2e_files_gbp or 0) > 0:
+            try:
+                ef = measure_e2e_files(args, eng, wl, coll, dev, world, rank, barrier, allmax, allsum)
+            except Exception as ex:  # a secondary figure must never take the bench down
+                import traceback
+                ef = dict(error=repr(ex)[:300], where=traceback.format_exc()[-400:])
+            if e2e is not None:
+                e2e["from_files"] = ef
+            res, iv, gaps = run_step(eng, wl, binds, coll)  # back to the resident state of the run
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -509,6 +521,121 @@ def measure_e2e(args, eng, wl, coll, dev, world, rank, numa, barrier, allmax, al
     return e2e
 
 
+def measure_e2e_files(args, eng, wl, coll, dev, world, rank, barrier, allmax, allsum):
+    """The reference's REAL boundary: chunk FASTQ files in, result files out.  The reads of (a part of) this rank's
+    first batch are written as the 2 x 10 chunk files split_ONT would leave (4-line FASTQ, quality '#';
+    page-cache warm: they sit in tmpfs) -- untimed set-up.  Timed: gavisunk_b200.cli.run_reads (parse + 2-bit pack
+    on the host threads, H2D of the words, every kernel of the path, the two exchanges) + cli.write_outputs
+    (sunkpos/, breaks/*.sunkpos, inter_outs/, bed_files/, final_out/ formatted natively and written to disk; the
+    exports of the database itself are left out, they belong to the database build).  A second pass times the
+    same files gzip-compressed (.fq.gz, what the rule really writes) on a tenth of the reads: zlib inflate bound."""
+    import gzip
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from gavisunk_b200 import cli
+    if not wl.batches:
+        return dict(skipped="this rank owns no batch")
+    b = wl.batches[0]
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    base_dir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    free = shutil.disk_usage(base_dir).free
+    want_gbp = args.e2e_files_gbp if args.e2e_files_gbp is not None else 4.0
+    cap_gbp = free * 0.45 / max(local_world, 1) / 2.1 / 1e9  # FASTQ = 2 bytes per base (+ names)
+    gbp = min(want_gbp, cap_gbp, b.total_bases / 1e9)
+    if gbp < 0.05:
+        return dict(skipped=f"no room for the chunk files under {base_dir} ({free / 1e9:.0f} GB free)")
+    root = tempfile.mkdtemp(prefix=f"gvs_e2e_r{rank}_", dir=base_dir)
+    try:
+        off = b.read_off.cpu().numpy().astype(np.int64)
+        cf = b.chunk_first.astype(np.int64)
+        frac = gbp * 1e9 / b.total_bases
+        files, file_hap, n_sel_reads, n_sel_bases, gz_files = [], [], 0, 0, []
+
+        def write_chunk(c):
+            r0, r1 = int(cf[c]), int(cf[c + 1])
+            r1 = r0 + max(1, int(round((r1 - r0) * frac)))  # the first part of every chunk
+            seq = b.reads[int(off[r0]):int(off[r1])].cpu().numpy()
+            lens = (off[r0 + 1:r1 + 1] - off[r0:r1]).astype(np.int64)
+            names = [b"@r%09d\n" % i for i in range(r0, r1)]
+            nl = np.fromiter((len(x) for x in names), np.int64, len(names))
+            rec = nl + 2 * lens + 4  # name line, seq, '\n+\n', quality, '\n'
+            out = np.full(int(rec.sum()), ord("#"), np.uint8)
+            o = np.concatenate([[0], np.cumsum(rec)[:-1]])
+            so = off[r0:r1] - off[r0]
+            for i in range(r1 - r0):
+                p0 = int(o[i])
+                out[p0:p0 + int(nl[i])] = np.frombuffer(names[i], np.uint8)
+                p1 = p0 + int(nl[i])
+                L = int(lens[i])
+                out[p1:p1 + L] = seq[int(so[i]):int(so[i]) + L]
+                out[p1 + L:p1 + L + 3] = (10, 43, 10)
+                out[p1 + 2 * L + 3] = 10
+            hap = int(b.chunk_hap[c])
+            idx = c - (0 if hap == 0 else int(np.sum(b.chunk_hap == 0)))
+            fp = os.path.join(root, f"hap{hap + 1}_{idx + 1}-of-10.fq")
+            out.tofile(fp)
+            gzp = None
+            if idx == 0:  # one chunk file per haplotype also as .fq.gz
+                gzp = fp + ".gz"
+                with gzip.open(gzp, "wb", compresslevel=1) as f:
+                    f.write(out.data)
+            return fp, hap, r1 - r0, int(lens.sum()), gzp
+        with ThreadPoolExecutor(max_workers=min(8, len(cf) - 1)) as ex:
+            for fp, hap, nr, nb, gzp in ex.map(write_chunk, range(len(cf) - 1)):
+                files.append(fp)
+                file_hap.append(hap)
+                n_sel_reads += nr
+                n_sel_bases += nb
+                if gzp:
+                    gz_files.append((gzp, hap, nb))
+        file_bytes = sum(os.path.getsize(f) for f in files)
+        clen = wl.contig_len.astype(np.uint32)
+
+        def one_pass(fl, fh, outdir, batch_gbp):
+            t0 = time.perf_counter()
+            results = cli.run_reads([eng], wl.contig_hap, fl, fh, batch_gbp=batch_gbp, coll=coll if world > 1 else None)
+            gaps, nodata = eng.gaps(clen)
+            t1 = time.perf_counter()
+            cli.write_outputs(args.k, eng, results, clen, wl.contig_hap, wl.contig_names, results[0]["iv"], gaps, nodata, outdir, db_files=False)
+            t2 = time.perf_counter()
+            return t2 - t0, t1 - t0, t2 - t1, results
+        outdir = os.path.join(root, "results")
+        one_pass(files, file_hap, outdir, 12.0)  # warm-up: buffers, page-locked pools
+        barrier()
+        times, split = [], [0.0, 0.0]
+        for _ in range(max(1, args.e2e_steps)):
+            shutil.rmtree(outdir, ignore_errors=True)
+            barrier()
+            t, t_run, t_write, results = one_pass(files, file_hap, outdir, 12.0)
+            times.append(t)
+            split[0] += t_run / max(1, args.e2e_steps)
+            split[1] += t_write / max(1, args.e2e_steps)
+        t_files = allmax(float(np.mean(times)))
+        total = allsum(n_sel_bases)
+        out_bytes = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(outdir) for f in fs)
+        kept_rows = int(len(results[0]["kept"]["read"]))
+        n_lines = sum(1 for _ in open(os.path.join(outdir, "sunkpos", "hap1.sunkpos"), "rb")) + \
+            sum(1 for _ in open(os.path.join(outdir, "sunkpos", "hap2.sunkpos"), "rb"))
+        assert n_lines == kept_rows, "every kept row must be a line of {hap}.sunkpos"
+        res = dict(value=total / t_files / 1e9, unit=UNIT, read_gbp=total / 1e9, s_per_pass=t_files, input_file_bytes_rank0=int(file_bytes),
+                   output_file_bytes_rank0=int(out_bytes), host_split_s=dict(ingest_and_gpu=round(split[0], 3), format_and_write=round(split[1], 3)),
+                   files=f"{len(files)} chunk FASTQ files per rank under {base_dir} (page-cache warm), one batch, ingest threads = "
+                         f"{max(1, (len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()))}",
+                   kept_rows_rank0=kept_rows, note="files -> files: parse + 2-bit pack (gvs_fastx_read_packed), H2D, kernels, D2H, native formatting "
+                                                   "(gvs_format_rows) and writes inside the timed region; database exports excluded")
+        if gz_files:
+            gl, gh = [g[0] for g in gz_files], [g[1] for g in gz_files]
+            gb = sum(g[2] for g in gz_files)
+            one_pass(gl, gh, os.path.join(root, "results_gz"), 12.0)
+            barrier()
+            tg, _, _, _ = one_pass(gl, gh, os.path.join(root, "results_gz"), 12.0)
+            res["fq_gz"] = dict(value=allsum(gb) / allmax(tg) / 1e9, unit=UNIT, read_gbp=allsum(gb) / 1e9, files=f"{len(gl)} .fq.gz chunk files per rank (gzip level 1)",
+                                note="same path from gzip-compressed chunk files: bound by zlib inflate, one host thread per file")
+        return res
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 # --------------------------------------------------------------------------------------------
 # CPU reference (oracle/_ref executables + oracle port of the Python stages) on a bounded sample
 # --------------------------------------------------------------------------------------------
@@ -621,15 +748,152 @@ def _cleanup_samples():
     _SAMPLE_CACHE.clear()
 
 
-def cpu_reference_sample(args, wl, eng, per_proc_mbp=12.0):
-    """Times the reference pipeline on the host cores for a sample of the same workload:
-    one kmerpos_annot3 -> diag_filter_v3 -> diag_filter_step2 process chain per chunk, all cores
-    busy (snakemake --cores N), then the oracle port of badsunks / process-by-contig / get_gaps.
-    The sample's input files (db, .loc, .fai, read chunks) are written once per process and reused by
-    later steps; only the pipeline itself is timed."""
+def _prepare_numpy_sample(args, per_proc_mbp, cores, asm_mbp=40.0):
+    """The reference arm's own inputs, made WITHOUT libgavisunk_b200.so: numpy generator of the same recipe (SURVEY
+    8d: i.i.d. haplotype 1 with 1 % segmental duplications in 10-100 kb blocks, haplotype 2 = SNPs at 1e-3, reads
+    log-normal N50 ~100 kb, 3 % substitutions + 2 % deletions + 1 % insertions, both strands), the oracle's
+    restatement of defineSUNKs.smk for jellyfish.db / kmer.loc (jellyfish, mrsfast, bedtools are not installed)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import gavisunk_oracle as O
+    import j1_sim as S
+    from concurrent.futures import ThreadPoolExecutor
+    workdir = tempfile.mkdtemp(prefix="gvs_ref_")
+    k = args.k
+    L = int(asm_mbp * 1e6)
+    rng = np.random.default_rng(1001)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    h1 = alpha[rng.integers(0, 4, L)]
+    done = 0
+    while done < L // 100:
+        ln = int(rng.integers(10000, 100000))
+        a, b = int(rng.integers(0, L - ln)), int(rng.integers(0, L - ln))
+        h1[b:b + ln] = h1[a:a + ln]
+        done += ln
+    h2 = h1.copy()
+    snp = rng.random(L) < 1e-3
+    h2[snp] = alpha[(O.BASE_LUT[h1[snp]] + rng.integers(1, 4, int(snp.sum()))) % 4]
+    n_ctg = 8  # contigs per haplotype: process_by_contig is one job per contig in the reference (tagONT.smk:170-191)
+    cuts = [L * i // n_ctg for i in range(n_ctg + 1)]
+    haps = [[(f"synH{h + 1}_chr{i + 1}", (h1, h2)[h][cuts[i]:cuts[i + 1]].tobytes()) for i in range(n_ctg)] for h in range(2)]
+    names = [n for h in haps for n, _ in h]
+    db = O.build_sunk_db(haps[0] + haps[1], k)
+    kms = np.asarray(db["kmer"], np.uint64)
+    shifts = (2 * np.arange(k - 1, -1, -1)).astype(np.uint64)
+    letters = alpha[((kms[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)].view(f"S{k}").ravel().astype(str)
+    import pandas as pd
+    dbp, locp = os.path.join(workdir, "jellyfish.db"), os.path.join(workdir, "kmer.loc")
+    pd.DataFrame({"k": letters}).to_csv(dbp, header=False, index=False)
+    pd.DataFrame({"c": np.asarray(names)[db["contig"]], "s": db["start"], "k": letters, "g": db["group"]}).to_csv(
+        locp, sep="\t", header=False, index=False)
+    fais = []
+    for hap in range(2):
+        fp = os.path.join(workdir, f"hap{hap + 1}.fai")
+        open(fp, "w").write("".join(f"{n}\t{len(sq)}\t0\t60\t61\n" for n, sq in haps[hap]))
+        fais.append(fp)
+    n50, sigma = 100000.0, 0.8
+    mu = math.log(n50) - sigma * sigma
+    per_hap_procs = max(1, cores // 2)
+    want = int(per_proc_mbp * 1e6)
+    jobs, rlen, sample_bases, sample_reads = [], {}, 0, 0
+
+    def make_chunk(hc):
+        hap, c = hc
+        r = np.random.default_rng(7000 + 100 * hap + c)
+        lens, tot = [], 0
+        while tot < want:
+            ln = int(min(max(r.lognormal(mu, sigma), 1000), 1000000))  # (clipped to its contig by the simulator)
+            lens.append(ln)
+            tot += ln
+        reads = S.simulate(haps[hap], lens, 9000 + 100 * hap + c, f"h{hap + 1}c{c}r")
+        fp = os.path.join(workdir, f"hap{hap + 1}_{c}.fa")
+        with open(fp, "wb") as f:
+            for n, sq in reads:
+                f.write(b">" + n.encode() + b"\n" + sq + b"\n")
+        return dict(workdir=workdir, tag=f"hap{hap + 1}_{c}", reads=fp, db=dbp, loc=locp, fai=fais[hap]), {n: len(sq) for n, sq in reads}
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for job, rl in ex.map(make_chunk, [(h, c) for h in range(2) for c in range(per_hap_procs)]):
+            jobs.append(job)
+            rlen.update(rl)
+            sample_bases += sum(rl.values())
+            sample_reads += len(rl)
+    note = (f"inputs made without libgavisunk_b200.so: numpy generator of the workload's recipe on a {asm_mbp:.0f} Mbp x2 diploid sample "
+            f"assembly ({len(kms)} SUNKs; jellyfish.db / kmer.loc from the oracle's restatement of defineSUNKs.smk), ")
+    return dict(workdir=workdir, jobs=jobs, dbp=dbp, locp=locp, rlen=rlen, sample_note=note, sample_bases=sample_bases,
+                sample_reads=sample_reads, hap_contigs=[{n for n, _ in haps[0]}, {n for n, _ in haps[1]}],
+                fai=[[(n, len(sq)) for n, sq in haps[h]] for h in range(2)])
+
+
+def _port_contig(task):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gavisunk_oracle as O
+    rr, rlen, bad, ctg = task
+    inter, bed = O.process_by_contig(rr, rlen, bad, ctg)
+    return ctg, bed
+
+
+def run_reference_pipeline(prep, cores):
+    """one timed pass of the reference pipeline over a prepared sample: kmerpos_annot3 -> diag_filter_v3 ->
+    diag_filter_step2 (the reference's ELFs), one process chain per chunk file with all cores busy (snakemake --cores
+    N), then the CPU port of badsunks_AR.py / process-by-contig_lowmem_AR.py / get_gaps.py on ALL chunks."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_runner as RR
     import gavisunk_oracle as O
+    from gavisunk_b200 import io as gio
+    workdir, jobs, dbp, locp, rlen = (prep[k2] for k2 in ("workdir", "jobs", "dbp", "locp", "rlen"))
+    for fn in os.listdir(workdir):  # outputs of an earlier step
+        if fn.endswith(".sunkpos"):
+            os.remove(os.path.join(workdir, fn))
+    t_load = RR.table_load_seconds(workdir, dbp, locp)
+    res, wall_elf = RR.run_chunks_parallel(jobs, cores)
+    t0 = time.perf_counter()
+    rows_h = [[], []]
+    for j, r in zip(jobs, res):
+        rows_h[0 if j["tag"].startswith("hap1") else 1] += gio.read_sunkpos(r["diag2"])
+    hapc = prep["hap_contigs"]
+    bad = O.bad_sunks(rows_h[0], hapc[0], rows_h[1], hapc[1])
+    beds, n_iv = {}, 0
+    tasks = []
+    for hap in range(2):
+        byc = {}
+        for row in rows_h[hap]:
+            byc.setdefault(row[2], []).append(row)
+        for ctg, rr in byc.items():
+            names_c = {r[0] for r in rr}
+            tasks.append((rr, {n: rlen[n] for n in names_c if n in rlen}, bad, ctg))
+    # one process_by_contig job per contig, `cores` at once, as snakemake runs the rule (tagONT.smk:170-191)
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(cores, max(1, len(tasks)))) as pool:
+        for ctg, bed in pool.map(_port_contig, tasks):
+            if bed is not None:
+                beds[ctg] = [(s, e) for _, s, e in bed]
+                n_iv += len(bed)
+    for hap in range(2):
+        O.get_gaps(prep["fai"][hap], beds)
+    t_py = time.perf_counter() - t0
+    wall = wall_elf + t_py
+    sample_bases = prep["sample_bases"]
+    # every reference process first parses jellyfish.db + kmer.loc from text (kmerpos_annot3.nim:20-69); for a bounded sample that
+    # load would dominate (at the reference's real chunk size of ~9 Gbp it is < 30 %), so `value` leaves it out and it is
+    # reported beside it
+    wall_noload = max(wall - t_load, 1e-9)
+    return dict(value=sample_bases / wall_noload / 1e9, unit=UNIT, cores=cores, kind="reference",
+                sample=(prep["sample_note"] + f"{prep['sample_reads']} reads / {sample_bases / 1e6:.0f} Mbp of the same workload in {len(jobs)} "
+                        f"chunk files; reference ELFs kmerpos_annot3+diag_filter_v3+diag_filter_step2 one process per chunk, {cores} at "
+                        f"once (wall {wall_elf:.1f} s, of which {t_load:.1f} s is every process loading the SUNK table from text: left out of "
+                        f"`value`, see value_incl_table_load), then the CPU port of badsunks / process-by-contig (one process per contig, {cores} at once) / get_gaps on "
+                        f"all chunks ({t_py:.1f} s; the reference's Python needs graph_tool/pyranges)"),
+                wall_s=wall, elf_wall_s=wall_elf, table_load_s=t_load, python_port_s=t_py,
+                value_incl_table_load=sample_bases / wall / 1e9,
+                scan_only_value=sample_bases / max(wall_elf - t_load, 1e-9) / 1e9, sample_intervals=n_iv)
+
+
+def cpu_reference_sample(args, wl, eng, per_proc_mbp=12.0):
+    """cpu_baseline leg of the b200 arm (rank 0, N = 1): the reference pipeline on a sample cut from THIS run's workload
+    (database exported from the engine, reads from the same generator).  The sample's input files are written once and
+    reused by later calls; only the pipeline itself is timed."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_runner as RR
     cores = os.cpu_count() or 1
     if not RR.available():
         return dict(error="oracle/_ref executables missing", cores=cores)
@@ -638,90 +902,51 @@ def cpu_reference_sample(args, wl, eng, per_proc_mbp=12.0):
         import atexit
         if not _SAMPLE_CACHE:
             atexit.register(_cleanup_samples)
-        _SAMPLE_CACHE[key] = _prepare_reference_sample(args, wl, eng, per_proc_mbp, cores)
-    prep = _SAMPLE_CACHE[key]
-    workdir, jobs, dbp, locp, rlen, sample_note = (prep[k2] for k2 in ("workdir", "jobs", "dbp", "locp", "rlen", "sample_note"))
-    sample_bases, sample_reads, wl = prep["sample_bases"], prep["sample_reads"], prep["wl"]
-    for fn in os.listdir(workdir):  # outputs of an earlier step
-        if fn.endswith(".sunkpos"):
-            os.remove(os.path.join(workdir, fn))
-    if True:
-        t_load = RR.table_load_seconds(workdir, dbp, locp)
-        res, wall_elf = RR.run_chunks_parallel(jobs, cores)
-        # ---- Python stages (port): bad SUNKs, per-contig validation, gaps ----
-        from gavisunk_b200 import io as gio
-        # the pure-Python port is slow: it runs on every `py_every`-th chunk file and its time is
-        # scaled back up (stated in `sample`)
-        py_every = max(1, len(jobs) // 4)
-        t0 = time.perf_counter()
-        rows_h = [[], []]
-        for ji, (j, r) in enumerate(zip(jobs, res)):
-            if ji % py_every:
-                continue
-            hap = 0 if j["tag"].startswith("hap1") else 1
-            rows_h[hap] += gio.read_sunkpos(r["diag2"])
-        nc = len(wl.contig_names) // 2
-        hapc = [set(wl.contig_names[:nc]), set(wl.contig_names[nc:])]
-        bad = O.bad_sunks(rows_h[0], hapc[0], rows_h[1], hapc[1])
-        beds, n_iv = {}, 0
-        for hap in range(2):
-            byc = {}
-            for row in rows_h[hap]:
-                byc.setdefault(row[2], []).append(row)
-            for ctg, rr in byc.items():
-                inter, bed = O.process_by_contig(rr, rlen, bad, ctg)
-                if bed is not None:
-                    beds[ctg] = [(s, e) for _, s, e in bed]
-                    n_iv += len(bed)
-        for hap in range(2):
-            fai = [(wl.contig_names[c], int(wl.contig_len[c])) for c in range(hap * nc, (hap + 1) * nc)]
-            O.get_gaps(fai, beds)
-        n_py = len([1 for ji in range(len(jobs)) if ji % py_every == 0])
-        t_py = (time.perf_counter() - t0) * len(jobs) / max(n_py, 1)
-        wall = wall_elf + t_py
-        return dict(value=sample_bases / wall / 1e9, unit=UNIT, cores=cores, kind="reference",
-                    sample=(sample_note + f"{sample_reads} reads / {sample_bases / 1e6:.0f} Mbp of the same workload in {len(jobs)} chunk files; "
-                            f"reference ELFs kmerpos_annot3+diag_filter_v3+diag_filter_step2 one process per chunk, {cores} at once "
-                            f"(wall {wall_elf:.1f} s incl. {t_load:.1f} s table load per process), then the single-process CPU port of "
-                            f"badsunks/process-by-contig/get_gaps (the reference's Python needs graph_tool/pyranges; timed on {n_py} of the "
-                            f"{len(jobs)} chunks and scaled: {t_py:.1f} s)"),
-                    wall_s=wall, elf_wall_s=wall_elf, table_load_s=t_load, python_port_s=t_py,
-                    scan_only_value=sample_bases / max(wall_elf - t_load, 1e-9) / 1e9, sample_intervals=n_iv)
+        prep = _prepare_reference_sample(args, wl, eng, per_proc_mbp, cores)
+        swl = prep["wl"]
+        nc = len(swl.contig_names) // 2
+        prep["hap_contigs"] = [set(swl.contig_names[:nc]), set(swl.contig_names[nc:])]
+        prep["fai"] = [[(swl.contig_names[c], int(swl.contig_len[c])) for c in range(h * nc, (h + 1) * nc)] for h in range(2)]
+        _SAMPLE_CACHE[key] = prep
+    return run_reference_pipeline(_SAMPLE_CACHE[key], cores)
 
 
 def main_reference(args):
-    """--impl reference: only rank 0 works; the workload (assembly, SUNK db, reads) is generated with
-    the same generator as the b200 arm (setup, untimed); every timed step runs the reference
-    executables + CPU port on the host cores."""
+    """--impl reference: only rank 0 works, on the host cores; no GPU and no libgavisunk_b200.so is involved: the
+    sample's inputs come from numpy + the oracle (_prepare_numpy_sample, untimed set-up), every timed step runs
+    the reference executables + the CPU port of its Python stages."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from gavisunk_b200.engine import Engine
-    torch.cuda.set_device(0)
-    eng = Engine(args.k, device=0)
-    wl = build_workload(args, eng, 0, 1, with_reads=False)  # assembly + SUNK database; the sample's reads are drawn below
-    # every step = the reference pipeline on a bounded sample (~8 s on 16 cores, most of it each process loading
-    # the SUNK table from text); K steps are run unless that would take more than ~2.5 minutes in total
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_runner as RR
+    cores = os.cpu_count() or 1
+    if not RR.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref executables missing"}))
+        return
+    import atexit
+    atexit.register(_cleanup_samples)
+    t_setup = time.perf_counter()
+    prep = _prepare_numpy_sample(args, args.cpu_sample_mbp or 24.0, cores, asm_mbp=args.ref_asm_mbp)
+    _SAMPLE_CACHE["ref"] = prep
+    t_setup = time.perf_counter() - t_setup
     vals, last = [], None
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_sample(args, wl, eng, per_proc_mbp=args.cpu_sample_mbp or 4.0)
     t_begin = time.perf_counter()
-    for _ in range(max(1, args.steps)):
-        last = cpu_reference_sample(args, wl, eng, per_proc_mbp=args.cpu_sample_mbp or 12.0)
-        if "value" not in last:
-            print(json.dumps({"impl": "reference", "unavailable": last.get("error", "reference run failed")}))
-            return
-        vals.append(last["value"])
-        if time.perf_counter() - t_begin > 150.0:
+    for i in range(min(args.warmup, 1) + max(1, args.steps)):
+        last = run_reference_pipeline(prep, cores)
+        if i >= min(args.warmup, 1):
+            vals.append(last["value"])
+        if time.perf_counter() - t_begin > 150.0 and vals:  # K steps unless that takes more than ~2.5 minutes in total
             break
     steps = len(vals)
     v = float(np.mean(vals))
+    spec = WORKLOADS[args.workload]
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps,
-           "warmup": min(args.warmup, 1), "ms_per_step": last["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": wl.meta["desc"], "k": args.k, "asm_haploid_mbp": wl.meta["asm_mbp"]},
+           "warmup": min(args.warmup, 1), "ms_per_step": (last["wall_s"] - last["table_load_s"]) * 1e3, "higher_is_better": True,
+           "scaling": args.scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": spec["desc"], "k": args.k, "asm_haploid_mbp": spec["mbp"], "setup_s": round(t_setup, 1),
+                      "native_so_loaded": "gavisunk_b200" in sys.modules and getattr(sys.modules.get("gavisunk_b200._lib"), "_lib", None) is not None},
            "cpu_baseline": dict(last, value=v),
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

@@ -567,53 +567,37 @@ class ThreadExchange:
         return _R
 
 
-def run_fused(k: int, hap_asm: Sequence[str], hap_reads: Sequence[Sequence[str]], outdir: str, device: int = 0,
-              devices: Sequence[int] = None, batch_files: int = 0, batch_gbp: float = 12.0, detailed: bool = False,
-              threads: int = 0, mrsfast_palindromes: bool = False):
-    """hap_asm: two FASTA paths; hap_reads: two lists of chunk files in scatter order.  The chunk files are
-    grouped into batches (plan_batches); every GPU of `devices` owns a contiguous block of the batches and runs
-    Engine.run_batches on it (one host thread per GPU, two exchanges per run).  Reads are parsed and 2-bit packed
-    in one pass (gio.NativeReads(packed=True)) while the previous batch is on the GPU.  Returns the first
-    device's engine."""
+def run_reads(engines, contig_hap, files: Sequence[str], file_hap: Sequence[int], batch_files: int = 0, batch_gbp: float = 12.0,
+              detailed: bool = False, threads: int = 0, min_read_len: int = 10000, coll=None):
+    """The read side of the fused rule on engines whose SUNK database is loaded: the chunk files (scatter order, with
+    the haplotype each belongs to) are grouped into batches (plan_batches); engine i owns a contiguous block of the
+    batches and runs Engine.run_batches on it (one host thread per GPU, two exchanges per run).  Reads are parsed
+    and 2-bit packed in one pass (gio.NativeReads(packed=True)) while the previous batch is on the GPU.
+    coll: exchange object of a multi-PROCESS run (gavisunk_b200.parallel.EngineExchange) when `engines` is this rank's
+    single engine.  -> one result dict per engine (read names / lengths / chunk tables, kept rows, validated pairs,
+    intervals)."""
     import threading
     from concurrent.futures import ThreadPoolExecutor
     from .parallel import shard_chunks
-    devices = list(devices) if devices else [device]
-    contigs, contig_hap, fai = [], [], [[], []]
-    for hap in range(2):
-        for n, s in gio.read_fastx(hap_asm[hap]):
-            contigs.append((n, s))
-            contig_hap.append(hap)
-            fai[hap].append((n, len(s)))
-    files = list(hap_reads[0]) + list(hap_reads[1])
-    file_hap = [0] * len(hap_reads[0]) + [1] * len(hap_reads[1])
     for p in files:
         if not os.path.exists(p):
             raise FileNotFoundError(p)
-    batches = plan_batches(files, len(devices), batch_files, batch_gbp)
-    shards = shard_chunks(len(batches), len(devices))
+    n_dev = len(engines)
+    batches = plan_batches(files, n_dev, batch_files, batch_gbp)
+    shards = shard_chunks(len(batches), n_dev)
     n_cpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    ingest_threads = threads or max(1, n_cpu // len(devices))
-    engines = [None] * len(devices)
-    results = [None] * len(devices)
+    ingest_threads = threads or max(1, n_cpu // n_dev)
+    results = [None] * n_dev
     errors = []
-    xch = None
-    ready = threading.Barrier(len(devices))
+    xch = ThreadExchange(engines)
 
     def worker(di):
-        nonlocal xch
         try:
-            eng = Engine(k, device=devices[di])
-            engines[di] = eng
-            eng.build_db(contigs)
-            ready.wait()
-            if di == 0:
-                xch = ThreadExchange(engines)
-            ready.wait()
-            coll = xch.for_rank(di)
+            eng = engines[di]
+            cx = coll if (coll is not None and n_dev == 1) else xch.for_rank(di)
             mine = batches[shards[di][0]:shards[di][1]]
             load = lambda fl: gio.NativeReads([files[i] for i in fl], threads=ingest_threads, packed=True)
-            info = dict(names=[], lens=[], chunk_first=[], chunk_hap=[], rows0=[], n_reads=0)
+            info = dict(names=[], lens=[], chunk_first=[], chunk_hap=[], rows0=[], n_reads=0, n_bases=0)
             with ThreadPoolExecutor(max_workers=1) as pre:
                 fut = pre.submit(load, mine[0]) if mine else None
                 held = []
@@ -634,6 +618,7 @@ def run_fused(k: int, hap_asm: Sequence[str], hap_reads: Sequence[Sequence[str]]
                         info["chunk_first"].append(reads.chunk_first.astype(np.int64) + info["n_reads"])
                         info["chunk_hap"].append(np.asarray(ch, np.uint8))
                         info["n_reads"] += reads.n_reads
+                        info["n_bases"] += reads.total_bases
                     return bind
 
                 def on_batch(e, b, base):
@@ -641,23 +626,20 @@ def run_fused(k: int, hap_asm: Sequence[str], hap_reads: Sequence[Sequence[str]]
                         r0 = e.rows(0)
                         r0["read"] = r0["read"] + np.uint32(base)
                         info["rows0"].append(r0)
-                iv, bases = eng.run_batches([bind_for(bi) for bi in range(len(mine))], contig_hap,
-                                            allreduce_hist=coll.allreduce_hist, gather_forests=coll.gather_forests,
-                                            on_batch=on_batch)
+                iv, bases = eng.run_batches([bind_for(bi) for bi in range(len(mine))], contig_hap, min_read_len=min_read_len,
+                                            allreduce_hist=cx.allreduce_hist, gather_forests=cx.gather_forests, on_batch=on_batch)
                 for old in held:
                     old.close()
-            info.update(kept=eng.rows(1), pairs=eng.pairs(), iv=iv)
+            info.update(kept=eng.rows(1, pinned=True), pairs=eng.pairs(pinned=True), iv=iv)
             results[di] = info
         except BaseException as ex:  # noqa: BLE001 -- reported by the caller; peers must not wait for this rank
             errors.append(ex)
-            ready.abort()
-            if xch is not None:
-                xch.abort()
+            xch.abort()
 
-    if len(devices) == 1:
+    if n_dev == 1:
         worker(0)
     else:
-        ths = [threading.Thread(target=worker, args=(i,)) for i in range(len(devices))]
+        ths = [threading.Thread(target=worker, args=(i,)) for i in range(n_dev)]
         for t in ths:
             t.start()
         for t in ths:
@@ -665,18 +647,53 @@ def run_fused(k: int, hap_asm: Sequence[str], hap_reads: Sequence[Sequence[str]]
     if errors:
         first = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)] or errors
         raise first[0]
+    return results
+
+
+def run_fused(k: int, hap_asm: Sequence[str], hap_reads: Sequence[Sequence[str]], outdir: str, device: int = 0,
+              devices: Sequence[int] = None, batch_files: int = 0, batch_gbp: float = 12.0, detailed: bool = False,
+              threads: int = 0, mrsfast_palindromes: bool = False):
+    """hap_asm: two FASTA paths; hap_reads: two lists of chunk files in scatter order.  Builds the SUNK database on
+    every GPU of `devices`, runs the reads (run_reads) and writes every file of the rules between jellyfish_count and
+    slop_gaps under `outdir`.  Returns the first device's engine."""
+    from concurrent.futures import ThreadPoolExecutor
+    devices = list(devices) if devices else [device]
+    contigs, contig_hap, fai = [], [], [[], []]
+    for hap in range(2):
+        for n, s in gio.read_fastx(hap_asm[hap]):
+            contigs.append((n, s))
+            contig_hap.append(hap)
+            fai[hap].append((n, len(s)))
+    files = list(hap_reads[0]) + list(hap_reads[1])
+    file_hap = [0] * len(hap_reads[0]) + [1] * len(hap_reads[1])
+    for p in files:
+        if not os.path.exists(p):
+            raise FileNotFoundError(p)
+
+    def make(d):
+        e = Engine(k, device=d)
+        e.build_db(contigs)
+        return e
+    if len(devices) == 1:
+        engines = [make(devices[0])]
+    else:
+        with ThreadPoolExecutor(max_workers=len(devices)) as ex:
+            engines = list(ex.map(make, devices))
+    results = run_reads(engines, contig_hap, files, file_hap, batch_files, batch_gbp, detailed, threads)
     eng = engines[0]
-    names = eng.contig_names
-    iv = results[0]["iv"]
     gaps, nodata = eng.gaps(np.asarray([len(s) for _, s in contigs], dtype=np.uint32))
-    _write_outputs(k, eng, results, contigs, contig_hap, fai, names, iv, gaps, nodata, outdir, detailed, mrsfast_palindromes)
+    write_outputs(k, eng, results, [len(s) for _, s in contigs], contig_hap, eng.contig_names, results[0]["iv"], gaps, nodata, outdir,
+                  detailed=detailed, palindromes=mrsfast_palindromes)
     for e in engines[1:]:
         e.close()
     return eng
 
 
-def _write_outputs(k, eng, results, contigs, contig_hap, fai, names, iv, gaps, nodata, outdir, detailed, palindromes):
-    """every file of SURVEY Appendix C that the rules between jellyfish_count and slop_gaps produce"""
+def write_outputs(k, eng, results, contig_len, contig_hap, names, iv, gaps, nodata, outdir, detailed=False, palindromes=False,
+                  db_files=True):
+    """every file of SURVEY Appendix C that the rules between jellyfish_count and slop_gaps produce (db_files=False:
+    without the exports of the database itself -- db/jellyfish.db|.fa, mrsfast/kmer.loc and its per-contig copies
+    breaks/*.loc -- which belong to the database build, not to a run over reads)"""
     d = lambda *p: os.path.join(outdir, *p)
     for sub in ("db", "mrsfast", "sunkpos", "breaks", "inter_outs", "bed_files", "final_out"):
         os.makedirs(d(sub), exist_ok=True)
@@ -709,17 +726,18 @@ def _write_outputs(k, eng, results, contigs, contig_hap, fai, names, iv, gaps, n
     pairs = cat_rows("pairs", ("read", "contig", "group"))
     sunk_cols = lambda t: [("name", t["read"], rtab), ("u32", t["pos"]), ("name", t["contig"], ctab), ("u32", t["start"]), ("u32", t["group"])]
     # ---- SUNK database files (defineSUNKs.smk:59-60, 126) ----
-    db = eng.db_export()
-    loc_cols = [("name", db["contig"], ctab), ("u32", db["start"]), ("kmer", db["kmer"], k), ("u32", db["group"])]
-    loc_sel = None
-    if palindromes and k % 2 == 0 and len(db["kmer"]):
-        # mrsfast reports a k-mer that is its own reverse complement on both strands: two identical rows
-        from .engine import revcomp_kmers
-        pal = db["kmer"] == revcomp_kmers(db["kmer"], k)
-        loc_sel = np.repeat(np.arange(len(pal), dtype=np.uint64), 1 + pal.astype(np.int64))
-    _write_bytes(d("db", "jellyfish.db"), gio.format_rows([("kmer", db["kmer"], k)]))
-    _write_bytes(d("db", "jellyfish.fa"), gio.format_rows([("kmer", db["kmer"], k, dict(prefix=b">", sep=b"\n")), ("kmer", db["kmer"], k)]))
-    _write_bytes(d("mrsfast", "kmer.loc"), gio.format_rows(loc_cols, sel=loc_sel))
+    from .engine import revcomp_kmers
+    loc_sel, loc_c = None, {}
+    if db_files:
+        db = eng.db_export()
+        loc_cols = [("name", db["contig"], ctab), ("u32", db["start"]), ("kmer", db["kmer"], k), ("u32", db["group"])]
+        if palindromes and k % 2 == 0 and len(db["kmer"]):
+            # mrsfast reports a k-mer that is its own reverse complement on both strands: two identical rows
+            pal = db["kmer"] == revcomp_kmers(db["kmer"], k)
+            loc_sel = np.repeat(np.arange(len(pal), dtype=np.uint64), 1 + pal.astype(np.int64))
+        _write_bytes(d("db", "jellyfish.db"), gio.format_rows([("kmer", db["kmer"], k)]))
+        _write_bytes(d("db", "jellyfish.fa"), gio.format_rows([("kmer", db["kmer"], k, dict(prefix=b">", sep=b"\n")), ("kmer", db["kmer"], k)]))
+        _write_bytes(d("mrsfast", "kmer.loc"), gio.format_rows(loc_cols, sel=loc_sel))
     # ---- per-haplotype row files (combine_ont, combine_ont_nofilt, read_lengths) ----
     khap = read_hap[kept["read"]] if len(kept["read"]) else np.zeros(0, np.uint8)
     all_reads = np.arange(nreads, dtype=np.uint32)
@@ -735,18 +753,39 @@ def _write_outputs(k, eng, results, contigs, contig_hap, fai, names, iv, gaps, n
     bad = eng.bad_list()
     _write_bytes(d("sunkpos", "bad_sunks.txt"), gio.format_rows([("name", gtab["contig"][bad], ctab, dict(sep=b":")), ("u32", gtab["group"][bad])]))
     # ---- per-contig files: breaks/*.sunkpos|.loc (split_locs.py:5-22), inter_outs/*.tsv, bed_files/*.bed ----
-    def by_contig(col):
-        order = np.argsort(col, kind="stable")
-        cs, first = np.unique(col[order], return_index=True)
-        ends = list(first[1:]) + [len(order)]
-        return {int(c): order[a:b] for c, a, b in zip(cs, first, ends)}
-    kept_c, loc_c, pair_c = by_contig(kept["contig"]), by_contig(db["contig"]), by_contig(pairs["contig"])
-    iv_c = by_contig(iv["contig"])
+    def by_contig(col, read=None, rank=None):
+        """row indices per contig, in row order (rank given: by rank[read] first, stable).  Rows come in runs of one
+        read on one contig, so the runs are sorted (a few per read), not the rows."""
+        n = len(col)
+        if n == 0:
+            return {}
+        brk = np.ones(n, bool)
+        if read is not None:
+            brk[1:] = (col[1:] != col[:-1]) | (read[1:] != read[:-1])
+        else:
+            brk[1:] = col[1:] != col[:-1]
+        starts = np.flatnonzero(brk)
+        lens = np.diff(np.append(starts, n))
+        rc = col[starts].astype(np.int64)
+        key = rc if rank is None else rc * np.int64(len(rank) + 1) + rank[read[starts]]
+        order = np.argsort(key, kind="stable")
+        starts, lens, rc = starts[order], lens[order], rc[order]
+        ends = np.cumsum(lens)
+        rows = np.repeat(starts - (ends - lens), lens) + np.arange(int(ends[-1]), dtype=np.int64)  # expand the sorted runs
+        cs, first = np.unique(rc, return_index=True)
+        lo = (ends - lens)[first]
+        hi = np.append(lo[1:], ends[-1])
+        return {int(c): rows[a:b] for c, a, b in zip(cs, lo, hi)}
     # `for rname, g in grouped`: groupby sorts read names (process-by-contig_lowmem_AR.py:135-136); rank of every read
     # name in that order (stable for equal names), pairs of a read stay in vertex order
     name_rank = np.empty(nreads, np.int64)
     if nreads:
         name_rank[np.argsort(rtab.as_bytes_array(), kind="stable")] = np.arange(nreads)
+    kept_c = by_contig(kept["contig"], kept["read"])
+    pair_c = by_contig(pairs["contig"], pairs["read"], name_rank)
+    if db_files:
+        loc_c = by_contig(db["contig"])
+    iv_c = by_contig(iv["contig"])
     for c, idx in kept_c.items():
         stem = f"{safe(names[c])}_hap{contig_hap[c] + 1}"
         _write_bytes(d("breaks", stem + ".sunkpos"), gio.format_rows(sunk_cols(kept), sel=idx))
@@ -757,14 +796,13 @@ def _write_outputs(k, eng, results, contigs, contig_hap, fai, names, iv, gaps, n
             _write_bytes(d("breaks", stem + ".loc"), gio.format_rows(loc_cols, sel=sel))
         if c in pair_c:
             pidx = pair_c[c]
-            pidx = pidx[np.argsort(name_rank[pairs["read"][pidx]], kind="stable")]
             _write_bytes(d("inter_outs", stem + ".tsv"), gio.format_rows([("u32", pairs["group"]), ("name", pairs["read"], rtab)], sel=pidx))
             _write_bytes(d("bed_files", stem + ".bed"), gio.format_rows([("name", iv["contig"], ctab), ("u32", iv["start"]), ("u32", iv["end"])],
                                                                     sel=iv_c.get(c, np.zeros(0, np.uint64))))
         else:  # "no usable reads": contig name only, bed touched empty by the rule (tagONT.smk:190)
             _write_bytes(d("inter_outs", stem + ".tsv"), (names[c] + "\n").encode("latin-1"))
             _write_bytes(d("bed_files", stem + ".bed"), b"")
-    clen = np.asarray([len(s) for _, s in contigs], dtype=np.uint32)
+    clen = np.asarray(contig_len, dtype=np.uint32)
     chap = np.asarray(contig_hap, np.uint8)
     for hap in range(2):
         hn = hap + 1

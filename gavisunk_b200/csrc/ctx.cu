@@ -408,6 +408,7 @@ static int reads_set_impl(gvs_ctx* ctx, const uint8_t* seq, bool packed, const u
   (void)gvs_pipe_join(ctx);  // a failure of the previous batch's submitter was gvs_match's to report, not this batch's
   ctx->reads_ready = false;
   ctx->match_ready = ctx->diag_ready = ctx->val_ready = false;
+  ctx->have_read_len = false;  // lengths come from this batch's offsets, not from an earlier gvs_reads_meta / gvs_batches_bind
   if (chunk_first[0] != 0 || chunk_first[n_chunks] != n_reads) return gvs_fail(ctx, GVS_E_ARG, "chunk_first must span [0, n_reads]");
   for (u32 c = 0; c < n_chunks; c++)
     if (chunk_first[c] > chunk_first[c + 1]) return gvs_fail(ctx, GVS_E_ARG, "chunk_first not monotone");

@@ -16,6 +16,8 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -141,9 +143,48 @@ static void parse(const std::vector<u8>& data, FileReads& out) {
 
 }  // namespace
 
+// Page-locking host memory costs about as much as parsing into it: the page-locked word arrays of freed batches are
+// kept (a few, process-wide) and handed to the next gvs_fastx_read_packed that fits -- a run streams many batches of
+// similar size through the same two buffers.
+namespace {
+struct PinnedCache {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;
+  static constexpr size_t MAX_KEEP = 3;
+  void* take(size_t bytes, size_t* cap) {
+    std::lock_guard<std::mutex> l(mu);
+    size_t best = free_list.size();
+    for (size_t i = 0; i < free_list.size(); i++)
+      if (free_list[i].second >= bytes && (best == free_list.size() || free_list[i].second < free_list[best].second)) best = i;
+    if (best == free_list.size()) return nullptr;
+    void* p = free_list[best].first;
+    *cap = free_list[best].second;
+    free_list.erase(free_list.begin() + (long)best);
+    return p;
+  }
+  void give(void* p, size_t cap) {
+    void* drop = nullptr;
+    {
+      std::lock_guard<std::mutex> l(mu);
+      free_list.emplace_back(p, cap);
+      if (free_list.size() > MAX_KEEP) {  // the smallest goes
+        size_t w = 0;
+        for (size_t i = 1; i < free_list.size(); i++)
+          if (free_list[i].second < free_list[w].second) w = i;
+        drop = free_list[w].first;
+        free_list.erase(free_list.begin() + (long)w);
+      }
+    }
+    if (drop) cudaFreeHost(drop);
+  }
+};
+PinnedCache g_pinned_words;
+}  // namespace
+
 struct gvs_fastx_impl {
   u32* words = nullptr;
   bool words_pinned = false;
+  size_t words_cap = 0;  // bytes of a page-locked `words` from the cache (0: plain allocation of gvs_fastx_pack)
   std::string names;
   std::vector<u64> name_off;
   std::vector<u64> read_off;
@@ -290,7 +331,9 @@ extern "C" void gvs_fastx_free(gvs_fastx* fx) {
   if (!fx || !fx->impl) return;
   gvs_fastx_impl* R = (gvs_fastx_impl*)fx->impl;
   if (R->words) {
-    if (R->words_pinned) cudaFreeHost(R->words); else free(R->words);
+    if (R->words_pinned && R->words_cap) g_pinned_words.give(R->words, R->words_cap);
+    else if (R->words_pinned) cudaFreeHost(R->words);
+    else free(R->words);
   }
   if (R->seq) {
     if (R->pinned) cudaFreeHost(R->seq); else free(R->seq);
@@ -578,6 +621,7 @@ extern "C" int gvs_fastx_read_packed(const char* const* paths, uint32_t n_files,
   if (!out || (n_files && !paths)) return fail("gvs_fastx_read_packed: null argument");
   memset(out, 0, sizeof(*out));
   if (block_bytes == 0) block_bytes = 1u << 20;
+  auto t_begin = std::chrono::steady_clock::now();
   std::vector<PackedFile> files(n_files);
   if (threads < 1) threads = 1;
   if ((u32)threads > n_files) threads = (int)(n_files ? n_files : 1);
@@ -597,6 +641,8 @@ extern "C" int gvs_fastx_read_packed(const char* const* paths, uint32_t n_files,
   }
   for (u32 i = 0; i < n_files; i++)
     if (!files[i].err.empty()) return fail(files[i].err);
+  const bool timing = getenv("GVS_FASTX_TIMING") != nullptr;
+  auto t_parse = std::chrono::steady_clock::now();
   gvs_fastx_impl* R = new gvs_fastx_impl();
   u64 n_reads = 0, total = 0;
   std::vector<u64> base(n_files + 1, 0);
@@ -623,8 +669,13 @@ extern "C" int gvs_fastx_read_packed(const char* const* paths, uint32_t n_files,
   }
   const u64 nw = (total + 15) / 16;
   const size_t bytes = (nw + 16) * 4;  // slack: the probe stages whole vectors
-  if (pin && cudaHostAlloc((void**)&R->words, bytes, cudaHostAllocDefault) == cudaSuccess) {
+  size_t cap = 0;
+  if (pin && (R->words = (u32*)g_pinned_words.take(bytes, &cap)) != nullptr) {
     R->words_pinned = true;
+    R->words_cap = cap;
+  } else if (pin && cudaHostAlloc((void**)&R->words, bytes + bytes / 8, cudaHostAllocDefault) == cudaSuccess) {
+    R->words_pinned = true;
+    R->words_cap = bytes + bytes / 8;
   } else {
     cudaGetLastError();
     R->words = (u32*)malloc(bytes);
@@ -665,6 +716,12 @@ extern "C" int gvs_fastx_read_packed(const char* const* paths, uint32_t n_files,
     R->words[g0] |= shifted_word(files[i].words, 0, sh);
     if (g1 != g0) R->words[g1] |= shifted_word(files[i].words, (i64)(g1 - g0), sh);
     std::vector<u32>().swap(files[i].words);
+  }
+  if (timing) {
+    auto t_end = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gvs_fastx_read_packed] parse+pack %.3f s, layout %.3f s (%llu bases, %u files, %d threads)\n",
+            std::chrono::duration<double>(t_parse - t_begin).count(), std::chrono::duration<double>(t_end - t_parse).count(),
+            (unsigned long long)total, n_files, threads);
   }
   out->impl = R;
   out->seq = nullptr;

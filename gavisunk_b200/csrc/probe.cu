@@ -25,6 +25,7 @@
 //     appends its records to its own region (position order, no per-hit atomics); a scan of the per-span
 //     counts + one coalesced copy give the dense ordered list
 #include "table.cuh"
+#include <stdlib.h>
 #include <vector>
 
 #define PW_WARPS 8     // warps per block
@@ -86,10 +87,11 @@ __device__ __forceinline__ u64 p_extract(u32 a, u32 b, u32 c, int off) {
   return v >> (64 - 2 * LEN);
 }
 
-struct WarpSmem {
+struct __align__(16) WarpSmem {
   u32 fw[PW_RING];   // forward packed words, ring index = (slot base + word) & 63
   u32 rc[PW_RING];   // rc[i] = reverse complement of fw[i] (same index)
-  uint4 raw[32];     // cp.async landing zone: 16 ASCII bases per lane
+  uint4 raw[32];     // landing zone of the tile's bulk copy (TMA): 16 ASCII bases per lane (PACKED: one word per lane)
+  u64 bar;           // mbarrier the bulk copy of a tile completes on (one per warp; the phase flips per tile)
   u32 bound[20];
   u32 shrt[20];
   u32 bpos[PW_MAXB];
@@ -178,41 +180,87 @@ __device__ __forceinline__ u32 p_ldg_u32(const u32* ptr, u64 pol) {
   return v;
 }
 
-// asynchronous copy of the 32 x 16 bases of `tile` into sm.raw (zero beyond the end): 16 ASCII bytes per lane,
-// or -- PACKED -- the lane's ready-made 2-bit word (gvs_reads_set_packed: 16 bases per big-endian u32)
-template <bool PACKED>
-__device__ __forceinline__ void p_stage_issue(WarpSmem& sm, const u8* __restrict__ seq, u64 tile, u64 total, int lane) {
-  u64 g = tile * PW_TILE + 16ull * lane;
-  if (PACKED) {
-    unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.raw[lane]);
-    if (g < total) {  // the word array is padded to whole words (bases beyond `total` are zero)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"((const u32*)seq + (g >> 4)) : "memory");
-    } else {
-      sm.raw[lane].x = 0;
-    }
-  } else if (g + 16 <= total) {
-    unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.raw[lane]);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(seq + g), "l"(p_policy_stream())
-                 : "memory");
-  } else {
-    u32 w[4] = {0, 0, 0, 0};
-    for (int i = 0; i < 16 && g + i < total; i++) w[i >> 2] |= (u32)seq[g + i] << (8 * (i & 3));
-    sm.raw[lane] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
+// ---- tile staging: ONE 1-D bulk copy (TMA, cp.async.bulk + mbarrier) per warp tile -------------------------
+// A tile is 512 consecutive bases = 512 B of ASCII (128 B of 2-bit words when PACKED), contiguous in HBM and
+// 16-byte aligned: lane 0 arms the warp's mbarrier with the byte count and issues the copy (evict_first: the
+// reads stream through L2 once), all lanes wait on the barrier's phase when they need the bytes.  Replaces
+// 32 cp.async (LDGSTS) + commit / wait_group per tile.
+__device__ __forceinline__ u32 p_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void p_bar_init(u64* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(p_smem_addr(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
-// pack the landed bases into ring slot `rb` (forward + reverse complement)
+__device__ __forceinline__ void p_bar_wait(u64* bar, u32 phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PW_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PW_DONE;\n"
+      "bra PW_WAIT;\n"
+      "PW_DONE:\n"
+      "}\n" ::"r"(p_smem_addr(bar)),
+      "r"(phase)
+      : "memory");
+}
+// bytes of `tile` that exist in the batch's sequence buffer, rounded up to the 16 bytes a bulk copy moves (the
+// buffer carries >= 64 bytes of slack); 0 beyond the end
 template <bool PACKED>
-__device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, int lane) {
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  u32 w;
+__device__ __forceinline__ u32 p_tile_bytes(u64 tile, u64 total) {
+  const u64 unit = PACKED ? PW_TILE / 4 : PW_TILE;
+  const u64 have = PACKED ? 4 * ((total + 15) >> 4) : total;
+  const u64 b0 = tile * unit;
+  if (b0 >= have) return 0;
+  const u64 r = have - b0;
+  return r >= unit ? (u32)unit : (u32)((r + 15) & ~15ull);
+}
+template <bool PACKED>
+__device__ __forceinline__ void p_stage_issue(WarpSmem& sm, const u8* __restrict__ seq, u64 tile, u64 total, int lane, u64 pol) {
+  const u32 bytes = p_tile_bytes<PACKED>(tile, total);
+  if (lane == 0 && bytes) {
+    const u32 bar = p_smem_addr(&sm.bar), dst = p_smem_addr(&sm.raw[0]);
+    const u8* src = seq + tile * (PACKED ? PW_TILE / 4 : PW_TILE);
+    // the lanes' reads of the previous tile in sm.raw (generic proxy; a __syncwarp lies in between) come before the
+    // copy engine's writes (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+  }
+}
+// wait for the tile's bytes and pack them into ring slot `rb` (forward + reverse complement); `phase` is the
+// warp's barrier phase (flips whenever a copy was waited for)
+template <bool PACKED>
+__device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, u64 tile, u64 total, int lane, u32& phase) {
+  const u32 bytes = p_tile_bytes<PACKED>(tile, total);
+  if (bytes) {
+    p_bar_wait(&sm.bar, phase);
+    phase ^= 1u;
+  }
+  u32 w = 0;
   if (PACKED) {
-    w = sm.raw[lane].x;
+    if (4u * lane < bytes) w = ((const u32*)sm.raw)[lane];  // the word array is zero-padded to whole words
   } else {
-    uint4 v = sm.raw[lane];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const u64 g = tile * PW_TILE + 16ull * lane;
+    const bool tail = g + 16 > total;  // the last bases of the batch: bytes beyond the end read as 0 (-> A; their windows are invalid)
+    if (16u * lane < bytes) {
+      v = sm.raw[lane];
+      if (tail) {
+        const u32 nv = g < total ? (u32)(total - g) : 0u;
+        u32 x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const u32 left = nv > 4u * i ? nv - 4u * i : 0u;
+          x[i] &= left >= 4u ? 0xFFFFFFFFu : ((1u << (8 * left)) - 1u);
+        }
+        v = make_uint4(x[0], x[1], x[2], x[3]);
+      }
+    }
     u32 bad = 0;
     w = p_pack16_be_fast(v, bad);
-    if (__any_sync(0xFFFFFFFFu, bad != 0)) w = p_pack16_be(v);  // N runs, U, control bytes: the exact byte map
+    if (__any_sync(0xFFFFFFFFu, (bad != 0) | tail)) w = p_pack16_be(v);  // N runs, U, control bytes, the batch's tail: the exact byte map
   }
   sm.fw[(rb + lane) & 63] = w;
   sm.rc[(rb + lane) & 63] = p_rc16(w);
@@ -233,7 +281,11 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
   constexpr int L = K - J + 1;
   constexpr int NG = 16 / J;
   const u64 pol_keep = p_policy_keep();
-  const u64 pol_blk = P.blk_stream ? p_policy_stream() : pol_keep;
+  const u64 pol_stream = p_policy_stream();
+  const u64 pol_blk = P.blk_stream ? pol_stream : pol_keep;
+  if (lane == 0) p_bar_init(&sm.bar);
+  __syncwarp();
+  u32 phase = 0;  // parity of the warp's mbarrier: flips with every tile copy waited for
 
   for (;;) {
     // ---- next span of tiles ----
@@ -263,10 +315,11 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
 
     // prologue: tiles T0 and T0+1 into ring slots 0 and 1
     __syncwarp();
-    p_stage_issue<PACKED>(sm, P.seq, tile0, P.total, lane);
-    p_stage_finish<PACKED>(sm, 0, lane);
-    p_stage_issue<PACKED>(sm, P.seq, tile0 + 1, P.total, lane);
-    p_stage_finish<PACKED>(sm, 32, lane);
+    p_stage_issue<PACKED>(sm, P.seq, tile0, P.total, lane, pol_stream);
+    p_stage_finish<PACKED>(sm, 0, tile0, P.total, lane, phase);
+    __syncwarp();
+    p_stage_issue<PACKED>(sm, P.seq, tile0 + 1, P.total, lane, pol_stream);
+    p_stage_finish<PACKED>(sm, 32, tile0 + 1, P.total, lane, phase);
     __syncwarp();
 
     u32 wcount = 0;  // hits of this span so far
@@ -274,7 +327,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
       const u64 ts = tile * PW_TILE;
       const u32 rb = (u32)((tile - tile0) & 1) * 32;  // ring base of this tile
       // prefetch tile T+2 (lands in sm.raw while this tile is processed)
-      p_stage_issue<PACKED>(sm, P.seq, tile + 2, P.total, lane);
+      p_stage_issue<PACKED>(sm, P.seq, tile + 2, P.total, lane, pol_stream);
 
       // ---- read boundaries in (ts, ts + 512 + K - 2] ----
       const u64 limit = ts + PW_TILE + (K > 1 ? K - 1 : 1);
@@ -615,7 +668,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
       }
       // ---- tile T is done: its ring slot receives tile T+2 ----
       __syncwarp();
-      p_stage_finish<PACKED>(sm, rb, lane);
+      p_stage_finish<PACKED>(sm, rb, tile + 2, P.total, lane, phase);
       __syncwarp();
     }
     if (lane == 0) P.warp_cnt[region] = wcount;
@@ -704,6 +757,15 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
     if (ctx->l2_persist_max < 0) ctx->l2_persist_max = 0;
   }
   const int persist_max = ctx->l2_persist_max, window_max = ctx->l2_window_max;
+  {
+    static bool said = false;
+    if (!said && getenv("GVS_EXP_VERBOSE")) {
+      said = true;
+      fprintf(stderr, "[gvs] L2 persisting max %d B, access window max %d B, presence filter %llu B, block filter %llu B, table %llu slots\n",
+              persist_max, window_max, (unsigned long long)ctx->filt1_words * 4, (unsigned long long)ctx->filt_words * 16,
+              (unsigned long long)ctx->tab_slots);
+    }
+  }
   const void* hot = ctx->filt1.p;
   size_t hot_bytes = ctx->filt1_words * 4;
   cudaLaunchConfig_t cfg = {};
@@ -712,8 +774,10 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   int n_attr = 0;
-  if (persist_max > 0 && window_max > 0) {
+  static const int exp_no_persist = getenv("GVS_EXP_NO_PERSIST") ? atoi(getenv("GVS_EXP_NO_PERSIST")) : 0;  // experiments
+  if (persist_max > 0 && window_max > 0 && exp_no_persist != 1) {
     size_t carve = hot_bytes < (size_t)persist_max ? hot_bytes : (size_t)persist_max;
+    if (exp_no_persist == 2) carve = (size_t)persist_max;
     if (ctx->l2_carve_set != carve) {
       cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
       ctx->l2_carve_set = carve;

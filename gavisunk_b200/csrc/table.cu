@@ -1,6 +1,7 @@
 // table.cu -- SUNK probe table + filter construction from .loc rows (kmerpos_annot3's table
 // load, workflow/src/kmerpos_annot3.nim:20-26,57-69) and database export.
 #include "table.cuh"
+#include <stdlib.h>
 
 // ---- kernels -------------------------------------------------------------------------------
 __global__ void k_fill_u64(u64* p, u64 n, u64 v) {
@@ -120,6 +121,10 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
     u64 w1 = next_pow2((n_loc ? n_loc : 1) * 5 / 8);
     if (w1 < (1ull << 10)) w1 = 1ull << 10;
     if (w1 > (1ull << 24)) w1 = 1ull << 24;
+    if (const char* e = getenv("GVS_EXP_FILT1_LOG2W")) {  // experiments: presence filter size (log2 of its 32-bit words)
+      int l2 = atoi(e);
+      if (l2 >= 10 && l2 <= 28) w1 = 1ull << l2;
+    }
     ctx->filt1_words = w1;
     CKR(gvs_reserve(ctx, ctx->filt1, w1 * 4));
     LAUNCH(k_fill_u32, grid_for(ctx, w1, 256), 256, 0, ctx->filt1.as<u32>(), w1, 0u);

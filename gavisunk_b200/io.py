@@ -95,7 +95,10 @@ class NativeReads:
         paths = [os.fspath(p) for p in paths]
         arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
         err = C.create_string_buffer(512)
-        nthr = threads or min(len(paths), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        nthr = threads or min(len(paths), ncpu)
+        if nthr < len(paths) <= 2 * nthr:
+            nthr = len(paths)  # one thread per file (a file is parsed by one thread): 20 files on 16 cores would take two rounds
         if packed:
             rc = lib.gvs_fastx_read_packed(arr, len(paths), nthr, 1 if pin else 0, int(block_bytes), C.byref(self._fx), err, 512)
         else:
