@@ -719,8 +719,8 @@ def write_outputs(k, eng, results, contig_len, contig_hap, names, iv, gaps, noda
             for i, r in enumerate(results):
                 tabs = r[key] if isinstance(r[key], list) else [r[key]]
                 for t in tabs:
-                    parts.append(t[c] + np.uint32(read_base[i]) if c == "read" else t[c])
-            out[c] = np.concatenate(parts) if parts else np.zeros(0, np.uint32)
+                    parts.append(t[c] + np.uint32(read_base[i]) if (c == "read" and read_base[i]) else t[c])
+            out[c] = parts[0] if len(parts) == 1 else (np.concatenate(parts) if parts else np.zeros(0, np.uint32))
         return out
     kept = cat_rows("kept", ("read", "pos", "contig", "start", "group"))
     pairs = cat_rows("pairs", ("read", "contig", "group"))

@@ -63,6 +63,7 @@ struct gvs_ctx {
   u64 n_loc = 0, n_groups = 0;
   u32 n_contigs = 0;
   DevBuf loc_kmer, loc_contig, loc_start, loc_group, loc_gidx;  // per .loc row
+  DevBuf loc_pack;                                               // per .loc row: (contig, start, group, 0) in one 16-byte word for the emit pass
   DevBuf grp_contig, grp_start;                                  // per group (index = gidx)
   DevBuf tab_keys, tab_rows, tab_gidx;                           // open-addressed probe table: keys, (build only) rows, (group index << 32 | row)
   u64 tab_slots = 0;                                             // power of two, buckets of 4

@@ -12,17 +12,46 @@
 
 namespace {
 
+static const char DIGIT_PAIRS[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566"
+    "676869707172737475767778798081828384858687888990919293949596979899";
+
+static inline unsigned dec_len32(uint32_t v) {
+  return v < 100000u ? (v < 100u ? (v < 10u ? 1 : 2) : (v < 1000u ? 3 : (v < 10000u ? 4 : 5)))
+                     : (v < 10000000u ? (v < 1000000u ? 6 : 7) : (v < 100000000u ? 8 : (v < 1000000000u ? 9 : 10)));
+}
 static inline unsigned dec_len(uint64_t v) {
-  unsigned n = 1;
-  while (v >= 10) { v /= 10; n++; }
-  return n;
+  if (v <= 0xFFFFFFFFull) return dec_len32((uint32_t)v);
+  unsigned n = 0;
+  while (v > 0xFFFFFFFFull) { v /= 10; n++; }
+  return n + dec_len32((uint32_t)v);
+}
+// digits written backwards from p + len, two at a time
+static inline void put_digits32(char* end, uint32_t v) {
+  while (v >= 100u) {
+    const uint32_t q = v / 100u, r = v - q * 100u;
+    end -= 2;
+    end[0] = DIGIT_PAIRS[2 * r];
+    end[1] = DIGIT_PAIRS[2 * r + 1];
+    v = q;
+  }
+  if (v >= 10u) {
+    end -= 2;
+    end[0] = DIGIT_PAIRS[2 * v];
+    end[1] = DIGIT_PAIRS[2 * v + 1];
+  } else {
+    *--end = (char)('0' + v);
+  }
 }
 static inline char* put_dec(char* p, uint64_t v) {
-  char tmp[20];
-  unsigned n = 0;
-  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-  while (n) *p++ = tmp[--n];
-  return p;
+  const unsigned n = dec_len(v);
+  char* end = p + n;
+  while (v > 0xFFFFFFFFull) {
+    *--end = (char)('0' + v % 10);
+    v /= 10;
+  }
+  put_digits32(end, (uint32_t)v);
+  return p + n;
 }
 
 static inline uint64_t cell_len(const gvs_col& c, uint64_t r) {

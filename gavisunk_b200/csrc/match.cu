@@ -62,8 +62,7 @@ __global__ void __launch_bounds__(256) k_emit_rows(const u32* __restrict__ hread
                                                    const u32* __restrict__ hrow, const u32* __restrict__ hgidx,
                                                    const u8* __restrict__ flags,
                                                    const u64* __restrict__ packed_excl, const u32* __restrict__ seg_base,
-                                                   u64 n, const u32* __restrict__ loc_contig,
-                                                   const u32* __restrict__ loc_start, const u32* __restrict__ loc_group,
+                                                   u64 n, const uint4* __restrict__ loc_pack,
                                                    u32* r_read, u32* r_pos,
                                                    u32* r_contig, u32* r_start, u32* r_group, u32* r_gidx) {
   u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,9 +75,10 @@ __global__ void __launch_bounds__(256) k_emit_rows(const u32* __restrict__ hread
   u32 row = hrow[j];
   r_read[out] = hread[j];
   r_pos[out] = hw[j] - (supp - base);  // `continue` skips `inc i` (nim:92,96; Q3)
-  r_contig[out] = loc_contig[row];
-  r_start[out] = loc_start[row];
-  r_group[out] = loc_group[row];
+  const uint4 l = __ldg(loc_pack + row);  // (contig, start, group) of the .loc row
+  r_contig[out] = l.x;
+  r_start[out] = l.y;
+  r_group[out] = l.z;
   r_gidx[out] = hgidx[j];
 }
 
@@ -314,8 +314,8 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
   u64 n_rows = packed_total >> 32;
   CKR(gvs_reserve_rows(ctx, ctx->rows, n_rows));
   LAUNCH(k_emit_rows, (unsigned)cdiv(nh, 256), 256, 0, ctx->ohit_read.as<u32>(), ctx->ohit_w.as<u32>(),
-         ctx->ohit_row.as<u32>(), ctx->ohit_gidx.as<u32>(), fl, pex, sb, nh, ctx->loc_contig.as<u32>(), ctx->loc_start.as<u32>(),
-         ctx->loc_group.as<u32>(), ctx->rows.read.as<u32>(), ctx->rows.pos.as<u32>(),
+         ctx->ohit_row.as<u32>(), ctx->ohit_gidx.as<u32>(), fl, pex, sb, nh, ctx->loc_pack.as<uint4>(), ctx->rows.read.as<u32>(),
+         ctx->rows.pos.as<u32>(),
          ctx->rows.contig.as<u32>(), ctx->rows.start.as<u32>(), ctx->rows.group.as<u32>(), ctx->rows.gidx.as<u32>());
   ctx->rows.n = n_rows;
   ctx->match_ready = true;

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
   extern __shared__ __align__(16) u8 smem[];
   __shared__ u32 s_n0[GROUPS], s_n1[GROUPS], s_m[GROUPS], s_kept[GROUPS], s_bestroot[GROUPS], s_flag[GROUPS], s_dup[GROUPS];
   __shared__ u32 s_pmin[GROUPS], s_pmax[GROUPS];  // span of the read's positions (all threads of the group)
+  __shared__ u32 s_up[GROUPS], s_dn[GROUPS];      // some position step up / down along ascending starts
   __shared__ unsigned long long s_best[GROUPS];
   __shared__ u32 s_wtot[GROUPS][NT / 32];  // per-warp counts of the order-preserving compaction
   const int grp = threadIdx.x / NT;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     const u32 mrows = b - a;
     if (mrows <= V.m_lo || mrows > V.m_hi) continue;  // another launch owns this read (group-uniform)
     gsync();
-    if (tid == 0) { s_m[grp] = 0; s_n0[grp] = 0; s_n1[grp] = 0; s_kept[grp] = 0; s_best[grp] = 0; s_bestroot[grp] = NOV; s_flag[grp] = 0; s_dup[grp] = 0; s_pmin[grp] = 0xFFFFFFFFu; s_pmax[grp] = 0; }
+    if (tid == 0) { s_m[grp] = 0; s_n0[grp] = 0; s_n1[grp] = 0; s_kept[grp] = 0; s_best[grp] = 0; s_bestroot[grp] = NOV; s_flag[grp] = 0; s_dup[grp] = 0; s_pmin[grp] = 0xFFFFFFFFu; s_pmax[grp] = 0; s_up[grp] = 0; s_dn[grp] = 0; }
     gsync();
     // read length filter (hard-coded 10000 in the reference, :106-108; Q13)
     const u32 rd = V.read[a];
@@ -224,6 +225,41 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       gsync();
       const bool narrow = s_flag[grp] != 2;
       u32 n0 = 0, n1 = 0;
+      // Reads follow one strand of one locus: along ascending starts their positions then never decrease (or never
+      // increase), every pair has the same sign, and with one row per ID nothing downstream needs the number of
+      // masked pairs -- only, per row, whether it has a partner and which partner comes first on either side
+      // (presence, first appearance in the edge list, first label).  Those are found by a search that stops at the
+      // first hit: O(rows) per read instead of O(rows^2) pair tests.
+      u32 p_up = 0, p_dn = 0;
+      if (!s_dup[grp]) {
+        for (u32 i = tid; i + 1 < m; i += NT) {
+          const u32 a0 = w.P[i], a1 = w.P[i + 1];
+          p_up |= a0 < a1;
+          p_dn |= a0 > a1;
+        }
+        if (p_up) s_up[grp] = 1;
+        if (p_dn) s_dn[grp] = 1;
+      }
+      gsync();
+      const bool steps_up = s_up[grp] != 0, steps_dn = s_dn[grp] != 0;
+      const u32 psign = (!s_dup[grp] && !(steps_up && steps_dn)) ? (steps_dn ? 2u : 1u) : 0u;  // 1: never decreases, 2: never increases
+      auto search = [&](auto ok_fn) {
+        for (u32 r = tid; r < m; r += NT) {
+          const u32 pr = w.P[r], sr = w.S[r];
+          u32 fp = NOV, fh = NOV;
+          for (u32 q = 0; q < r; q++) {
+            const u32 pq = w.P[q];
+            if (ok_fn(sr - w.S[q], pq > pr ? pq - pr : pr - pq)) { fp = q; break; }
+          }
+          for (u32 q = r + 1; q < m; q++) {
+            const u32 pq = w.P[q];
+            if (ok_fn(w.S[q] - sr, pq > pr ? pq - pr : pr - pq)) { fh = q; break; }
+          }
+          const u32 d = (fp != NOV) + (fh != NOV);
+          if (psign == 1) { w.uP[r] = fp; w.uS[r] = fh; w.uID[r] = NOV; w.uG[r] = NOV; w.deg[r] = d; w.label[r] = 0; n0 += fh != NOV; }
+          else { w.uP[r] = NOV; w.uS[r] = NOV; w.uID[r] = fp; w.uG[r] = fh; w.deg[r] = 0; w.label[r] = d; n1 += fh != NOV; }
+        }
+      };
       auto walk = [&](auto ok_fn) {
         for (u32 r = tid; r < m; r += NT) {
           const u32 pr = w.P[r], sr = w.S[r];
@@ -259,7 +295,10 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
         }
       };
       // 0.9 < dpos/dstart < 1.1 in float64 (:145-147) as exact integers (Q12)
-      if (narrow) walk([](u32 ds, u32 dp) -> u32 { return (9u * ds < 10u * dp) & (10u * dp < 11u * ds); });
+      if (psign) {
+        if (narrow) search([](u32 ds, u32 dp) -> bool { return (9u * ds < 10u * dp) & (10u * dp < 11u * ds); });
+        else search([](u32 ds, u32 dp) -> bool { return (9ull * ds < 10ull * dp) & (10ull * dp < 11ull * ds); });
+      } else if (narrow) walk([](u32 ds, u32 dp) -> u32 { return (9u * ds < 10u * dp) & (10u * dp < 11u * ds); });
       else walk([](u32 ds, u32 dp) -> u32 { return (9ull * ds < 10ull * dp) & (10ull * dp < 11ull * ds); });
       for (int d = 16; d; d >>= 1) {
         n0 += __shfl_xor_sync(0xFFFFFFFFu, n0, d);
@@ -381,6 +420,9 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       if (differs) s_n1[grp] = 1;
     }
     gsync();
+    // one row per ID and a single component found by the shortcut: every present row but the first has that first
+    // row as its first left partner, so the vertices were inserted in row order (see the output pass below)
+    const bool in_row_order = !s_dup[grp] && s_n1[grp] == 0;
     // ---- components: min-label propagation over surviving edges and same-ID rows until stable ----
     for (int round = 0; s_n1[grp] && round < 4096; round++) {
       if (tid == 0) s_flag[grp] = 0;
@@ -420,8 +462,9 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
       // the first present row of an ID represents the vertex
       const u32 idr = w.ID[r];
       u32 firstp = r;
-      for (u32 q = 0; q < r; q++)
-        if (w.ID[q] == idr && (w.flags[q] & F_PRES)) { firstp = q; break; }
+      if (s_dup[grp])  // (with one row per ID every present row is its own vertex)
+        for (u32 q = 0; q < r; q++)
+          if (w.ID[q] == idr && (w.flags[q] & F_PRES)) { firstp = q; break; }
       if (firstp != r) continue;
       u32 lab = w.label[r];
       atomicAdd(&w.csize[lab], 1u);
@@ -446,6 +489,36 @@ __global__ void __launch_bounds__(NT* GROUPS) k_validate(const ValParams V) {
     gsync();
     const u32 broot = s_bestroot[grp];
     // ---- output in vertex order (first appearance in the edge list, source before target) ----
+    if (in_row_order) {
+      // vertex order == row order: the first vertex v0 enters as the source of its first edge (v0, r1), every other
+      // row r as the target of (v0, r), and edges are listed by (left row, right row); rank = vertices before the row
+      u32 done = 0;
+      for (u32 base = 0; base < m; base += NT) {
+        const u32 r = base + tid;
+        const bool mem = r < m && (w.flags[r] & 8u);
+        const u32 bal = __ballot_sync(0xFFFFFFFFu, mem);
+        if (NT > 32) {
+          if ((tid & 31) == 0) s_wtot[grp][tid >> 5] = __popc(bal);
+          gsync();
+        }
+        u32 before = 0, total = __popc(bal);
+        if (NT > 32) {
+          total = 0;
+          for (int wv = 0; wv < NT / 32; wv++) {
+            const u32 c = s_wtot[grp][wv];
+            before += wv < (tid >> 5) ? c : 0u;
+            total += c;
+          }
+        }
+        if (mem) {
+          const u32 rank = done + before + __popc(bal & ((1u << (tid & 31)) - 1));
+          V.out_id[a + rank] = w.ID[r];
+          V.out_gidx[a + rank] = w.G[r];
+        }
+        done += total;
+        if (NT > 32) gsync();
+      }
+    } else
     for (u32 r = tid; r < m; r += NT) {
       if ((w.flags[r] & 8u) && w.label[r] == broot) {
         const u64 t = w.tv[w.rep[r]];

@@ -212,3 +212,43 @@ def test_simulated_reads_are_reproducible():
     # no simulated read of haplotype 1 may span the desert; spot-check the generator's own rule on a few lengths
     r1 = S.simulate(haps[0], case["lengths"][0][:40], case["seed"], "h1r", forbid=tuple(case["forbid"]), skip=case["skip"])
     assert len(r1) == 40 and all(len(s) > 0 for _, s in r1)
+
+
+@pytest.mark.gpu
+def test_fused_on_two_contexts_equals_reference_outputs(j1):
+    """`--devices 0,0`: two contexts (one host thread each) share the chunk files of the sample and exchange the
+    histogram and the forests inside the process (cli.ThreadExchange) -- the multi-GPU path of the fused rule; the files
+    are the reference's, byte for byte"""
+    case, tmp = j1["case"], j1["tmp"]
+    outdir = tmp / "results_2ctx"
+    argv = ["fused", "--k", str(case["k"]), "--hap1-asm", j1["asm"][0], "--hap2-asm", j1["asm"][1], "--hap1-reads", *j1["chunks"][0],
+            "--hap2-reads", *j1["chunks"][1], "--outdir", str(outdir), "--devices", "0,0", "--batch-files", "3"]
+    assert cli.main(argv) == 0
+    rd = lambda *p: open(os.path.join(outdir, *p)).read()
+    assert _sha(rd("mrsfast", "kmer.loc")) == case["loc_sha"]
+    _check_final(case, rd)
+
+
+@pytest.mark.gpu
+def test_split_ont_then_fused_equals_reference_outputs(j1):
+    """split_ONT emulation (cli split_ont: FASTQ with '#' qualities, round-robin over 10 outputs, gzip) on the whole
+    read set of each haplotype, then the fused rule: the chunk files hold the same records as the reference run's, so
+    every output is the reference's (parity of the split itself is unpinned: seqtk / rustybam are absent)"""
+    case, tmp = j1["case"], j1["tmp"]
+    haps = [[(n, s.encode()) for n, s in h] for h in case["asm"]]
+    forbid = tuple(case["forbid"]) if case["forbid"] else None
+    chunks = [[], []]
+    for hi in range(2):
+        reads = S.simulate(haps[hi], case["lengths"][hi], case["seed"] + hi, f"h{hi + 1}r", forbid=forbid, skip=case["skip"])
+        whole = tmp / f"hap{hi + 1}.ONT.fa.gz"
+        whole.write_bytes(gzip.compress(b"".join(b">" + n.encode() + b" some comment\n" + s + b"\n" for n, s in reads), compresslevel=1))
+        outs = [str(tmp / f"split_hap{hi + 1}_{i + 1}-of-{case['nchunks']}.fq.gz") for i in range(case["nchunks"])]
+        assert cli.main(["split_ont", "--reads", str(whole), "--out", *outs]) == 0
+        chunks[hi] = outs
+        first = gio.read_fastx(outs[0])
+        assert [n for n, _ in first] == [n for n, _ in reads[0::case["nchunks"]]]
+        assert gzip.open(outs[1]).read().split(b"\n")[3] == b"#" * len(reads[1][1])
+    outdir = tmp / "results_split"
+    assert cli.main(["fused", "--k", str(case["k"]), "--hap1-asm", j1["asm"][0], "--hap2-asm", j1["asm"][1], "--hap1-reads", *chunks[0],
+                     "--hap2-reads", *chunks[1], "--outdir", str(outdir)]) == 0
+    _check_final(case, lambda *p: open(os.path.join(outdir, *p)).read())
