@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the run (all batches) is the same for every N; weak: one batch per rank")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary figures of the N = 1 run (2-bit resident reads, s150 k sweep)")
     ap.add_argument("--resident", default="ascii", choices=["ascii", "packed"],
                     help="form of the HBM-resident reads of `value`: ASCII bases (what the reference consumes) or the 2-bit words the "
                          "ingest emits (gvs_fastx_read_packed)")
@@ -384,6 +385,21 @@ def main_b200(args):
                 e2e["from_files"] = ef
             res, iv, gaps = run_step(eng, wl, binds, coll)  # back to the resident state of the run
 
+    # ---- secondary figures (N = 1): the same run with the reads resident as the ingest's 2-bit words, and BASELINE
+    #      configs 3 / 5 (150 Mbp, SUNK_len sweep) ----
+    secondary = None
+    if world == 1 and not args.no_secondary and args.workload == "h3100":
+        secondary = {}
+        try:
+            secondary["resident_2bit"] = measure_packed_resident(args, eng, wl, coll, run_step)
+        except Exception as ex:
+            secondary["resident_2bit"] = dict(error=repr(ex)[:300])
+        try:
+            secondary["s150_k_sweep"] = measure_k_sweep(args, local)
+        except Exception as ex:
+            secondary["s150_k_sweep"] = dict(error=repr(ex)[:300])
+        res, iv, gaps = run_step(eng, wl, binds, coll)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -407,11 +423,84 @@ def main_b200(args):
                        "db_build_ms": wl.meta["db_build_ms"], "stage_ms_per_step_rank0": stage_ms,
                        "parallelism": f"batches of chunk files sharded over {world} GPU(s), SUNK table replicated; 2 collectives per run"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "parity_check": parity_check,
+            "clocks": clocks, "parity_check": parity_check, "secondary": secondary,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_packed_resident(args, eng, wl, coll, run_step, steps=5):
+    """`value` again with every batch resident in HBM as 2-bit words -- the form gvs_fastx_read_packed delivers and
+    cli.run_reads feeds to the GPU (the PACKED instantiation of the probe; 2.9 GB instead of 11.5 GB per batch stream
+    through L2).  Results must equal the ASCII-resident run's."""
+    import torch
+    from gavisunk_b200 import workload as W
+    want, _, _ = run_step(eng, wl, [(lambda e, b=b: W.bind_batch(e, b)) for b in wl.batches], coll)
+    for b in wl.batches:
+        W.pack_batch_on_device(b, drop_ascii=False)
+    binds = [(lambda e, b=b: W.bind_batch(e, b)) for b in wl.batches]
+    try:
+        got, _, _ = run_step(eng, wl, binds, coll)
+        assert got == want, "2-bit resident reads must give the ASCII run's results"
+        run_step(eng, wl, binds, coll)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run_step(eng, wl, binds, coll)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        probe = []
+        eng.run_batches(binds, wl.contig_hap, on_batch=lambda e, b, base: probe.append(e.stage_ms("probe")))
+        bases = sum(b.total_bases for b in wl.batches)
+        return dict(value=bases / (ms * 1e-3) / 1e9, unit=UNIT, ms_per_step=ms, steps=steps, probe_ms_per_launch=float(np.mean(probe)),
+                    note="reads resident as 2-bit words (kmer.encode's byte map; what the ingest emits); identical results")
+    finally:
+        for b in wl.batches:
+            b.words = None
+
+
+def measure_k_sweep(args, device, steps=8):
+    """BASELINE configs 3 and 5: synthetic 150 Mbp x2 assembly + 30x reads (N50 ~50 kb, 4.5 Gbp, one batch), SUNK_len
+    16 / 20 / 24 / 31, reads resident in HBM; one engine per SUNK_len"""
+    import copy
+    import torch
+    from gavisunk_b200.engine import Engine
+    from gavisunk_b200 import workload as W
+    out = {}
+    for k in (16, 20, 24, 31):
+        a2 = copy.copy(args)
+        a2.workload, a2.k, a2.asm_mbp, a2.coverage, a2.batches, a2.resident, a2.scaling = "s150", k, None, None, None, "ascii", "strong"
+        e2 = Engine(k, device=device, stream=torch.cuda.current_stream().cuda_stream)
+        try:
+            w2 = build_workload(a2, e2, 0, 1)
+
+            class _NoColl:
+                allreduce_hist = None
+                gather_forests = None
+            binds = [(lambda e, b=b: W.bind_batch(e, b)) for b in w2.batches]
+            for _ in range(3):
+                r2, _, _ = run_step(e2, w2, binds, _NoColl)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                run_step(e2, w2, binds, _NoColl)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            bases = sum(b.total_bases for b in w2.batches)
+            ns, ng = e2.db_size()
+            out[f"k{k}"] = dict(value=bases / (ms * 1e-3) / 1e9, unit=UNIT, ms_per_step=ms, read_gbp=bases / 1e9, n_sunks=ns, n_groups=ng,
+                                rows=r2["rows"], probe_ms=e2.stage_ms("probe"), db_build_ms=w2.meta["db_build_ms"])
+            del w2, binds
+        finally:
+            e2.close()
+            torch.cuda.empty_cache()
+    out["workload"] = WORKLOADS["s150"]["desc"]
+    return out
 
 
 def measure_e2e(args, eng, wl, coll, dev, world, rank, numa, barrier, allmax, allsum):

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "gvs_pairs_get": (C.c_int, [vp, vp, vp, vp, vp]),
     "gvs_components_local": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     "gvs_components_merge": (C.c_int, [vp, vp]),
+    "gvs_components_merge_all": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32]),
     "gvs_intervals": (C.c_int, [vp, u64p]),
     "gvs_intervals_get": (C.c_int, [vp, vp, vp, vp]),
     "gvs_intervals_set": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint32]),

@@ -329,7 +329,9 @@ __host__ __device__ __forceinline__ u32 gvs_fp_bit(u32 hb) { return (hb * 0x85EB
 // this (K-J+1)-mer a sub-mer of any SUNK" from L2, so that only the window groups that pass (a few % for
 // a 150 Mbp database, ~20 % for a whole genome whose 1.4e8 sub-mers saturate the 64 MiB that L2 can hold)
 // go on to hash their windows and fetch their 16-byte block.
-__host__ __device__ __forceinline__ u32 gvs_p1_word(u32 hb, u32 mask) { return ((hb * 0x9E3779B1u) >> 7) & mask; }
+// (any number of words: multiply-shift range reduction of a re-mixed hash, so that the filter can be sized to what stays
+// resident in L2 instead of to a power of two)
+__host__ __device__ __forceinline__ u32 gvs_p1_word(u32 hb, u32 n_words) { return (u32)(((u64)(hb * 0x9E3779B1u) * n_words) >> 32); }
 __host__ __device__ __forceinline__ u32 gvs_p1_bits(u32 hb) { return (1u << (hb & 31)) | (1u << ((hb >> 5) & 31)); }
 // reverse complement of an L-mer in 2-bit big-endian packing
 __host__ __device__ __forceinline__ u64 gvs_revcomp(u64 x, int L) {

@@ -55,6 +55,27 @@ __global__ void __launch_bounds__(256) k_comp_merge(const u32* __restrict__ peer
   present[p] = 1;
   guf_union(par, (u32)g, p);
 }
+// forest -> every entry points at its root (depth 1): what the peers receive, and what makes their merge cheap
+__global__ void __launch_bounds__(256) k_comp_flatten(u32* par, u64 ng) {
+  u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  u32 r = guf_find(par, (u32)g);
+  if (par[g] != r) par[g] = r;  // (only ever moves an entry higher up its own tree)
+}
+// all peers' forests in one pass: gathered[r * ng + g] = parent of g on rank r
+__global__ void __launch_bounds__(256) k_comp_merge_all(const u32* __restrict__ gathered, u32 n_ranks, u32 own, u64 ng, u32* par,
+                                                        u8* present) {
+  u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  for (u32 r = 0; r < n_ranks; r++) {
+    if (r == own) continue;
+    u32 p = __ldg(gathered + (u64)r * ng + g);
+    if (p == (u32)g || p >= ng) continue;
+    present[g] = 1;
+    present[p] = 1;
+    guf_union(par, (u32)g, p);
+  }
+}
 __global__ void __launch_bounds__(256) k_comp_stats(u32* par, const u8* __restrict__ present, u64 ng,
                                                     const u32* __restrict__ grp_start, u32* cnt, u32* mn, u32* mx) {
   u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,9 +119,23 @@ extern "C" int gvs_components_local(gvs_ctx* ctx, int accumulate, uint32_t** par
   if (n > 1)
     LAUNCH(k_comp_pairs, (unsigned)cdiv(n, 256), 256, 0, ctx->pair_read.as<u32>(), ctx->pair_gidx.as<u32>(), n,
            ctx->parent.as<u32>(), ctx->present.as<u8>());
+  // entries point straight at their roots: the array that crosses GPUs is a depth-1 forest
+  if (n > 1 || accumulate) LAUNCH(k_comp_flatten, (unsigned)cdiv(ctx->n_groups ? ctx->n_groups : 1, 256), 256, 0, ctx->parent.as<u32>(), ctx->n_groups);
   ctx->comp_ready = true;
   ctx->iv_ready = false;
   if (parent_dev) *parent_dev = ctx->parent.as<u32>();
+  return 0;
+}
+
+extern "C" int gvs_components_merge_all(gvs_ctx* ctx, const uint32_t* gathered_dev, uint32_t n_ranks, uint32_t own_rank) {
+  if (!ctx || !gathered_dev) return GVS_E_ARG;
+  if (!ctx->comp_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_components_merge_all before gvs_components_local");
+  CK(cudaSetDevice(ctx->device));
+  StageTimer tm(ctx, GVS_ST_INTERVALS);
+  u64 ng = ctx->n_groups;
+  if (ng && n_ranks > 1)
+    LAUNCH(k_comp_merge_all, (unsigned)cdiv(ng, 256), 256, 0, gathered_dev, n_ranks, own_rank, ng, ctx->parent.as<u32>(), ctx->present.as<u8>());
+  ctx->iv_ready = false;
   return 0;
 }
 

@@ -141,7 +141,7 @@ struct Probe2Params {
   const u32* __restrict__ filt;
   u32 filt_mask;
   const u32* __restrict__ filt1;  // presence filter of the sub-mers
-  u32 filt1_mask;
+  u32 filt1_words;  // presence filter size in 32-bit words (any number)
   TabView tab;
   u32* hit_read;  // hit records (first hit of a run on one group + number of followers), see common.cuh
   u32* hit_w;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           hbv[g] = gvs_bhash(sf < sr ? sf : sr);
           const u32 gm = (1u << J) - 1;
           const bool any_valid = ((inval >> (J * g)) & gm) != gm;
-          w1[g] = any_valid ? p_ldg_u32(P.filt1 + gvs_p1_word(hbv[g], P.filt1_mask), pol_keep) : 0u;
+          w1[g] = any_valid ? p_ldg_u32(P.filt1 + gvs_p1_word(hbv[g], P.filt1_words), pol_keep) : 0u;
         }
 #pragma unroll
         for (int g = 0; g < NG; g++)  // both bits of gvs_p1_bits(hb) set in the word (the funnel shift wraps mod 32)
@@ -735,7 +735,7 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   P.filt = ctx->filt.as<u32>();
   P.filt_mask = (u32)(ctx->filt_words - 1);
   P.filt1 = ctx->filt1.as<u32>();
-  P.filt1_mask = (u32)(ctx->filt1_words - 1);
+  P.filt1_words = (u32)ctx->filt1_words;
   P.blk_stream = ctx->filt_words * 16 > (32ull << 20) ? 1u : 0u;
   P.tab.keys = ctx->tab_keys.as<u64>();
   P.tab.val = ctx->tab_gidx.as<u64>();

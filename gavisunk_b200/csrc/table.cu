@@ -29,7 +29,7 @@ __global__ void k_tab_mark_db(const u64* __restrict__ kmer, u64 n, u64* keys, u3
   }
 }
 __global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slots, u32* filt, u64 filt_blocks, int k,
-                               u32* filt1, u32 filt1_mask, int fp_layout) {
+                               u32* filt1, u32 filt1_words, int fp_layout) {
   const int J = GVS_FJ(k), L = k - J + 1;
   const u64 lmask = (L >= 32) ? ~0ull : ((1ull << (2 * L)) - 1);
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
@@ -49,7 +49,7 @@ __global__ void k_tab_finalize(const u64* __restrict__ keys, u32* rows, u64 slot
       u64 rc = gvs_revcomp(sub, L);
       u32 hb = gvs_bhash(sub < rc ? sub : rc);
       u64 blk = hb & (filt_blocks - 1);
-      atomicOr(&filt1[gvs_p1_word(hb, filt1_mask)], gvs_p1_bits(hb));
+      atomicOr(&filt1[gvs_p1_word(hb, filt1_words)], gvs_p1_bits(hb));
       atomicOr(&filt[4 * blk + 0], 1u << (h & 31));
       atomicOr(&filt[4 * blk + 1], 1u << ((h >> 5) & 31));
       atomicOr(&filt[4 * blk + 2], 1u << ((h >> 10) & 31));
@@ -125,6 +125,10 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
       int l2 = atoi(e);
       if (l2 >= 10 && l2 <= 28) w1 = 1ull << l2;
     }
+    if (const char* e = getenv("GVS_EXP_FILT1_MIB")) {  // experiments: presence filter size in MiB (any value)
+      int mib = atoi(e);
+      if (mib >= 1 && mib <= 1024) w1 = (u64)mib << 18;
+    }
     ctx->filt1_words = w1;
     CKR(gvs_reserve(ctx, ctx->filt1, w1 * 4));
     LAUNCH(k_fill_u32, grid_for(ctx, w1, 256), 256, 0, ctx->filt1.as<u32>(), w1, 0u);
@@ -141,7 +145,7 @@ int gvs_tab_build_impl(gvs_ctx* ctx, const u64* d_db_kmer, u64 n_db) {
     LAUNCH(k_tab_mark_db, grid_for(ctx, n_loc, 256), 256, 0, ctx->loc_kmer.as<u64>(), n_loc, keys, rows, slots);
   }
   LAUNCH(k_tab_finalize, grid_for(ctx, slots, 256), 256, 0, keys, rows, slots, ctx->filt.as<u32>(), fw, ctx->k,
-         ctx->filt1.as<u32>(), (u32)(ctx->filt1_words - 1), ctx->filt_fp ? 1 : 0);
+         ctx->filt1.as<u32>(), (u32)ctx->filt1_words, ctx->filt_fp ? 1 : 0);
   return 0;
 }
 

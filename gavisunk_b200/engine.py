@@ -402,8 +402,7 @@ class Engine:
         self.validate(min_read_len)
         pp = self.components_local()
         if gather_forests is not None:
-            for peer in gather_forests(pp, self.db_groups()):
-                self.components_merge(peer)
+            self._merge_forests(gather_forests, pp)
         return self.intervals()
 
     # ------------------------------------------------------------------------------------
@@ -460,8 +459,7 @@ class Engine:
         self.validate(min_read_len)
         pp = self.components_local()
         if gather_forests is not None:
-            for peer in gather_forests(pp, self.db_groups()):
-                self.components_merge(peer)
+            self._merge_forests(gather_forests, pp)
         return self.intervals(), bases
 
     def db_groups(self) -> int:
@@ -536,6 +534,19 @@ class Engine:
 
     def components_merge(self, peer_parent_ptr: int):
         self._ck(self.lib.gvs_components_merge(self.ctx, C.c_void_p(peer_parent_ptr)))
+
+    def components_merge_all(self, gathered_ptr: int, n_ranks: int, own_rank: int):
+        """unions in every peer's forest in one pass (gathered = [n_ranks][n_groups] parent arrays on this device)"""
+        self._ck(self.lib.gvs_components_merge_all(self.ctx, C.c_void_p(gathered_ptr), int(n_ranks), int(own_rank)))
+
+    def _merge_forests(self, gather_forests, pp):
+        peers = gather_forests(pp, self.db_groups())
+        if isinstance(peers, tuple):  # (pointer of the gathered [n_ranks][n_groups] array, n_ranks, own rank)
+            if peers[1] > 1:
+                self.components_merge_all(*peers)
+        else:
+            for peer in peers:
+                self.components_merge(peer)
 
     def intervals(self) -> Dict[str, np.ndarray]:
         """process-by-contig_lowmem_AR.py:215-260 -> rows of bed_files/*.bed."""

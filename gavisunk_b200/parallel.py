@@ -170,6 +170,7 @@ class EngineExchange:
         if self.x.world == 1 or not n_groups:
             return []
         self._before()
-        peers = self.x.gather_forests(alias_device_array(ptr, n_groups, "<i4", self.device))
+        self.x.gather_forests(alias_device_array(ptr, n_groups, "<i4", self.device))
         self._after()
-        return [int(p.data_ptr()) for p in peers]
+        # the gathered [world][n_groups] array itself: Engine unions all peers in one pass (gvs_components_merge_all)
+        return int(self.x._keep.data_ptr()), self.x.world, self.x.rank

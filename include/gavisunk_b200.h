@@ -323,6 +323,9 @@ int gvs_pairs_get(gvs_ctx* ctx, uint32_t* read_idx, uint32_t* contig, uint32_t* 
  * peer's forest (device pointer, e.g. an all-gathered copy), gvs_intervals finalises. */
 int gvs_components_local(gvs_ctx* ctx, int accumulate, uint32_t** parent_dev);
 int gvs_components_merge(gvs_ctx* ctx, const uint32_t* peer_parent_dev);
+/* All peers at once: gathered_dev = the all-gathered parent arrays, rank r's at gathered_dev + r * n_groups (own_rank's
+ * slice is skipped).  One pass over the groups instead of one launch per peer. */
+int gvs_components_merge_all(gvs_ctx* ctx, const uint32_t* gathered_dev, uint32_t n_ranks, uint32_t own_rank);
 /* validated intervals (contig, min group, max group) of components with >= 3 groups, sorted by
  * (contig, start) = rows of bed_files/{contig}_{hap}.bed */
 int gvs_intervals(gvs_ctx* ctx, uint64_t* n_intervals);
