@@ -141,19 +141,53 @@ __global__ void __launch_bounds__(VOTE_WARPS * 32) k_cand_vote_warp(const u32* _
   if (tid < 4) s_med[grp][tid] = 0;
   __syncwarp();
   const u32 lo = (cnt - 1) >> 1;
-  for (u32 i = tid; i < cnt; i += 32) {
-    const i64 a0 = n0[i], a1 = n1[i];
-    u32 r0 = 0, r1 = 0;
-    for (u32 j = 0; j < cnt; j++) {
-      const i64 b0 = n0[j], b1 = n1[j];
-      const bool before = j < i;
-      r0 += (b0 < a0) || (b0 == a0 && before);
-      r1 += (b1 < a1) || (b1 == a1 && before);
+  // A read that follows one strand of its contig has one diagonal sorted along its rows (pos + start for a forward
+  // read, start - pos for a reverse one) and its group ids strictly monotone: the sorted diagonal's median elements are
+  // read off by index, and only the other one (the jittery true diagonal) needs rank counting.
+  bool up0 = true, dn0 = true, up1 = true, dn1 = true, gup = true, gdn = true;
+  for (u32 i = tid; i + 1 < cnt; i += 32) {
+    const i64 x0 = n0[i], y0 = n0[i + 1], x1 = n1[i], y1 = n1[i + 1];
+    const u32 g0 = sg[i], g1 = sg[i + 1];
+    up0 &= x0 <= y0; dn0 &= x0 >= y0;
+    up1 &= x1 <= y1; dn1 &= x1 >= y1;
+    gup &= g0 < g1; gdn &= g0 > g1;
+  }
+  up0 = __all_sync(0xFFFFFFFFu, up0); dn0 = __all_sync(0xFFFFFFFFu, dn0);
+  up1 = __all_sync(0xFFFFFFFFu, up1); dn1 = __all_sync(0xFFFFFFFFu, dn1);
+  const bool groups_distinct = __all_sync(0xFFFFFFFFu, gup) || __all_sync(0xFFFFFFFFu, gdn);
+  const bool sorted0 = up0 || dn0, sorted1 = up1 || dn1;
+  if (tid == 0) {
+    const u32 hi = lo + 1 < cnt ? lo + 1 : lo;  // (rank lo + 1 exists whenever it is used: even cnt)
+    if (sorted0) { s_med[grp][0] = up0 ? n0[lo] : n0[cnt - 1 - lo]; s_med[grp][1] = up0 ? n0[hi] : n0[cnt - 1 - hi]; }
+    if (sorted1) { s_med[grp][2] = up1 ? n1[lo] : n1[cnt - 1 - lo]; s_med[grp][3] = up1 ? n1[hi] : n1[cnt - 1 - hi]; }
+  }
+  if (!sorted0 || !sorted1) {
+    for (u32 i = tid; i < cnt; i += 32) {
+      const i64 a0 = n0[i], a1 = n1[i];
+      u32 r0 = 0, r1 = 0;
+      if (!sorted0 && !sorted1) {
+        for (u32 j = 0; j < cnt; j++) {
+          const i64 b0 = n0[j], b1 = n1[j];
+          const bool before = j < i;
+          r0 += (b0 < a0) || (b0 == a0 && before);
+          r1 += (b1 < a1) || (b1 == a1 && before);
+        }
+      } else if (!sorted0) {
+        for (u32 j = 0; j < cnt; j++) {
+          const i64 b0 = n0[j];
+          r0 += (b0 < a0) || (b0 == a0 && j < i);
+        }
+      } else {
+        for (u32 j = 0; j < cnt; j++) {
+          const i64 b1 = n1[j];
+          r1 += (b1 < a1) || (b1 == a1 && j < i);
+        }
+      }
+      if (!sorted0 && r0 == lo) s_med[grp][0] = a0;
+      if (!sorted0 && r0 == lo + 1) s_med[grp][1] = a0;
+      if (!sorted1 && r1 == lo) s_med[grp][2] = a1;
+      if (!sorted1 && r1 == lo + 1) s_med[grp][3] = a1;
     }
-    if (r0 == lo) s_med[grp][0] = a0;
-    if (r0 == lo + 1) s_med[grp][1] = a0;
-    if (r1 == lo) s_med[grp][2] = a1;
-    if (r1 == lo + 1) s_med[grp][3] = a1;
   }
   __syncwarp();
   i64 med[2];
@@ -180,10 +214,12 @@ __global__ void __launch_bounds__(VOTE_WARPS * 32) k_cand_vote_warp(const u32* _
   for (u32 i = tid; i < cnt; i += 32) {
     const u32 f = sf[i];
     if (!f) continue;
-    const u32 gi = sg[i];
     u32 seen = 0;  // orientations in which an earlier in-band row already carries this group
-    for (u32 j = 0; j < i; j++)
-      if (sg[j] == gi) seen |= sf[j];
+    if (!groups_distinct) {
+      const u32 gi = sg[i];
+      for (u32 j = 0; j < i; j++)
+        if (sg[j] == gi) seen |= sf[j];
+    }
     good0 += (f & ~seen) & 1u;
     good1 += ((f & ~seen) >> 1) & 1u;
   }
@@ -217,19 +253,46 @@ __global__ void __launch_bounds__(NT) k_cand_vote(const u32* __restrict__ cand_r
     const u32 cnt = row_cnt[cand_row[ci]];
     const u32 o = cand_voff[ci];
     u32 good2[2] = {0, 0};
+    // strictly monotone group ids are all distinct: the duplicate scan of the band count is not needed then
+    bool gup = true, gdn = true;
+    for (u32 i = tid; i + 1 < cnt; i += NT) {
+      const u32 g0 = v_group[o + i], g1 = v_group[o + i + 1];
+      gup &= g0 < g1;
+      gdn &= g0 > g1;
+    }
+    const bool groups_distinct = __syncthreads_and(gup) || __syncthreads_and(gdn);
     for (int orient = 0; orient < 2; orient++) {  // 0: reverse (pos + start), 1: forward (start - pos)
       if (tid == 0) { s_alo = 0; s_ahi = 0; s_good = 0; }
       __syncthreads();
       const u32 lo = (cnt - 1) >> 1;
-      for (u32 i = tid; i < cnt; i += NT) {
-        i64 ni = orient == 0 ? (i64)v_start[o + i] + (i64)v_pos[o + i] : (i64)v_start[o + i] - (i64)v_pos[o + i];
-        u32 rank = 0;
-        for (u32 j = 0; j < cnt; j++) {
-          i64 nj = orient == 0 ? (i64)v_start[o + j] + (i64)v_pos[o + j] : (i64)v_start[o + j] - (i64)v_pos[o + j];
-          rank += (nj < ni) || (nj == ni && j < i);
+      auto val = [&](u32 i) -> i64 {
+        return orient == 0 ? (i64)v_start[o + i] + (i64)v_pos[o + i] : (i64)v_start[o + i] - (i64)v_pos[o + i];
+      };
+      // a diagonal that is sorted along the rows (the one across the read's strand) gives its median elements by index
+      bool up = true, dn = true;
+      for (u32 i = tid; i + 1 < cnt; i += NT) {
+        const i64 x = val(i), y = val(i + 1);
+        up &= x <= y;
+        dn &= x >= y;
+      }
+      const bool is_up = __syncthreads_and(up), is_dn = __syncthreads_and(dn);
+      if (is_up || is_dn) {
+        if (tid == 0) {
+          const u32 hi = lo + 1 < cnt ? lo + 1 : lo;
+          s_alo = is_up ? val(lo) : val(cnt - 1 - lo);
+          s_ahi = is_up ? val(hi) : val(cnt - 1 - hi);
         }
-        if (rank == lo) s_alo = ni;
-        if (rank == lo + 1) s_ahi = ni;
+      } else {
+        for (u32 i = tid; i < cnt; i += NT) {
+          const i64 ni = val(i);
+          u32 rank = 0;
+          for (u32 j = 0; j < cnt; j++) {
+            const i64 nj = val(j);
+            rank += (nj < ni) || (nj == ni && j < i);
+          }
+          if (rank == lo) s_alo = ni;
+          if (rank == lo + 1) s_ahi = ni;
+        }
       }
       __syncthreads();
       // arraymancer percentile(n, 50): linear interpolation in float64, then int() truncation
@@ -247,7 +310,7 @@ __global__ void __launch_bounds__(NT) k_cand_vote(const u32* __restrict__ cand_r
         if (dv >= BANDWIDTH) continue;
         u32 gi = v_group[o + i];
         bool dup = false;
-        for (u32 j = 0; j < i && !dup; j++) {
+        for (u32 j = 0; j < i && !dup && !groups_distinct; j++) {
           if (v_group[o + j] != gi) continue;
           i64 nj = orient == 0 ? (i64)v_start[o + j] + (i64)v_pos[o + j] : (i64)v_start[o + j] - (i64)v_pos[o + j];
           i64 dj = nj - med;

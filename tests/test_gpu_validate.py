@@ -160,3 +160,69 @@ def test_rows_set_rejects_rows_outside_the_tables():
     with pytest.raises(GavisunkError, match="contig"):
         eng.set_rows(1, [0, 1], [1, 2], [0, 2], [10, 20], [10, 20], n_contigs=2)
     eng.set_rows(1, [0, 1], [1, 2], [0, 1], [10, 20], [10, 20], n_contigs=2)
+
+
+def _rows_case(rng, m, kind):
+    """rows of ONE read on one contig (read pos, assembly start, ID) shaped to hit the branches of k_validate: reads that
+    follow one strand (positions monotone along the starts -> the first-partner search), with jitter small or large
+    against short distances, equal positions / equal starts, outliers off the diagonal, repeated IDs"""
+    gaps = rng.integers(15, 3000, m)
+    start = 10_000 + np.cumsum(gaps)
+    if kind in ("fwd", "fwd_jitter", "fwd_ties", "fwd_outlier", "fwd_dupid", "sparse_links"):
+        pos = 500 + (start - start[0]) + rng.integers(-3, 4, m).cumsum()
+    else:
+        pos = 5_000_000 - (start - start[0]) + rng.integers(-3, 4, m).cumsum()
+    if kind.endswith("jitter"):
+        pos = pos + rng.integers(-40, 41, m)           # breaks short-range pairs, may break monotonicity
+    if kind == "fwd_ties":
+        j = rng.choice(m - 1, max(1, m // 8), replace=False)
+        pos[j + 1] = pos[j]                            # equal positions, different starts: never a passing pair
+    if kind == "fwd_outlier":
+        j = rng.choice(m, max(1, m // 10), replace=False)
+        pos[j] += rng.integers(20_000, 2_000_000, len(j)) * rng.choice([-1, 1], len(j))
+    if kind == "sparse_links":
+        pos = 500 + ((start - start[0]) * 1.3).astype(np.int64)   # ratio 1.3: no pair passes ...
+        k = rng.choice(m, min(m, max(3, m // 3)), replace=False)
+        pos[k] = 500 + (start[k] - start[0])                        # ... except among these rows
+    pos = np.maximum(pos, 0)
+    ids = start.copy()
+    if kind == "fwd_dupid" and m > 3:
+        j = rng.choice(m - 2, max(1, m // 12), replace=False)
+        ids[j + 2] = ids[j]                            # the same group again two rows later (Q5, multipos clean-up)
+    order = np.argsort(pos, kind="stable")             # a read's rows come in increasing read position
+    return [("rd", int(pos[i]), "c1", int(start[i]), int(ids[i])) for i in order]
+
+
+@pytest.mark.parametrize("kind", ["fwd", "rev", "fwd_jitter", "rev_jitter", "fwd_ties", "fwd_outlier", "fwd_dupid", "sparse_links"])
+def test_validate_shaped_reads_against_oracle(kind):
+    """per-read validation of hand-shaped reads in all three row-count tiers against the oracle's restatement of
+    process-by-contig_lowmem_AR.py:136-198 (pairs in vertex order, then the contig's intervals)"""
+    from gavisunk_b200.engine import Engine
+    rng = np.random.default_rng(sum(map(ord, kind)))
+    sizes = [2, 3, 5, 17, 33, 64, 65, 100, 257, 512, 513, 700]
+    reads, all_rows, rlen = [], [], {}
+    for ri, m in enumerate(sizes * 3):
+        rows = _rows_case(rng, m, kind)
+        name = f"r{ri:04d}"
+        # every read on its own stretch of the contig, so that the contig-wide components keep them apart
+        shift = ri * 20_000_000
+        rows = [(name, p, c, s + shift, g + shift) for _, p, c, s, g in rows]
+        all_rows += rows
+        rlen[name] = max(p for _, p, _, _, _ in rows) + 10_000
+    inter, bed = O.process_by_contig(all_rows, rlen, set(), "c1", minlen=10000)
+    eng = Engine(20)
+    eng.contig_names = ["c1"]
+    names = sorted(rlen)
+    ridx = {n: i for i, n in enumerate(names)}
+    eng.set_reads_meta(np.array([min(rlen[n], 0xFFFFFFFF) for n in names], np.uint32))
+    eng.set_rows(1, [ridx[r[0]] for r in all_rows], [r[1] for r in all_rows], np.zeros(len(all_rows), np.uint32),
+                 [r[3] for r in all_rows], [r[4] for r in all_rows], n_contigs=1)
+    eng.set_contigs([0])
+    eng.validate(10000)
+    p = eng.pairs()
+    got = [(int(g), names[int(r)]) for g, r in zip(p["group"], p["read"])]
+    assert got == (inter or []), kind
+    eng.components_local()
+    iv = eng.intervals()
+    assert [("c1", int(s), int(e)) for s, e in zip(iv["start"], iv["end"])] == (bed or []), kind
+    assert len(got) > 100
