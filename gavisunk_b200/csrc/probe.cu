@@ -214,9 +214,10 @@ __device__ __forceinline__ u32 p_tile_bytes(u64 tile, u64 total) {
   const u64 r = have - b0;
   return r >= unit ? (u32)unit : (u32)((r + 15) & ~15ull);
 }
-template <bool PACKED>
+// FULL: the caller knows that the tile lies entirely inside the batch (every tile of a span but the batch's last few)
+template <bool PACKED, bool FULL = false>
 __device__ __forceinline__ void p_stage_issue(WarpSmem& sm, const u8* __restrict__ seq, u64 tile, u64 total, int lane, u64 pol) {
-  const u32 bytes = p_tile_bytes<PACKED>(tile, total);
+  const u32 bytes = FULL ? (PACKED ? PW_TILE / 4 : PW_TILE) : p_tile_bytes<PACKED>(tile, total);
   if (lane == 0 && bytes) {
     const u32 bar = p_smem_addr(&sm.bar), dst = p_smem_addr(&sm.raw[0]);
     const u8* src = seq + tile * (PACKED ? PW_TILE / 4 : PW_TILE);
@@ -231,8 +232,24 @@ __device__ __forceinline__ void p_stage_issue(WarpSmem& sm, const u8* __restrict
 }
 // wait for the tile's bytes and pack them into ring slot `rb` (forward + reverse complement); `phase` is the
 // warp's barrier phase (flips whenever a copy was waited for)
-template <bool PACKED>
+template <bool PACKED, bool FULL = false>
 __device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, u64 tile, u64 total, int lane, u32& phase) {
+  if (FULL) {
+    p_bar_wait(&sm.bar, phase);
+    phase ^= 1u;
+    u32 w;
+    if (PACKED) {
+      w = ((const u32*)sm.raw)[lane];
+    } else {
+      const uint4 v = sm.raw[lane];
+      u32 bad = 0;
+      w = p_pack16_be_fast(v, bad);
+      if (__any_sync(0xFFFFFFFFu, bad != 0)) w = p_pack16_be(v);  // N runs, U, control bytes: the exact byte map
+    }
+    sm.fw[(rb + lane) & 63] = w;
+    sm.rc[(rb + lane) & 63] = p_rc16(w);
+    return;
+  }
   const u32 bytes = p_tile_bytes<PACKED>(tile, total);
   if (bytes) {
     p_bar_wait(&sm.bar, phase);
@@ -322,12 +339,15 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
     p_stage_finish<PACKED>(sm, 32, tile0 + 1, P.total, lane, phase);
     __syncwarp();
 
+    // all tiles this span stages (its own and the two prefetched past its end) lie entirely inside the batch: no tail handling
+    const bool span_full = (tile_end + 2) * PW_TILE <= P.total;
     u32 wcount = 0;  // hits of this span so far
     for (u64 tile = tile0; tile < tile_end; tile++) {
       const u64 ts = tile * PW_TILE;
       const u32 rb = (u32)((tile - tile0) & 1) * 32;  // ring base of this tile
       // prefetch tile T+2 (lands in sm.raw while this tile is processed)
-      p_stage_issue<PACKED>(sm, P.seq, tile + 2, P.total, lane, pol_stream);
+      if (span_full) p_stage_issue<PACKED, true>(sm, P.seq, tile + 2, P.total, lane, pol_stream);
+      else p_stage_issue<PACKED>(sm, P.seq, tile + 2, P.total, lane, pol_stream);
 
       // ---- read boundaries in (ts, ts + 512 + K - 2] ----
       const u64 limit = ts + PW_TILE + (K > 1 ? K - 1 : 1);
@@ -668,7 +688,8 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
       }
       // ---- tile T is done: its ring slot receives tile T+2 ----
       __syncwarp();
-      p_stage_finish<PACKED>(sm, rb, tile + 2, P.total, lane, phase);
+      if (span_full) p_stage_finish<PACKED, true>(sm, rb, tile + 2, P.total, lane, phase);
+      else p_stage_finish<PACKED>(sm, rb, tile + 2, P.total, lane, phase);
       __syncwarp();
     }
     if (lane == 0) P.warp_cnt[region] = wcount;
