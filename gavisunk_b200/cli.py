@@ -699,6 +699,10 @@ def write_outputs(k, eng, results, contig_len, contig_hap, names, iv, gaps, noda
         os.makedirs(d(sub), exist_ok=True)
     ctab = gio.NameTable(names)
     safe = lambda n: n.replace("#", "_")
+    jobs = []  # (path, columns, options): formatted and written by a small pool at the end (the files are independent)
+
+    def emit(path, cols, **kw):
+        jobs.append((path, cols, kw))
     # ---- run-wide read table: devices in order, batches in order ----
     read_base, nreads = [], 0
     for r in results:
@@ -735,9 +739,9 @@ def write_outputs(k, eng, results, contig_len, contig_hap, names, iv, gaps, noda
             # mrsfast reports a k-mer that is its own reverse complement on both strands: two identical rows
             pal = db["kmer"] == revcomp_kmers(db["kmer"], k)
             loc_sel = np.repeat(np.arange(len(pal), dtype=np.uint64), 1 + pal.astype(np.int64))
-        _write_bytes(d("db", "jellyfish.db"), gio.format_rows([("kmer", db["kmer"], k)]))
-        _write_bytes(d("db", "jellyfish.fa"), gio.format_rows([("kmer", db["kmer"], k, dict(prefix=b">", sep=b"\n")), ("kmer", db["kmer"], k)]))
-        _write_bytes(d("mrsfast", "kmer.loc"), gio.format_rows(loc_cols, sel=loc_sel))
+        emit(d("db", "jellyfish.db"), [("kmer", db["kmer"], k)])
+        emit(d("db", "jellyfish.fa"), [("kmer", db["kmer"], k, dict(prefix=b">", sep=b"\n")), ("kmer", db["kmer"], k)])
+        emit(d("mrsfast", "kmer.loc"), loc_cols, sel=loc_sel)
     # ---- per-haplotype row files (combine_ont, combine_ont_nofilt, read_lengths) ----
     khap = read_hap[kept["read"]] if len(kept["read"]) else np.zeros(0, np.uint8)
     all_reads = np.arange(nreads, dtype=np.uint32)
@@ -745,13 +749,13 @@ def write_outputs(k, eng, results, contig_len, contig_hap, names, iv, gaps, noda
         rows0 = cat_rows("rows0", ("read", "pos", "contig", "start", "group"))
         r0hap = read_hap[rows0["read"]] if len(rows0["read"]) else np.zeros(0, np.uint8)
     for hap in range(2):
-        _write_bytes(d("sunkpos", f"hap{hap + 1}.sunkpos"), gio.format_rows(sunk_cols(kept), sel=np.flatnonzero(khap == hap)))
-        _write_bytes(d("sunkpos", f"hap{hap + 1}.rlen"), gio.format_rows([("name", all_reads, rtab), ("u32", lens)], sel=np.flatnonzero(read_hap == hap)))
+        emit(d("sunkpos", f"hap{hap + 1}.sunkpos"), sunk_cols(kept), sel=np.flatnonzero(khap == hap))
+        emit(d("sunkpos", f"hap{hap + 1}.rlen"), [("name", all_reads, rtab), ("u32", lens)], sel=np.flatnonzero(read_hap == hap))
         if detailed:  # unfiltered rows for plot_detailed (viz_detailed.py:48)
-            _write_bytes(d("sunkpos", f"hap{hap + 1}_detailed.sunkpos"), gio.format_rows(sunk_cols(rows0), sel=np.flatnonzero(r0hap == hap)))
+            emit(d("sunkpos", f"hap{hap + 1}_detailed.sunkpos"), sunk_cols(rows0), sel=np.flatnonzero(r0hap == hap))
     gtab = eng.groups()
     bad = eng.bad_list()
-    _write_bytes(d("sunkpos", "bad_sunks.txt"), gio.format_rows([("name", gtab["contig"][bad], ctab, dict(sep=b":")), ("u32", gtab["group"][bad])]))
+    emit(d("sunkpos", "bad_sunks.txt"), [("name", gtab["contig"][bad], ctab, dict(sep=b":")), ("u32", gtab["group"][bad])])
     # ---- per-contig files: breaks/*.sunkpos|.loc (split_locs.py:5-22), inter_outs/*.tsv, bed_files/*.bed ----
     def by_contig(col, read=None, rank=None):
         """row indices per contig, in row order (rank given: by rank[read] first, stable).  Rows come in runs of one
@@ -788,17 +792,17 @@ def write_outputs(k, eng, results, contig_len, contig_hap, names, iv, gaps, noda
     iv_c = by_contig(iv["contig"])
     for c, idx in kept_c.items():
         stem = f"{safe(names[c])}_hap{contig_hap[c] + 1}"
-        _write_bytes(d("breaks", stem + ".sunkpos"), gio.format_rows(sunk_cols(kept), sel=idx))
+        emit(d("breaks", stem + ".sunkpos"), sunk_cols(kept), sel=idx)
         if c in loc_c:
             sel = loc_c[c]
             if loc_sel is not None:
                 sel = np.repeat(sel, 1 + (db["kmer"][sel] == revcomp_kmers(db["kmer"][sel], k)).astype(np.int64))
-            _write_bytes(d("breaks", stem + ".loc"), gio.format_rows(loc_cols, sel=sel))
+            emit(d("breaks", stem + ".loc"), loc_cols, sel=sel)
         if c in pair_c:
             pidx = pair_c[c]
-            _write_bytes(d("inter_outs", stem + ".tsv"), gio.format_rows([("u32", pairs["group"]), ("name", pairs["read"], rtab)], sel=pidx))
-            _write_bytes(d("bed_files", stem + ".bed"), gio.format_rows([("name", iv["contig"], ctab), ("u32", iv["start"]), ("u32", iv["end"])],
-                                                                    sel=iv_c.get(c, np.zeros(0, np.uint64))))
+            emit(d("inter_outs", stem + ".tsv"), [("u32", pairs["group"]), ("name", pairs["read"], rtab)], sel=pidx)
+            emit(d("bed_files", stem + ".bed"), [("name", iv["contig"], ctab), ("u32", iv["start"]), ("u32", iv["end"])],
+                                                                    sel=iv_c.get(c, np.zeros(0, np.uint64)))
         else:  # "no usable reads": contig name only, bed touched empty by the rule (tagONT.smk:190)
             _write_bytes(d("inter_outs", stem + ".tsv"), (names[c] + "\n").encode("latin-1"))
             _write_bytes(d("bed_files", stem + ".bed"), b"")
@@ -808,13 +812,20 @@ def write_outputs(k, eng, results, contig_len, contig_hap, names, iv, gaps, noda
         hn = hap + 1
         open(d("breaks", f"hap{hn}_splits_pos.done"), "a").close()  # touch() of the checkpoint (tagONT.smk:158)
         bed3 = lambda t: [("name", t["contig"], ctab), ("u32", t["start"]), ("u32", t["end"])]
-        _write_bytes(d("final_out", f"hap{hn}.valid.bed"), gio.format_rows(bed3(iv), sel=np.flatnonzero(chap[iv["contig"]] == hap)))
+        emit(d("final_out", f"hap{hn}.valid.bed"), bed3(iv), sel=np.flatnonzero(chap[iv["contig"]] == hap))
         gsel = np.flatnonzero(chap[gaps["contig"]] == hap)
-        _write_bytes(d("final_out", f"hap{hn}.gaps.bed"), gio.format_rows(bed3(gaps), sel=gsel))
+        emit(d("final_out", f"hap{hn}.gaps.bed"), bed3(gaps), sel=gsel)
         nd = nodata[chap[nodata] == hap]
-        _write_bytes(d("final_out", f"hap{hn}.nodata.bed"), gio.format_rows([("name", nd, ctab), ("u32", np.zeros(len(nd), np.uint32)), ("u32", clen[nd])]))
+        emit(d("final_out", f"hap{hn}.nodata.bed"), [("name", nd, ctab), ("u32", np.zeros(len(nd), np.uint32)), ("u32", clen[nd])])
         s2, e2 = eng.slop(gaps["contig"][gsel], gaps["start"][gsel], gaps["end"][gsel], clen, 200000)  # bedtools slop -b 200000 (tagONT.smk:249)
-        _write_bytes(d("final_out", f"hap{hn}.gaps.slop.bed"), gio.format_rows([("name", gaps["contig"][gsel], ctab), ("i64", s2), ("i64", e2)]))
+        emit(d("final_out", f"hap{hn}.gaps.slop.bed"), [("name", gaps["contig"][gsel], ctab), ("i64", s2), ("i64", e2)])
+    from concurrent.futures import ThreadPoolExecutor
+    n_cpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = max(1, min(8, n_cpu // 2))
+    per_job = max(1, n_cpu // workers)
+    jobs.sort(key=lambda j: -(len(j[2]["sel"]) if j[2].get("sel") is not None else len(j[1][0][1])))  # big files first
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        list(ex.map(lambda j: _write_bytes(j[0], gio.format_rows(j[1], threads=per_job, **j[2])), jobs))
 
 
 def cmd_fused(argv):

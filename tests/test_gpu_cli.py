@@ -238,3 +238,39 @@ def test_rule_shims_chain(fused_case):
             assert got[i][:4] == (c, s, e, mg)
             assert got[i][4] == pytest.approx(p, rel=1e-6, abs=1e-15)  # tolerance of BASELINE.json's north_star
             n_gap_rows += 1
+
+
+@pytest.mark.gpu
+def test_fused_palindromic_sunks_option(tmp_path):
+    """a SUNK that is its own reverse complement (even SUNK_len) would be reported by mrsfast on both
+    strands, i.e. twice in kmer.loc.  Unpinned (mrsfast is absent): one row by default, two with --mrsfast-palindromes;
+    nothing downstream changes (every consumer de-duplicates)."""
+    rng = np.random.default_rng(12)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    s1 = alpha[rng.integers(0, 4, 6000)].copy()
+    s1[1000:1008] = np.frombuffer(b"ACGTACGT", np.uint8)  # its own reverse complement
+    s2 = s1.copy()
+    s2[1004] = ord("C")  # (ACGT-A-CGT -> ACGT-C-CGT: the palindrome exists in haplotype 1 only, once)
+    (tmp_path / "h1.fa").write_bytes(b">c1\n" + s1.tobytes() + b"\n")
+    (tmp_path / "h2.fa").write_bytes(b">c2\n" + s2.tobytes() + b"\n")
+    reads = b"".join(b">r%d\n" % i + s1[i * 500:i * 500 + 3000].tobytes() + b"\n" for i in range(6))
+    (tmp_path / "r1.fa").write_bytes(reads)
+    (tmp_path / "r2.fa").write_bytes(reads.replace(b">r", b">q"))
+    outs = {}
+    for flag in (False, True):
+        out = tmp_path / ("pal" if flag else "plain")
+        argv = ["fused", "--k", "8", "--hap1-asm", str(tmp_path / "h1.fa"), "--hap2-asm", str(tmp_path / "h2.fa"), "--hap1-reads",
+                str(tmp_path / "r1.fa"), "--hap2-reads", str(tmp_path / "r2.fa"), "--outdir", str(out)] + (["--mrsfast-palindromes"] if flag else [])
+        assert cli.main(argv) == 0
+        outs[flag] = out
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    loc0 = (outs[False] / "mrsfast" / "kmer.loc").read_text().splitlines()
+    loc1 = (outs[True] / "mrsfast" / "kmer.loc").read_text().splitlines()
+    pal = [l for l in loc0 if l.split("\t")[2] == "".join(comp[c] for c in reversed(l.split("\t")[2]))]
+    assert len(loc0) == len(set(loc0)) and len(pal) >= 1  # default: one row per SUNK
+    exp = []
+    for l in loc0:
+        exp += [l, l] if l in pal else [l]
+    assert loc1 == exp  # palindromes twice, in place
+    for f in ("sunkpos/hap1.sunkpos", "sunkpos/hap2.sunkpos", "final_out/hap1.valid.bed", "final_out/hap1.gaps.bed", "db/jellyfish.db"):
+        assert (outs[False] / f).read_text() == (outs[True] / f).read_text(), f
