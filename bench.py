@@ -278,7 +278,12 @@ def main_b200(args):
         for st in per_batch:
             per_batch[st].clear()
         eng.run_batches(binds, wl.contig_hap, allreduce_hist=coll.allreduce_hist, gather_forests=coll.gather_forests, on_batch=on_batch)
-    phase2 = {st: (eng.stage_ms(st) if wl.batches else 0.0) for st in ("validate", "intervals")}
+    phase2 = {}
+    for st in ("mode", "bad", "validate", "components", "merge", "intervals"):  # the once-per-run stages (merge: N > 1 only)
+        try:
+            phase2[st] = eng.stage_ms(st) if wl.batches else 0.0
+        except Exception:
+            pass
     stage_ms = {st: float(np.sum(v)) for st, v in per_batch.items()}
     stage_ms.update(phase2)
 

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgavisunk_b200.so")
+LIB_PATH = os.environ.get("GVS_LIB_PATH") or os.path.join(_HERE, "libgavisunk_b200.so")  # (the variable: kernel experiments only)
 
 u8p, u32p, u64p, i32p, i64p, f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_double))
 vp = C.c_void_p
@@ -102,7 +102,8 @@ class ColStruct(C.Structure):
 PROTOTYPES["gvs_format_rows"] = (C.c_int64, [C.POINTER(ColStruct), C.c_uint32, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, C.c_int])
 
 GVS_E_KEYERROR = -3
-STAGES = {"probe": 0, "emit": 1, "diag": 2, "hist": 3, "validate": 4, "intervals": 5, "dbbuild": 6}
+STAGES = {"probe": 0, "emit": 1, "diag": 2, "hist": 3, "validate": 4, "intervals": 5, "dbbuild": 6, "components": 7, "mode": 8,
+          "bad": 9, "merge": 10}
 
 _lib = None
 

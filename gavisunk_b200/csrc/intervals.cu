@@ -76,14 +76,31 @@ __global__ void __launch_bounds__(256) k_comp_merge_all(const u32* __restrict__ 
     guf_union(par, (u32)g, p);
   }
 }
+// count / smallest / largest group start per component root.  Neighbouring groups almost always share their root
+// (a component is a run of groups along a contig; at 30x a contig is a handful of components), so the lanes of a
+// warp are combined per distinct root first: one atomic triple per root and warp instead of per group
 __global__ void __launch_bounds__(256) k_comp_stats(u32* par, const u8* __restrict__ present, u64 ng,
                                                     const u32* __restrict__ grp_start, u32* cnt, u32* mn, u32* mx) {
-  u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= ng || !present[g]) return;
-  u32 r = guf_find(par, (u32)g);
-  atomicAdd(&cnt[r], 1u);
-  atomicMin(&mn[r], grp_start[g]);
-  atomicMax(&mx[r], grp_start[g]);
+  const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool act = g < ng && present[g];
+  const u32 r = act ? guf_find(par, (u32)g) : 0xFFFFFFFFu;
+  const u32 s = act ? grp_start[g] : 0u;
+  u32 todo = __ballot_sync(0xFFFFFFFFu, act);
+  while (todo) {  // warp-uniform
+    const int leader = __ffs(todo) - 1;
+    const u32 rl = __shfl_sync(0xFFFFFFFFu, r, leader);
+    const bool mine = act && r == rl;
+    const u32 m = __ballot_sync(0xFFFFFFFFu, mine);
+    const u32 lo = __reduce_min_sync(0xFFFFFFFFu, mine ? s : 0xFFFFFFFFu);
+    const u32 hi = __reduce_max_sync(0xFFFFFFFFu, mine ? s : 0u);
+    if (lane == leader) {
+      atomicAdd(&cnt[rl], (u32)__popc(m));
+      atomicMin(&mn[rl], lo);
+      atomicMax(&mx[rl], hi);
+    }
+    todo &= ~m;
+  }
 }
 __global__ void __launch_bounds__(256) k_iv_write(const u32* __restrict__ excl, const u32* __restrict__ cnt, u64 ng,
                                                   const u32* __restrict__ grp_contig, const u32* __restrict__ mn,
@@ -113,7 +130,7 @@ extern "C" int gvs_components_local(gvs_ctx* ctx, int accumulate, uint32_t** par
   if (!ctx->val_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_components_local before gvs_validate");
   if (!ctx->groups_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_components_local: no group index");
   CK(cudaSetDevice(ctx->device));
-  StageTimer tm(ctx, GVS_ST_INTERVALS);
+  StageTimer tm(ctx, GVS_ST_COMPONENTS);
   CKR(ensure_forest(ctx, !accumulate));
   u64 n = ctx->n_pairs;
   if (n > 1)
@@ -131,7 +148,7 @@ extern "C" int gvs_components_merge_all(gvs_ctx* ctx, const uint32_t* gathered_d
   if (!ctx || !gathered_dev) return GVS_E_ARG;
   if (!ctx->comp_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_components_merge_all before gvs_components_local");
   CK(cudaSetDevice(ctx->device));
-  StageTimer tm(ctx, GVS_ST_INTERVALS);
+  StageTimer tm(ctx, GVS_ST_MERGE);
   u64 ng = ctx->n_groups;
   if (ng && n_ranks > 1)
     LAUNCH(k_comp_merge_all, (unsigned)cdiv(ng, 256), 256, 0, gathered_dev, n_ranks, own_rank, ng, ctx->parent.as<u32>(), ctx->present.as<u8>());
@@ -143,6 +160,7 @@ extern "C" int gvs_components_merge(gvs_ctx* ctx, const uint32_t* peer_parent_de
   if (!ctx || !peer_parent_dev) return GVS_E_ARG;
   if (!ctx->comp_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_components_merge before gvs_components_local");
   CK(cudaSetDevice(ctx->device));
+  StageTimer tm(ctx, GVS_ST_MERGE);
   u64 ng = ctx->n_groups;
   if (ng) LAUNCH(k_comp_merge, (unsigned)cdiv(ng, 256), 256, 0, peer_parent_dev, ng, ctx->parent.as<u32>(), ctx->present.as<u8>());
   ctx->iv_ready = false;

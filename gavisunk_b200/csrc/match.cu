@@ -20,13 +20,16 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out);  // probe.
 __global__ void __launch_bounds__(128) k_gather_hits(const u32* __restrict__ warp_cnt, const u64* __restrict__ warp_dst, u64 cap_w,
                                                      const u32* __restrict__ a0, const u32* __restrict__ a1,
                                                      const u32* __restrict__ a2, const u32* __restrict__ a3,
-                                                     const u8* __restrict__ a4, u32* b0, u32* b1, u32* b2, u32* b3, u8* b4) {
+                                                     const u8* __restrict__ a4, u32* b0, u32* b1, u32* b2, u32* b3, u8* b4,
+                                                     const u64* __restrict__ read_off) {
   const u64 w = blockIdx.x;
   const u32 c = warp_cnt[w];
   const u64 s = w * cap_w, d = warp_dst[w];
   for (u32 i = threadIdx.x; i < c; i += blockDim.x) {
-    b0[d + i] = a0[s + i];
-    b1[d + i] = a1[s + i];
+    const u32 rd = a0[s + i];
+    b0[d + i] = rd;
+    // the probe leaves the low word of the hit's batch position: window = position - start of its read (mod 2^32)
+    b1[d + i] = a1[s + i] - (u32)read_off[rd];
     b2[d + i] = a2[s + i];
     b3[d + i] = a3[s + i];
     b4[d + i] = a4[s + i];
@@ -282,7 +285,8 @@ extern "C" int gvs_match(gvs_ctx* ctx, uint64_t* n_rows_out) {
     CKR(gvs_reserve(ctx, ctx->ohit_nf, nh));
     LAUNCH(k_gather_hits, (unsigned)n_warps, 128, 0, ctx->tile_cnt.as<u32>(), ctx->tile_dst.as<u64>(), cap_w, ctx->hit_read.as<u32>(),
            ctx->hit_w.as<u32>(), ctx->hit_row.as<u32>(), ctx->hit_gidx.as<u32>(), ctx->hit_nf.as<u8>(), ctx->ohit_read.as<u32>(),
-           ctx->ohit_w.as<u32>(), ctx->ohit_row.as<u32>(), ctx->ohit_gidx.as<u32>(), ctx->ohit_nf.as<u8>());
+           ctx->ohit_w.as<u32>(), ctx->ohit_row.as<u32>(), ctx->ohit_gidx.as<u32>(), ctx->ohit_nf.as<u8>(),
+           ctx->read_off);
   }
   // ---- suppression + position drift ----
   CKR(gvs_reserve(ctx, ctx->flags_a, nh));          // u8 flags

@@ -28,7 +28,12 @@
 #include <stdlib.h>
 #include <vector>
 
+#ifndef PW_WARPS
 #define PW_WARPS 8     // warps per block
+#endif
+#ifndef PW_BLOCKS
+#define PW_BLOCKS 4    // resident blocks per SM (PW_WARPS * PW_BLOCKS warps of 65536 / (32 * PW_WARPS * PW_BLOCKS) registers per thread)
+#endif
 #define PW_TILE 512    // window starts per warp tile
 static_assert(PW_TILE == GVS_TILE_BASES, "ctx.cu sizes the copy segments in probe tiles");
 #define PW_RING 64     // packed words in the ring: two tile slots of 32 words (16 bases each)
@@ -169,14 +174,16 @@ __device__ __forceinline__ u64 p_policy_keep() {
 }
 __device__ __forceinline__ uint4 p_ldg_v4(const uint4* ptr, u64 pol) {
   uint4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+  // .L2::64B: a sector miss fills 64 bytes of the line instead of all 128 (profiles/microbench/fetch_granularity.cu:
+  // 61 instead of 118 bytes of DRAM traffic per random 16-byte read, at the same 40 G reads/s)
+  asm volatile("ld.global.nc.L2::cache_hint.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(ptr), "l"(pol));
   return v;
 }
 __device__ __forceinline__ u32 p_ldg_u32(const u32* ptr, u64 pol) {
   u32 v;
-  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.L2::64B.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
   return v;
 }
 
@@ -286,7 +293,7 @@ __device__ __forceinline__ void p_stage_finish(WarpSmem& sm, u32 rb, u64 tile, u
 // SMALL: the blocked filter is L2-resident (<= 32 MiB): few groups pass the presence gate, one window round
 // is the rule and gets a path without the multi-round bookkeeping
 template <int K, bool PACKED, bool SMALL>
-__global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params P) {
+__global__ void __launch_bounds__(PW_WARPS * 32, PW_BLOCKS) k_probe2(const Probe2Params P) {
   __shared__ WarpSmem sm_all[PW_WARPS];
   const int lane = threadIdx.x & 31;
   WarpSmem& sm = sm_all[threadIdx.x >> 5];
@@ -497,7 +504,9 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
           const u32 after = lane == 31 ? 0u : ~((2u << lane) - 1);                    // lanes above this one
           const u64 o = region * P.cap_w + wcount + __popc(hb & ((1u << lane) - 1));
           P.hit_read[o] = rd;
-          P.hit_w[o] = (u32)(ts + pp - __ldg(P.read_off + rd));
+          // low word of the hit's batch position: the gather pass (match.cu) subtracts the read's start, so that no
+          // dependent load of read_off[rd] sits on the warp's path
+          P.hit_w[o] = (u32)(ts + pp);
           P.hit_row[o] = row;
           P.hit_gidx[o] = gi;
           P.hit_nf[o] = (u8)__popc(bal & upto & after);
@@ -542,7 +551,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
             const u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
                           __funnelshift_r(b4.w, 0u, h >> 15);
             if (valid && (t & 1u)) {
-              row = tab_lookup(P.tab, canon, gvs_mix(canon), &gi);
+              row = tab_lookup_spec(P.tab, canon, gvs_mix(canon), &gi);
               if (row == GVS_ROW_MISSING) {
                 atomicOr(P.flags, FLAG_KEYERROR);
                 row = GVS_NOHIT;
@@ -675,7 +684,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
             u32 e = sm.q_p[base + lane];
             pp = e & 0x7FFFu;
             u64 canon = p_canon_at<K>(sm, rb, pp, (e >> 15) != 0);
-            row = tab_lookup(P.tab, canon, gvs_mix(canon), &gi);
+            row = tab_lookup_spec(P.tab, canon, gvs_mix(canon), &gi);
             if (row == GVS_ROW_MISSING) {
               atomicOr(P.flags, FLAG_KEYERROR);
               row = GVS_NOHIT;
@@ -699,8 +708,13 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) k_probe2(const Probe2Params 
 typedef void (*probe_fn)(const Probe2Params);
 static probe_fn probe_table(int k, bool packed, bool small) {
   switch (k) {
+#ifdef GVS_PROBE_ONLY_K  // experiment builds: one SUNK_len, seconds instead of minutes
+#define PK(n) case n: if (n != GVS_PROBE_ONLY_K) return nullptr; return packed ? (small ? k_probe2<GVS_PROBE_ONLY_K, true, true> : k_probe2<GVS_PROBE_ONLY_K, true, false>) \
+                                    : (small ? k_probe2<GVS_PROBE_ONLY_K, false, true> : k_probe2<GVS_PROBE_ONLY_K, false, false>);
+#else
 #define PK(n) case n: return packed ? (small ? k_probe2<n, true, true> : k_probe2<n, true, false>) \
                                     : (small ? k_probe2<n, false, true> : k_probe2<n, false, false>);
+#endif
     PK(1) PK(2) PK(3) PK(4) PK(5) PK(6) PK(7) PK(8) PK(9) PK(10) PK(11) PK(12) PK(13) PK(14) PK(15) PK(16)
     PK(17) PK(18) PK(19) PK(20) PK(21) PK(22) PK(23) PK(24) PK(25) PK(26) PK(27) PK(28) PK(29) PK(30) PK(31)
 #undef PK
@@ -728,7 +742,7 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   std::vector<Seg> plan;
   const bool piped = !ctx->seg_tile_end.empty() && ctx->seq == ctx->own_seq.as<u8>();
   const u64 n_launch = piped ? ctx->seg_tile_end.size() : 1;
-  const u64 resident_warps = (u64)ctx->n_sm * 4 * PW_WARPS;
+  const u64 resident_warps = (u64)ctx->n_sm * PW_BLOCKS * PW_WARPS;
   u64 spans = 0;
   for (u64 s = 0, t0 = 0; s < n_launch; s++) {
     u64 t1 = piped ? ctx->seg_tile_end[s] : n_tiles;
@@ -738,7 +752,7 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
       if (st > 1024) st = 1024;
       u64 ns = cdiv(t1 - t0, st);
       u64 blocks = cdiv(ns, PW_WARPS);
-      if (blocks > (u64)ctx->n_sm * 4) blocks = (u64)ctx->n_sm * 4;
+      if (blocks > (u64)ctx->n_sm * PW_BLOCKS) blocks = (u64)ctx->n_sm * PW_BLOCKS;
       plan.push_back({t0, t1, spans, s, (u32)st, (u32)ns, (u32)blocks});
       spans += ns;
     }

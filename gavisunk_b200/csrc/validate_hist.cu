@@ -114,7 +114,7 @@ extern "C" int gvs_hist_mode(gvs_ctx* ctx, int64_t mode[2]) {
   if (!ctx->hist_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_hist_mode before gvs_group_hist");
   if (ctx->contig_hap.cap == 0) return gvs_fail(ctx, GVS_E_STATE, "gvs_hist_mode: contig haplotypes unknown (gvs_contigs_set)");
   CK(cudaSetDevice(ctx->device));
-  StageTimer tm(ctx, GVS_ST_HIST);
+  StageTimer tm(ctx, GVS_ST_MODE);
   u64 ng = ctx->n_groups;
   mode[0] = mode[1] = 0;
   if (ng == 0) return 0;
@@ -144,7 +144,7 @@ extern "C" int gvs_bad_groups(gvs_ctx* ctx, const int64_t limit_floor[2], uint64
   if (!ctx || !limit_floor) return GVS_E_ARG;
   if (!ctx->hist_ready) return gvs_fail(ctx, GVS_E_STATE, "gvs_bad_groups before gvs_group_hist");
   CK(cudaSetDevice(ctx->device));
-  StageTimer tm(ctx, GVS_ST_HIST);
+  StageTimer tm(ctx, GVS_ST_BAD);
   u64 ng = ctx->n_groups;
   CKR(gvs_reserve(ctx, ctx->bad_flag, ng ? ng : 1));
   CKR(gvs_reserve(ctx, ctx->bad_list, (ng ? ng : 1) * 4));

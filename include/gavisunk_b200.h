@@ -48,11 +48,15 @@ enum {
   GVS_ST_PROBE = 0,     /* read scan / probe kernel (kmerpos_annot3.nim:85-96 inner loop)         */
   GVS_ST_EMIT = 1,      /* hit ordering + consecutive-group suppression                           */
   GVS_ST_DIAG = 2,      /* diag_filter_v3 + diag_filter_step2                                     */
-  GVS_ST_HIST = 3,      /* badsunks_AR.py histogram + mode                                        */
+  GVS_ST_HIST = 3,      /* badsunks_AR.py histogram (gvs_group_hist)                              */
   GVS_ST_VALIDATE = 4,  /* process-by-contig per-read validation                                  */
-  GVS_ST_INTERVALS = 5, /* contig-wide components + intervals + gaps                              */
+  GVS_ST_INTERVALS = 5, /* components -> intervals (gvs_intervals), gaps (gvs_gaps): the last call */
   GVS_ST_DBBUILD = 6,
-  GVS_ST_COUNT = 8
+  GVS_ST_COMPONENTS = 7, /* local forest of the validated pairs (gvs_components_local)             */
+  GVS_ST_MODE = 8,      /* badsunks_AR.py mode per haplotype (gvs_hist_mode)                      */
+  GVS_ST_BAD = 9,       /* bad SUNK groups (gvs_bad_groups)                                       */
+  GVS_ST_MERGE = 10,    /* union with the peers' forests (gvs_components_merge / _merge_all)      */
+  GVS_ST_COUNT = 12
 };
 
 /* ------------------------------------------------------------------------------------------ */
