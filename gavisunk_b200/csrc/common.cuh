@@ -65,7 +65,7 @@ struct gvs_ctx {
   DevBuf loc_kmer, loc_contig, loc_start, loc_group, loc_gidx;  // per .loc row
   DevBuf loc_pack;                                               // per .loc row: (contig, start, group, 0) in one 16-byte word for the emit pass
   DevBuf grp_contig, grp_start;                                  // per group (index = gidx)
-  DevBuf tab_keys, tab_rows, tab_gidx;                           // open-addressed probe table: keys, (build only) rows, (group index << 32 | row)
+  DevBuf tab_keys, tab_rows, tab_kv;                             // open-addressed probe table: (build only) keys and rows; buckets of 4 keys + 4 (group index << 32 | row) words
   u64 tab_slots = 0;                                             // power of two, buckets of 4
   DevBuf filt;                                                   // 32-bit-word blocked Bloom filter
   u64 filt_words = 0;                                            // number of 16-byte blocks, power of two

@@ -166,7 +166,7 @@ extern "C" void gvs_destroy(gvs_ctx* c) {
   }
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->own_words, &c->loc_pack, &c->loc_kmer, &c->loc_contig, &c->loc_start, &c->loc_group, &c->loc_gidx, &c->grp_contig,
-                   &c->grp_start, &c->tab_keys, &c->tab_rows, &c->tab_gidx, &c->hit_gidx, &c->hit_nf, &c->ohit_gidx, &c->ohit_nf, &c->filt, &c->filt1, &c->contig_hap, &c->contig_hash,
+                   &c->grp_start, &c->tab_keys, &c->tab_rows, &c->tab_kv, &c->hit_gidx, &c->hit_nf, &c->ohit_gidx, &c->ohit_nf, &c->filt, &c->filt1, &c->contig_hap, &c->contig_hash,
                    &c->contig_len, &c->own_seq, &c->own_off, &c->chunk_first, &c->chunk_hap, &c->tile_first,
                    &c->tile_cnt, &c->tile_off, &c->tile_dst, &c->hit_read, &c->hit_w, &c->hit_row, &c->ohit_read,
                    &c->ohit_w, &c->ohit_row, &c->counters, &c->scan_tmp, &c->scan_tmp2, &c->flags_a, &c->flags_b,

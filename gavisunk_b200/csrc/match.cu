@@ -158,8 +158,7 @@ static int match_k32(gvs_ctx* ctx, u64* n_hits) {
   v.read_off = ctx->read_off;
   v.n_reads = ctx->n_reads;
   v.total = ctx->total_bases;
-  v.tab.keys = ctx->tab_keys.as<u64>();
-  v.tab.val = ctx->tab_gidx.as<u64>();
+  v.tab.kv = ctx->tab_kv.as<u64>();
   v.tab.slots = ctx->tab_slots;
   v.flags = (u32*)(counters + 1);
   // the segments of a pipelined host batch must have landed (gvs_probe_launch waits per segment)

@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, PW_BLOCKS) k_probe2(const Probe
             const u32 t = __funnelshift_r(b4.x, 0u, h) & __funnelshift_r(b4.y, 0u, h >> 5) & __funnelshift_r(b4.z, 0u, h >> 10) &
                           __funnelshift_r(b4.w, 0u, h >> 15);
             if (valid && (t & 1u)) {
-              row = tab_lookup_spec(P.tab, canon, gvs_mix(canon), &gi);
+              row = tab_lookup(P.tab, canon, gvs_mix(canon), &gi);
               if (row == GVS_ROW_MISSING) {
                 atomicOr(P.flags, FLAG_KEYERROR);
                 row = GVS_NOHIT;
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32, PW_BLOCKS) k_probe2(const Probe
             u32 e = sm.q_p[base + lane];
             pp = e & 0x7FFFu;
             u64 canon = p_canon_at<K>(sm, rb, pp, (e >> 15) != 0);
-            row = tab_lookup_spec(P.tab, canon, gvs_mix(canon), &gi);
+            row = tab_lookup(P.tab, canon, gvs_mix(canon), &gi);
             if (row == GVS_ROW_MISSING) {
               atomicOr(P.flags, FLAG_KEYERROR);
               row = GVS_NOHIT;
@@ -772,8 +772,7 @@ int gvs_probe_launch(gvs_ctx* ctx, u64* n_warps_out, u64* cap_w_out) {
   P.filt1 = ctx->filt1.as<u32>();
   P.filt1_words = (u32)ctx->filt1_words;
   P.blk_stream = ctx->filt_words * 16 > (32ull << 20) ? 1u : 0u;
-  P.tab.keys = ctx->tab_keys.as<u64>();
-  P.tab.val = ctx->tab_gidx.as<u64>();
+  P.tab.kv = ctx->tab_kv.as<u64>();
   P.tab.slots = ctx->tab_slots;
   P.hit_read = ctx->hit_read.as<u32>();
   P.hit_w = ctx->hit_w.as<u32>();

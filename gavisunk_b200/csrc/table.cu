@@ -153,18 +153,21 @@ __global__ void k_loc_pack(const u32* __restrict__ contig, const u32* __restrict
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
     out[i] = make_uint4(contig[i], start[i], group[i], 0u);
 }
-__global__ void k_tab_gidx(const u32* __restrict__ rows, u64 slots, const u32* __restrict__ loc_gidx, u64 n_loc, u64* val) {
+__global__ void k_tab_kv(const u64* __restrict__ keys, const u32* __restrict__ rows, u64 slots, const u32* __restrict__ loc_gidx, u64 n_loc,
+                         u64* kv) {
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
-    u32 r = rows[s];
-    val[s] = ((u64)(r < n_loc ? loc_gidx[r] : 0xFFFFFFFFu) << 32) | r;
+    const u32 r = rows[s];
+    const u64 o = ((s >> 2) << 3) + (s & 3);  // bucket * 8 + slot: keys; + 4: values
+    kv[o] = keys[s];
+    kv[o + 4] = ((u64)(r < n_loc ? loc_gidx[r] : 0xFFFFFFFFu) << 32) | r;
   }
 }
-// (row, group index) of every slot in one 8-byte word, so that the probe learns both with one load;
-// the 4-byte row array of the build is released
+// the probe's table: every bucket's 4 keys and 4 (row, group index) words in one 64-byte unit, so that a lookup is a
+// single access to HBM; the key and row arrays of the build are released
 int gvs_tab_attach_gidx(gvs_ctx* ctx) {
-  CKR(gvs_reserve(ctx, ctx->tab_gidx, ctx->tab_slots * sizeof(u64)));
-  LAUNCH(k_tab_gidx, grid_for(ctx, ctx->tab_slots, 256), 256, 0, ctx->tab_rows.as<u32>(), ctx->tab_slots, ctx->loc_gidx.as<u32>(),
-         ctx->n_loc, ctx->tab_gidx.as<u64>());
+  CKR(gvs_reserve(ctx, ctx->tab_kv, ctx->tab_slots * 2 * sizeof(u64)));
+  LAUNCH(k_tab_kv, grid_for(ctx, ctx->tab_slots, 256), 256, 0, ctx->tab_keys.as<u64>(), ctx->tab_rows.as<u32>(), ctx->tab_slots,
+         ctx->loc_gidx.as<u32>(), ctx->n_loc, ctx->tab_kv.as<u64>());
   // the emit pass turns a hit's .loc row into (contig, start, group): one 16-byte load instead of three scattered 4-byte ones
   CKR(gvs_reserve(ctx, ctx->loc_pack, (ctx->n_loc ? ctx->n_loc : 1) * sizeof(uint4)));
   if (ctx->n_loc)
@@ -172,6 +175,7 @@ int gvs_tab_attach_gidx(gvs_ctx* ctx) {
            ctx->n_loc, ctx->loc_pack.as<uint4>());
   CK(cudaStreamSynchronize(ctx->stream));
   gvs_release(ctx->tab_rows);
+  gvs_release(ctx->tab_keys);
   return 0;
 }
 
