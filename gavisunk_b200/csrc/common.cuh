@@ -121,6 +121,7 @@ struct gvs_ctx {
   DevBuf ohit_read, ohit_w, ohit_row, ohit_gidx, ohit_nf;  // dense, position order
   u64 hit_cap = 0, n_hits = 0;
   DevBuf counters;                     // small block of device counters / flags
+  void* mailbox = nullptr;             // 256 page-locked bytes: where read_dev() lands the scalars the host needs (sizes, flags)
   DevBuf scan_tmp, scan_tmp2, flags_a, flags_b, flags_c;
   Rows rows;                           // gvs_match output
   bool match_ready = false;
@@ -473,6 +474,12 @@ static int device_scan(gvs_ctx* ctx, u64 n, F f, G g, Op op, T* total_dev) {
 // small helpers to read device scalars (synchronises the stream)
 template <typename T>
 static int read_dev(gvs_ctx* ctx, const T* d, T* h, size_t n = 1) {
+  if (ctx->mailbox && n * sizeof(T) <= 256) {  // page-locked landing zone: the copy is a plain DMA, no staging by the driver
+    CK(cudaMemcpyAsync(ctx->mailbox, d, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(h, ctx->mailbox, n * sizeof(T));
+    return 0;
+  }
   CK(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;

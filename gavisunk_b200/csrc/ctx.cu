@@ -144,6 +144,7 @@ extern "C" gvs_ctx* gvs_create(int device, int k) {
     delete c;
     return nullptr;
   }
+  if (cudaHostAlloc(&c->mailbox, 256, cudaHostAllocDefault) != cudaSuccess) c->mailbox = nullptr;  // (read_dev falls back to pageable copies)
   return c;
 }
 
@@ -199,6 +200,7 @@ extern "C" void gvs_destroy(gvs_ctx* c) {
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);
   }
+  if (c->mailbox) cudaFreeHost(c->mailbox);
   delete c;
 }
 

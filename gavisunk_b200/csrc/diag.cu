@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(256) k_row_first(const u32* __restrict__ conti
   u32 s = row_seg[j];
   u32 a = seg_start[s], b = seg_start[s + 1];
   u32 c = contig[j];
-  for (u32 i = a; i < (u32)j; i++)
+  // (a read's rows come in long runs of one contig: the row before almost always settles it)
+  if ((u32)j > a && contig[j - 1] == c) { row_cnt[j] = 0; return; }
+  for (u32 i = a; i + 1 < (u32)j; i++)
     if (contig[i] == c) { row_cnt[j] = 0; return; }
   u32 cnt = 1;
   for (u32 i = (u32)j + 1; i < b; i++) cnt += contig[i] == c;
@@ -601,9 +603,9 @@ static int diag_impl(gvs_ctx* ctx, u64* n_best_out, u64* n_kept_out) {
     auto g = [be] __device__(u64 s, u32 ex, u32 v) { be[s] = ex; };
     CKR((device_scan<u32>(ctx, n_seg, f, g, OpSum(), bt)));
   }
-  u32 n_kept = 0, n_best = 0;
-  CKR(read_dev(ctx, kt, &n_kept));
-  CKR(read_dev(ctx, bt, &n_best));
+  u64 kb[2] = {0, 0};  // counters 13 and 14: one read-back for both totals
+  CKR(read_dev(ctx, ctx->counters.as<u64>() + 13, kb, 2));
+  const u32 n_kept = (u32)kb[0], n_best = (u32)kb[1];
   CKR(gvs_reserve_rows(ctx, ctx->kept, n_kept));
   CKR(gvs_reserve(ctx, ctx->best_read, (u64)n_best * 4));
   CKR(gvs_reserve(ctx, ctx->best_contig, (u64)n_best * 4));
