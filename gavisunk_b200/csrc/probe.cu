@@ -536,7 +536,9 @@ __global__ void __launch_bounds__(PW_WARPS * 32, PW_BLOCKS) k_probe2(const Probe
         }
         __syncwarp();
         const u32 n_ent = n_grp * J;
-        constexpr int RB = 4;  // rounds whose block loads are issued back to back before any window math
+        // (2, not more: a tile seldom queues more than 32 groups, and every extra round of loads held in registers
+        // costs the whole kernel -- measured 24.3 ms with 2 or 1 against 24.6 ms with 4)
+        constexpr int RB = 2;  // rounds whose block loads are issued back to back before any window math
         if (SMALL && n_ent <= 32 && !any_s16) {
           // one round, and the queue order is the position order: test, exact lookup and record output in
           // one go (no candidate bitmap, no second extraction of the k-mer)
