@@ -79,17 +79,21 @@ __global__ void __launch_bounds__(256) k_db_tile_index(const u64* __restrict__ o
 // find-or-insert into the count table: buckets of 4 slots, ANY bucket count (multiply-shift range reduction
 // instead of a mask, so that the table can be sized to the memory that is free rather than to a power of
 // two -- half as many passes over a 6.2 Gbp assembly)
-__device__ __forceinline__ u64 cnt_insert(u64* keys, u64 n_buckets, u64 key, u64 h) {
+// Layout: a bucket is 64 bytes -- its 4 keys followed by their 4 value words -- so that the value update that follows
+// every find-or-insert lands in the line the key access has just brought into L2: one random HBM line per window instead
+// of two (the build is bound by exactly that: a line fill and a write-back per random atomic).
+// Returns the index of the key's VALUE word in kv.
+__device__ __forceinline__ u64 cnt_insert(u64* kv, u64 n_buckets, u64 key, u64 h) {
   u64 b = ((h >> 32) * n_buckets) >> 32;
   for (;;) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      u64 s = (b << 2) + j;
-      u64 cur = keys[s];
-      if (cur == key) return s;
+      u64 s = (b << 3) + j;
+      u64 cur = kv[s];
+      if (cur == key) return s + 4;
       if (cur == GVS_EMPTY_KEY) {
-        u64 old = atomicCAS((unsigned long long*)&keys[s], (unsigned long long)GVS_EMPTY_KEY, (unsigned long long)key);
-        if (old == GVS_EMPTY_KEY || old == key) return s;
+        u64 old = atomicCAS((unsigned long long*)&kv[s], (unsigned long long)GVS_EMPTY_KEY, (unsigned long long)key);
+        if (old == GVS_EMPTY_KEY || old == key) return s + 4;
       }
     }
     b = b + 1 == n_buckets ? 0 : b + 1;
@@ -104,13 +108,15 @@ struct DbCountParams {
   const u32* __restrict__ tile_first;
   u64 n_tiles;
   int k;
-  u64* keys;
-  u64* vals;
+  u64* kv;  // count table: buckets of 4 keys + 4 values (cnt_insert)
   u64 slots;
   u32 n_parts, part;
 };
 
-__global__ void __launch_bounds__(DT, 2) k_db_count(const DbCountParams P) {
+#ifndef DB_BLOCKS
+#define DB_BLOCKS 2  // resident blocks per SM of the count kernel (3 / 4 / 6 measured: 0.76 ... 3.7 s instead of 0.9 s -- CAS storms, erratic)
+#endif
+__global__ void __launch_bounds__(DT, DB_BLOCKS) k_db_count(const DbCountParams P) {
   __shared__ u32 s_bases[DT + 4];
   __shared__ u32 s_inv[(DT + 4) / 2 + 2];  // 16 invalid bits per packed word, two per u32
   __shared__ u32 s_bound[DBW];
@@ -174,9 +180,9 @@ __global__ void __launch_bounds__(DT, 2) k_db_count(const DbCountParams P) {
         u64 c = f < r ? f : r;
         u64 h = gvs_mix(c);
         if (P.n_parts == 1 || (u32)h % P.n_parts == P.part) {  // low hash bits pick the pass, high bits the bucket
-          u64 s = cnt_insert(P.keys, P.slots >> 2, c, h);
-          u64 old = atomicCAS((unsigned long long*)&P.vals[s], (unsigned long long)VAL_EMPTY, (unsigned long long)(p0 + i));
-          if (old != VAL_EMPTY && !(old & VAL_DUP)) atomicOr((unsigned long long*)&P.vals[s], (unsigned long long)VAL_DUP);
+          u64 s = cnt_insert(P.kv, P.slots >> 2, c, h);
+          u64 old = atomicCAS((unsigned long long*)&P.kv[s], (unsigned long long)VAL_EMPTY, (unsigned long long)(p0 + i));
+          if (old != VAL_EMPTY && !(old & VAL_DUP)) atomicOr((unsigned long long*)&P.kv[s], (unsigned long long)VAL_DUP);
         }
       }
     }
@@ -184,11 +190,11 @@ __global__ void __launch_bounds__(DT, 2) k_db_count(const DbCountParams P) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_db_mark(const u64* __restrict__ keys, const u64* __restrict__ vals, u64 slots,
-                                                 u32* bitmap) {
+__global__ void __launch_bounds__(256) k_db_mark(const u64* __restrict__ kv, u64 slots, u32* bitmap) {
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (u64)gridDim.x * blockDim.x) {
-    if (keys[s] == GVS_EMPTY_KEY) continue;
-    u64 v = vals[s];
+    const u64 o = ((s >> 2) << 3) + (s & 3);  // key of slot s; its value sits 4 words on
+    if (kv[o] == GVS_EMPTY_KEY) continue;
+    u64 v = kv[o + 4];
     if (v == VAL_EMPTY || (v & VAL_DUP)) continue;
     atomicOr(&bitmap[v >> 5], 1u << (v & 31));
   }
@@ -294,21 +300,21 @@ static int db_build_device(gvs_ctx* ctx, const u8* seq, const u64* contig_off, u
   }
   if ((slots >> 2) >= (1ull << 32)) return gvs_fail(ctx, GVS_E_OVERFLOW, "SUNK count table has too many buckets");
   if (slots * 16 > budget) return gvs_fail(ctx, GVS_E_NOMEM, "SUNK count table does not fit (%llu slots)", (unsigned long long)slots);
-  CKR(gvs_reserve(ctx, keys, slots * 8));
-  CKR(gvs_reserve(ctx, vals, slots * 8));
+  CKR(gvs_reserve(ctx, keys, slots * 16));  // keys and values, bucket by bucket (cnt_insert)
+  (void)vals;
   CKR(gvs_reserve(ctx, bitmap, n_words * 4));
   CK(cudaMemsetAsync(bitmap.p, 0, n_words * 4, ctx->stream));
   for (u32 part = 0; part < n_parts; part++) {
-    LAUNCH(k_fill64, grid_cap(ctx, slots, 256, 16), 256, 0, keys.as<u64>(), slots, GVS_EMPTY_KEY);
-    LAUNCH(k_fill64, grid_cap(ctx, slots, 256, 16), 256, 0, vals.as<u64>(), slots, VAL_EMPTY);
+    static_assert(GVS_EMPTY_KEY == VAL_EMPTY, "one fill value for keys and values");
+    LAUNCH(k_fill64, grid_cap(ctx, slots * 2, 256, 16), 256, 0, keys.as<u64>(), slots * 2, GVS_EMPTY_KEY);
     DbCountParams P;
     P.seq = seq; P.total = total; P.contig_off = contig_off; P.n_contigs = n_contigs;
     P.tile_first = ctx->tile_first.as<u32>(); P.n_tiles = n_tiles; P.k = k;
-    P.keys = keys.as<u64>(); P.vals = vals.as<u64>(); P.slots = slots; P.n_parts = n_parts; P.part = part;
-    u64 grid = (u64)ctx->n_sm * 2;
+    P.kv = keys.as<u64>(); P.slots = slots; P.n_parts = n_parts; P.part = part;
+    u64 grid = (u64)ctx->n_sm * DB_BLOCKS;
     if (grid > n_tiles) grid = n_tiles;
     LAUNCH(k_db_count, (unsigned)grid, DT, 0, P);
-    LAUNCH(k_db_mark, grid_cap(ctx, slots, 256, 16), 256, 0, keys.as<u64>(), vals.as<u64>(), slots, bitmap.as<u32>());
+    LAUNCH(k_db_mark, grid_cap(ctx, slots, 256, 16), 256, 0, keys.as<u64>(), slots, bitmap.as<u32>());
   }
   // rank of every SUNK
   CKR(gvs_reserve(ctx, wrank, n_words * 4));
