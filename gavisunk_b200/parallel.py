@@ -114,22 +114,36 @@ class Exchange:
         if self.world == 1 or parent.numel() == 0:
             return []
         n = parent.numel()
-        buf = torch.empty(self.world * n, dtype=parent.dtype, device=parent.device)
+        buf = getattr(self, "_keep", None)  # one gather buffer per run shape, reused (a rank pays this once per run)
+        if buf is None or buf.numel() != self.world * n or buf.dtype != parent.dtype or buf.device != parent.device:
+            buf = torch.empty(self.world * n, dtype=parent.dtype, device=parent.device)
         self.dist.all_gather_into_tensor(buf, parent, group=self.group) if parent.is_cuda else \
             self.dist.all_gather(list(buf.view(self.world, n).unbind(0)), parent, group=self.group)
         self._keep = buf
         return [buf[r * n:(r + 1) * n] for r in range(self.world) if r != self.rank]
 
 
+_ALIASES: dict = {}
+
+
 def alias_device_array(ptr: int, n: int, typestr: str, device):
-    """torch tensor over a raw device pointer owned by libgavisunk_b200.so (CUDA array interface)"""
+    """torch tensor over a raw device pointer owned by libgavisunk_b200.so (CUDA array interface); the wrapper of a
+    given (pointer, length) is built once -- the library's histogram / forest buffers keep their place from run to run"""
     import torch
+    key = (int(ptr), int(n), typestr, str(device))
+    t = _ALIASES.get(key)
+    if t is not None:
+        return t
+    if len(_ALIASES) > 64:
+        _ALIASES.clear()
 
     class _A:
         pass
     a = _A()
     a.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(ptr, False), version=2)
-    return torch.as_tensor(a, device=device)
+    t = torch.as_tensor(a, device=device)
+    _ALIASES[key] = t
+    return t
 
 
 class EngineExchange:
