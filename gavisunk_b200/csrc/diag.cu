@@ -285,16 +285,49 @@ __global__ void __launch_bounds__(NT) k_cand_vote(const u32* __restrict__ cand_r
           s_ahi = is_up ? val(hi) : val(cnt - 1 - hi);
         }
       } else {
+        // Elements of rank lo and lo + 1 by bisection on the value (~30 counting passes over the candidate's rows)
+        // instead of ranking every row against every other: these candidates have hundreds to thousands of rows.
+        i64 mn = 0x7FFFFFFFFFFFFFFFll, mx = -0x7FFFFFFFFFFFFFFFll - 1;
         for (u32 i = tid; i < cnt; i += NT) {
-          const i64 ni = val(i);
-          u32 rank = 0;
-          for (u32 j = 0; j < cnt; j++) {
-            const i64 nj = val(j);
-            rank += (nj < ni) || (nj == ni && j < i);
-          }
-          if (rank == lo) s_alo = ni;
-          if (rank == lo + 1) s_ahi = ni;
+          const i64 v = val(i);
+          mn = v < mn ? v : mn;
+          mx = v > mx ? v : mx;
         }
+        if (tid == 0) { s_alo = 0x7FFFFFFFFFFFFFFFll; s_ahi = -0x7FFFFFFFFFFFFFFFll - 1; }
+        __syncthreads();
+        atomicMin((long long*)&s_alo, (long long)mn);
+        atomicMax((long long*)&s_ahi, (long long)mx);
+        __syncthreads();
+        i64 vlo = s_alo, vhi = s_ahi;  // the value of rank lo lies in [vlo, vhi]
+        __syncthreads();
+        auto count_le = [&](i64 x) -> u32 {  // rows with value <= x (block-uniform result)
+          u32 c = 0;
+          for (u32 base = 0; base < cnt; base += NT) {
+            const u32 i = base + tid;
+            c += (u32)__syncthreads_count(i < cnt && val(i) <= x);
+          }
+          return c;
+        };
+        while (vlo < vhi) {
+          const i64 mid = vlo + (i64)(((u64)vhi - (u64)vlo) >> 1);
+          if (count_le(mid) >= lo + 1) vhi = mid; else vlo = mid + 1;
+        }
+        // rank lo + 1: the same value if it occurs often enough, else the smallest larger one
+        i64 nxt = vlo;
+        if (count_le(vlo) < lo + 2) {
+          i64 best = 0x7FFFFFFFFFFFFFFFll;
+          for (u32 i = tid; i < cnt; i += NT) {
+            const i64 v = val(i);
+            if (v > vlo && v < best) best = v;
+          }
+          if (tid == 0) s_ahi = 0x7FFFFFFFFFFFFFFFll;
+          __syncthreads();
+          atomicMin((long long*)&s_ahi, (long long)best);
+          __syncthreads();
+          nxt = s_ahi;  // (only used when cnt is even, i.e. when rank lo + 1 exists)
+          __syncthreads();
+        }
+        if (tid == 0) { s_alo = vlo; s_ahi = nxt; }
       }
       __syncthreads();
       // arraymancer percentile(n, 50): linear interpolation in float64, then int() truncation
