@@ -163,7 +163,52 @@ __global__ void __launch_bounds__(VOTE_WARPS * 32) k_cand_vote_warp(const u32* _
     if (sorted0) { s_med[grp][0] = up0 ? n0[lo] : n0[cnt - 1 - lo]; s_med[grp][1] = up0 ? n0[hi] : n0[cnt - 1 - hi]; }
     if (sorted1) { s_med[grp][2] = up1 ? n1[lo] : n1[cnt - 1 - lo]; s_med[grp][3] = up1 ? n1[hi] : n1[cnt - 1 - hi]; }
   }
-  if (!sorted0 || !sorted1) {
+  // Unsorted diagonal of a larger candidate: elements of rank lo and lo + 1 by bisection on the value (one counting pass
+  // per bit of the diagonal's spread) instead of ranking every row against every other
+  auto select2 = [&](const i64* x, i64* out) {
+    i64 mn = 0x7FFFFFFFFFFFFFFFll, mx = -0x7FFFFFFFFFFFFFFFll - 1;
+    for (u32 i = tid; i < cnt; i += 32) {
+      const i64 v = x[i];
+      mn = v < mn ? v : mn;
+      mx = v > mx ? v : mx;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      const i64 a = __shfl_xor_sync(0xFFFFFFFFu, mn, d), b = __shfl_xor_sync(0xFFFFFFFFu, mx, d);
+      mn = a < mn ? a : mn;
+      mx = b > mx ? b : mx;
+    }
+    auto count_le = [&](i64 v) -> u32 {
+      u32 c = 0;
+      for (u32 i = tid; i < cnt; i += 32) c += x[i] <= v;
+      return __reduce_add_sync(0xFFFFFFFFu, c);
+    };
+    i64 vlo = mn, vhi = mx;
+    while (vlo < vhi) {  // warp-uniform
+      const i64 mid = vlo + (i64)(((u64)vhi - (u64)vlo) >> 1);
+      if (count_le(mid) >= lo + 1) vhi = mid; else vlo = mid + 1;
+    }
+    i64 nxt = vlo;
+    if (count_le(vlo) < lo + 2) {  // rank lo + 1 is the smallest larger value
+      i64 best = 0x7FFFFFFFFFFFFFFFll;
+      for (u32 i = tid; i < cnt; i += 32) {
+        const i64 v = x[i];
+        if (v > vlo && v < best) best = v;
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        const i64 a = __shfl_xor_sync(0xFFFFFFFFu, best, d);
+        best = a < best ? a : best;
+      }
+      nxt = best;
+    }
+    if (tid == 0) { out[0] = vlo; out[1] = nxt; }
+  };
+  const bool bisect = cnt > 48;
+  if (bisect) {
+    if (!sorted0) select2(n0, &s_med[grp][0]);
+    if (!sorted1) select2(n1, &s_med[grp][2]);
+  } else if (!sorted0 || !sorted1) {
     for (u32 i = tid; i < cnt; i += 32) {
       const i64 a0 = n0[i], a1 = n1[i];
       u32 r0 = 0, r1 = 0;
