@@ -45,3 +45,13 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, fn)).read()
                 assert "gavisunk_oracle" not in src and "oracle/" not in src, fn
+
+
+def test_stage_ids_match_header():
+    """gavisunk_b200._lib.STAGES (names used by Engine.stage_ms and bench.py) are the header's GVS_ST_* ids"""
+    from gavisunk_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "gavisunk_b200.h")).read()
+    ids = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"\bGVS_ST_([A-Z]+)\s*=\s*(\d+)", txt)}
+    count = ids.pop("count")
+    assert ids == _lib.STAGES
+    assert max(ids.values()) < count
