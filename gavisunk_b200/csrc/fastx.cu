@@ -701,7 +701,24 @@ extern "C" int gvs_fastx_read_packed(const char* const* paths, uint32_t n_files,
         if (base[i + 1] == base[i]) continue;
         const u64 g0 = base[i] / 16, g1 = (base[i + 1] - 1) / 16;  // first / last global word the file touches
         const u32 sh = (u32)(base[i] % 16);
-        for (u64 g = g0 + 1; g < g1; g++) R->words[g] = shifted_word(files[i].words, (i64)(g - g0), sh);
+        // interior words: both local words exist, no bounds to check (a vectorisable shift / a plain copy); the few
+        // words left over at the file's end take the checked path
+        const std::vector<u32>& loc = files[i].words;
+        const u64 nl = loc.size();
+        const u64 jmax = g1 - g0 < nl ? g1 - g0 : nl;  // j in [1, jmax): loc[j - 1] and loc[j] exist
+        u64 g = g0 + 1;
+        if (jmax > 1) {
+          const u32* L = loc.data();
+          u32* W = R->words + g0;
+          if (sh == 0) {
+            memcpy(W + 1, L + 1, (size_t)(jmax - 1) * 4);
+          } else {
+            const u32 ls = 32 - 2 * sh, rs = 2 * sh;
+            for (u64 j = 1; j < jmax; j++) W[j] = (L[j - 1] << ls) | (L[j] >> rs);
+          }
+          g = g0 + jmax;
+        }
+        for (; g < g1; g++) R->words[g] = shifted_word(loc, (i64)(g - g0), sh);
       }
     };
     std::vector<std::thread> pool;
